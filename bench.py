@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""Benchmark of the weak-supervision hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload pairwise|layercam]
+
+Default workload = BASELINE.json configs[1]: AlternatingDirectionCutLoss + BoundaryLoss forward+backward on
+synthetic 32x2x224x224 maps with smooth RGB affinities.  One "step" = one cut-loss fwd+bwd launch + one
+boundary-loss fwd+bwd launch over one batch; the metric counts pixels once per loss (2*B*H*W per step).
+`--workload layercam` runs configs[2] instead (fused LayerCAM->normalise->threshold at 512x512, image-sharded);
+the default run reports it too, under "also".
+
+One JSON line on stdout (rank 0).  Under torchrun every rank processes its own batch (weak scaling, no
+data-path collective); the elapsed time is the max over ranks.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PAIR = dict(B=32, C=2, H=224, W=224, window=5, sigma_cut=0.05, sigma_bnd=0.1, sigma_space=5.0)
+LCAM = dict(S=512, layers=((1024, 32, 32), (2048, 32, 32)), chunk=128, thresh=0.3, alpha=1.0, n_images=3680)
+N_SETS = 8  # rotated input sets: 8 x 45 MB > 126 MB L2
+BYTES_PER_PIX = 28  # 20 B read (2 logits + 3 rgb) + 8 B gradient written, C=2
+L2_MB = 126
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def smooth_images(gen, B, H, W, device):
+    import torch
+
+    raw = torch.rand(B, 3, H + 16, W + 16, generator=gen, device=device)
+    img = torch.nn.functional.avg_pool2d(raw, 9, stride=1)[..., 4:H + 4, 4:W + 4]
+    lo = img.amin(dim=(1, 2, 3), keepdim=True)
+    hi = img.amax(dim=(1, 2, 3), keepdim=True)
+    return ((img - lo) / (hi - lo)).contiguous()
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.ok:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_pairwise_sample(sample_B, reps, threads):
+    """The reference's CPU path for configs[1] (oracle port: same ATen op sequence as
+    AlternatingDirectionCutLoss.py:71-105 / AlternatingDirectionBoundaryLoss.py:20-70 incl. autograd backward)."""
+    import torch
+
+    from oracle import wsdl_oracle as O
+
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(1)
+    H, W = PAIR["H"], PAIR["W"]
+    logits = torch.randn(sample_B, 2, H, W, generator=gen)
+    img = smooth_images(gen, sample_B, H, W, "cpu")
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.loss_and_grad(O.cut_loss, logits, img, sigma_color=PAIR["sigma_cut"], window_size=PAIR["window"])
+        probs = torch.softmax(logits, dim=1)
+        for b in range(sample_B):  # the reference's boundary loss is per image (BoundaryLoss.py:20)
+            O.loss_and_grad(O.boundary_loss, probs[b], img[b], sigma_color=PAIR["sigma_bnd"],
+                            sigma_space=PAIR["sigma_space"], window_size=PAIR["window"])
+        best = min(best, time.perf_counter() - t0)
+    return 2 * sample_B * H * W / best / 1e9, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    threads = os.cpu_count() or 1
+    sample_B = 4
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, t = cpu_pairwise_sample(sample_B, 1, threads)
+        if i >= args.warmup:
+            times.append(t)
+    total = sum(times)
+    pix = 2 * sample_B * PAIR["H"] * PAIR["W"] * len(times)
+    value = pix / total / 1e9
+    line = {
+        "impl": "reference", "metric": "cut+boundary loss fwd+bwd throughput", "value": value, "unit": "Gpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: cut + boundary loss fwd/bwd, 2x224x224 maps, smooth RGB",
+                   "sample": f"{sample_B} of 32 images per step"},
+        "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_B}x2x224x224 per step, oracle port of the reference ATen op sequence "
+                                   f"(torch {torch.__version__} CPU, autograd backward)"},
+        "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from weaklysuperviseddl_b200 import _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _native.lib()
+    stream = torch.cuda.current_stream(dev)
+
+    if args.workload == "layercam":
+        res = bench_layercam(args, lib, dev, rank, world)
+    else:
+        res = bench_pairwise(args, lib, dev, rank, world)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _timed(run_steps, warmup, steps, dev, world, sampler):
+    """W warm-up steps, barrier+sync, EXACTLY `steps` steps between CUDA events, sync+barrier; max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    run_steps(warmup)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+    e0.record()
+    run_steps(steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, clocks
+
+
+def make_pairwise_state(lib, dev, seed):
+    import torch
+
+    B, C, H, W = PAIR["B"], PAIR["C"], PAIR["H"], PAIR["W"]
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    sets = []
+    for _ in range(N_SETS):
+        logits = torch.randn(B, C, H, W, generator=gen, device=dev)
+        img = smooth_images(gen, B, H, W, dev)
+        sets.append((logits, torch.softmax(logits, dim=1), img, torch.empty_like(logits), torch.empty_like(logits)))
+    nws = lib.wsdl_pairwise_workspace_bytes(B, H, W)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    loss_cut = torch.empty(1, device=dev)
+    loss_bnd = torch.empty(B, device=dev)
+    return sets, ws, nws, loss_cut, loss_bnd
+
+
+def bench_pairwise(args, lib, dev, rank, world):
+    import torch
+
+    B, C, H, W = PAIR["B"], PAIR["C"], PAIR["H"], PAIR["W"]
+    sets, ws, nws, loss_cut, loss_bnd = make_pairwise_state(lib, dev, 1 + rank)
+    sp = lambda: torch.cuda.current_stream(dev).cuda_stream
+
+    def one_step(i):
+        logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
+        rc = lib.wsdl_pairwise_fwd_bwd(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_cut"],
+                                       0.0, 1, 1, 0, None, loss_cut.data_ptr(), g_cut.data_ptr(), ws.data_ptr(), nws, sp())
+        _native_check(rc)
+        rc = lib.wsdl_pairwise_fwd_bwd(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_bnd"],
+                                       PAIR["sigma_space"], 0, 0, 1, None, loss_bnd.data_ptr(), g_bnd.data_ptr(),
+                                       ws.data_ptr(), nws, sp())
+        _native_check(rc)
+
+    graph = None
+    if not args.no_graph:
+        for i in range(N_SETS):
+            one_step(i)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(N_SETS):
+                one_step(i)
+
+    def run_steps(n):
+        full, rem = (n // N_SETS, n % N_SETS) if graph is not None else (0, n)
+        for _ in range(full):
+            graph.replay()
+        for i in range(rem):
+            one_step(i)
+
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    ms, clocks = _timed(run_steps, args.warmup, args.steps, dev, world, sampler)
+    if rank == 0 and clocks is not None and ms < 400.0:  # too short for NVML to see: probe the same load, untimed
+        probe = ClockSampler(dev.index)
+        probe.start()
+        t0 = time.time()
+        while time.time() - t0 < 0.6:
+            run_steps(N_SETS * 16)
+            torch.cuda.synchronize(dev)
+        clocks = dict(probe.stop(), note="sampled over an untimed 0.6 s repeat of the same steps (timed region < 0.4 s)")
+    pix_per_step = 2 * B * H * W  # counted once per loss
+    value = world * pix_per_step * args.steps / (ms * 1e-3) / 1e9
+    ms_per_step = ms / args.steps
+    peak, peak_src = peaks()
+    # dominant kernel: pairwise_fwd_bwd_kernel<2,2>, two launches per step and nothing else but two 4-byte memsets
+    launch_ms = ms_per_step / 2.0
+    achieved = BYTES_PER_PIX * B * H * W / (launch_ms * 1e-3) / 1e9
+    res = {
+        "metric": "cut+boundary loss fwd+bwd throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "configs[1]: AlternatingDirectionCutLoss + BoundaryLoss fwd/bwd, 32x2x224x224 per GPU, "
+                        "smooth RGB affinities (SURVEY.md 8d)",
+            "step": "1 cut fwd+bwd launch (logits, sigma 0.05) + 1 boundary fwd+bwd launch (32 images, sigma 0.1/5); "
+                    "pixels counted once per loss",
+            "l2": f"rotating {N_SETS} input sets ({N_SETS * 45} MB) > {L2_MB} MB L2",
+            "launch": "CUDA graph of 8 steps" if graph is not None else "direct C-ABI calls",
+            "sharding": "batch per rank, no data-path collective",
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "pairwise_fwd_bwd_kernel<2,2>",
+                     "algorithmic_bytes_per_launch": BYTES_PER_PIX * B * H * W, "launch_ms": launch_ms,
+                     "peak_source": peak_src,
+                     "note": "launch duration = timed step / 2 launches (CUDA events on the launching stream)"},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+    }
+    e2e = e2e_pairwise(dev, world, max(3, min(50, args.steps)), max(3, min(5, args.warmup)))
+    if rank == 0:
+        res["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, t = cpu_pairwise_sample(8, 2, threads)
+            res["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": threads, "kind": "port",
+                                   "sample": f"8 of 32 images (8x2x224x224), best of 2, {t:.2f} s; oracle port of the "
+                                             "reference ATen op sequence incl. autograd backward"}
+        if world == 1 and not args.no_also:
+            res["also"] = {"layercam_512": bench_layercam_core(lib, dev, 0, 1, 30, 5)}
+    return res
+
+
+def _native_check(rc):
+    if rc != 0:
+        from weaklysuperviseddl_b200 import _native
+
+        _native.check(rc, "wsdl call in bench.py")
+
+
+def e2e_pairwise(dev, world, steps, warmup):
+    """Same metric through the public modules with HOST buffers: H2D of logits+images from pinned memory,
+    LocalNormalizedCutLoss + batched ConstrainToBoundaryLossSingle, backward, D2H of loss and gradient.
+    Every rank runs its own batch concurrently (shared host links included); max time over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    import weaklysuperviseddl_b200 as Wm
+
+    B, C, H, W = PAIR["B"], PAIR["C"], PAIR["H"], PAIR["W"]
+    gen = torch.Generator().manual_seed(1)
+    h_logits = torch.randn(B, C, H, W, generator=gen).pin_memory()
+    h_img = smooth_images(gen, B, H, W, "cpu").pin_memory()
+    h_grad = torch.empty(B, C, H, W).pin_memory()
+    h_loss = torch.empty(1).pin_memory()
+    cut = Wm.LocalNormalizedCutLoss(PAIR["sigma_cut"], PAIR["window"])
+    bnd = Wm.ConstrainToBoundaryLossSingle(PAIR["sigma_bnd"], PAIR["sigma_space"], PAIR["window"])
+
+    def step():
+        logits = h_logits.to(dev, non_blocking=True).requires_grad_(True)
+        img = h_img.to(dev, non_blocking=True)
+        loss = cut(logits, img) + bnd(torch.softmax(logits, dim=1), img).mean()
+        loss.backward()
+        h_grad.copy_(logits.grad, non_blocking=True)
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": world * 2 * B * H * W * steps / (ms * 1e-3) / 1e9, "unit": "Gpix/s",
+            "h2d_bytes_per_step": h_logits.numel() * 4 + h_img.numel() * 4,
+            "d2h_bytes_per_step": h_grad.numel() * 4 + 4, "steps": steps, "ms_per_step": ms / steps,
+            "api": "LocalNormalizedCutLoss()(logits, images) + ConstrainToBoundaryLossSingle()(softmax, images).mean(); "
+                   ".backward(); pinned host buffers"}
+
+
+# ------------------------------------------------------------------------------------------ configs[2]
+def bench_layercam_core(lib, dev, rank, world, steps, warmup):
+    """Fused LayerCAM -> normalise -> upsample -> threshold on a resident chunk of 512x512-sized hooks
+    (1024x32x32 + 2048x32x32 fp32 per image); two rotated chunks (2 x 3.2 GB) defeat the L2."""
+    import torch
+
+    chunk = LCAM["chunk"]
+    S = LCAM["S"]
+    layers = LCAM["layers"]
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sets = []
+    for _ in range(2):
+        acts = [torch.randn(chunk, C, h, w, device=dev, generator=gen).relu_() for (C, h, w) in layers]
+        grads = [torch.randn(chunk, C, h, w, device=dev, generator=gen).mul_(1e-3) for (C, h, w) in layers]
+        sets.append((acts, grads))
+    n = len(layers)
+    IntArr, PtrArr = ctypes.c_int * n, ctypes.c_void_p * n
+    Cs, hs, ws_ = IntArr(*[l[0] for l in layers]), IntArr(*[l[1] for l in layers]), IntArr(*[l[2] for l in layers])
+    nws = lib.wsdl_layercam_workspace_bytes(Cs, hs, ws_, n, chunk, 0)
+    wsb = torch.empty(nws, dtype=torch.uint8, device=dev)
+    mask = torch.empty(chunk, S, S, dtype=torch.uint8, device=dev)
+    near = torch.zeros(1, dtype=torch.int64, device=dev)
+    sp = lambda: torch.cuda.current_stream(dev).cuda_stream
+
+    def one(i):
+        acts, grads = sets[i % 2]
+        rc = lib.wsdl_layercam_fused(PtrArr(*[t.data_ptr() for t in acts]), PtrArr(*[t.data_ptr() for t in grads]),
+                                     Cs, hs, ws_, n, chunk, 0, S, S, LCAM["alpha"], 0, LCAM["thresh"], 1e-6, None,
+                                     mask.data_ptr(), near.data_ptr(), wsb.data_ptr(), nws, sp())
+        _native_check(rc)
+
+    def run_steps(k):
+        for i in range(k):
+            one(i)
+
+    ms, _ = _timed(run_steps, warmup, steps, dev, world, None)
+    per_image = sum(2 * C * h * w * 4 for (C, h, w) in layers) + S * S
+    masks_per_s = world * chunk * steps / (ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = per_image * chunk * steps / (ms * 1e-3) / 1e9
+    return {"metric": "pseudo-masks/s (fused LayerCAM->normalise->threshold, 512x512, layers 3+4 fp32)",
+            "value": masks_per_s, "unit": "masks/s", "gpix_per_s": masks_per_s * S * S / 1e9,
+            "ms_per_step": ms / steps, "images_per_step": chunk, "steps": steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_image": per_image, "peak_source": peak_src,
+                         "note": "both kernels of the call (channel-sum + upsample/threshold) and the ctrl memset"},
+            "time_for_3680_images_ms": LCAM["n_images"] / (masks_per_s / world) * 1e3 / world,
+            "l2": "2 rotated chunks of 3.2 GB"}
+
+
+def bench_layercam(args, lib, dev, rank, world):
+    steps, warmup = args.steps, args.warmup
+    core = bench_layercam_core(lib, dev, rank, world, steps, warmup)
+    return {
+        "metric": "pseudo-masks/s", "value": core["value"], "unit": "masks/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": core["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: fused LayerCAM->normalise->threshold, 512x512, image-sharded; "
+                               f"{LCAM['chunk']} images per step per GPU", "l2": core["l2"]},
+        "roofline": core["roofline"], "gpu_launches": 2 * steps, "extra": core,
+    }
+
+
+if __name__ == "__main__":
+    main()

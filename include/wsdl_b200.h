@@ -1,0 +1,127 @@
+/*
+ * wsdl_b200.h -- C ABI of the B200-native weak-supervision hot path.
+ *
+ * The reference (alexncoleman/WeaklySupervisedDL) has no FFI of its own: its hot
+ * path is a handful of Python callables that dispatch ATen ops.  Each entry point
+ * below replaces the ATen op sequence of one of those callables; the Python
+ * mirror in weaklysuperviseddl_b200/ binds them with ctypes (raw device pointers,
+ * sizes, the current CUDA stream).  Reference paths are relative to
+ * /root/reference/TraditionalModel.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current device unless the name
+ *     ends in _host; tensors are dense NCHW;
+ *   - the caller owns every buffer, including workspaces; the library keeps no
+ *     state, allocates nothing and never synchronises the host;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 ok, <0 argument error (WSDL_E_*), >0 a cudaError_t from
+ *     the launch; wsdl_strerror() renders either.  Nothing throws across the ABI.
+ */
+#ifndef WSDL_B200_H_
+#define WSDL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSDL_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define WSDL_E_NULL (-1)      /* required pointer is NULL */
+#define WSDL_E_SHAPE (-2)     /* bad extent (<=0, too many layers/classes, window even or > 2*min(H,W)-1 ...) */
+#define WSDL_E_ALIGN (-3)     /* pointer not aligned to its element size */
+#define WSDL_E_WORKSPACE (-4) /* workspace too small */
+#define WSDL_E_DTYPE (-5)     /* unknown dtype code */
+#define WSDL_E_ARG (-6)       /* other invalid argument (alpha_mode, sigma<=0 ...) */
+
+#define WSDL_MAX_LAYERS 8  /* LayerCAM target layers per call */
+#define WSDL_MAX_CLASSES 8 /* classes of the pairwise losses */
+
+#define WSDL_F32 0
+#define WSDL_BF16 1
+#define WSDL_F16 2
+
+int wsdl_version(void);
+const char* wsdl_strerror(int rc);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 1+2: LayerCAM -> normalise -> upsample -> fuse -> threshold.
+ * Replaces LayerCAMGenerator.generate's post-backbone part (LayerCAM.py:52-76; variant
+ * AlternatingDirectionCutLoss.py:262-286 with alpha_mode=1) and the threshold idiom
+ * `cam[cam < t] = 0; mask = cam > 0` (PsuedoMasks.py:59-62, LayerCAM.py:103-107).
+ *
+ *   act_host[l], grad_host[l]  device pointers to (B, C[l], h[l], w[l]) of `dtype`
+ *   cam_out   nullable, (B, out_h, out_w) f32      -- what generate() returns
+ *   mask_out  nullable, (B, out_h, out_w) u8 {0,1} -- (cam >= thresh) && (cam > 0)
+ *   near_thresh_count nullable, one u64, INCREMENTED by the number of pixels with
+ *             |cam - thresh| < near_band (north_star's "counted and reported" band)
+ *   alpha_mode 0: mean of layers -> clamp(0) ** alpha           (LayerCAM.py:74-76)
+ *              1: per layer normalise, ** alpha, normalise again (CutLoss.py:271-279)
+ * Two kernels are enqueued (channel-sum+min/max+normalise; upsample+fuse+threshold); the
+ * full-resolution CAM is never written unless cam_out is given.
+ * ------------------------------------------------------------------------------------- */
+size_t wsdl_layercam_workspace_bytes(const int* C_host, const int* h_host, const int* w_host, int n_layers, int B,
+                                     int dtype);
+
+int wsdl_layercam_fused(const void* const* act_host, const void* const* grad_host, const int* C_host,
+                        const int* h_host, const int* w_host, int n_layers, int B, int dtype, int out_h, int out_w,
+                        float alpha, int alpha_mode, float thresh, float near_band, float* cam_out,
+                        uint8_t* mask_out, unsigned long long* near_thresh_count, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Standalone threshold idiom on an existing CAM (LayerCAM.py:103-107, CutLoss.py:529-536):
+ * mask = (cam >= thresh) && (cam > 0), n elements. */
+int wsdl_threshold_mask(const float* cam, size_t n, float thresh, float near_band, uint8_t* mask_out,
+                        unsigned long long* near_thresh_count, void* stream);
+
+/* keep_largest (PsuedoMasks.py:15-21; duplicate AlternatingDirectionCutLoss.py:206-213):
+ * 8-connected components of mask != 0 (skimage.measure.label defaults), keep the largest by area
+ * (ties: the component whose first pixel comes first in raster order, i.e. skimage's lowest label).
+ * mask/out (B,H,W) u8; out gets {0,1}; an empty mask gives an all-zero out (the reference returns
+ * the -- all-zero -- input).  best_area nullable, B u32 (area of the kept component, 0 if none).
+ * out may alias mask. */
+size_t wsdl_keep_largest_workspace_bytes(int B, int H, int W);
+
+int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8_t* out, unsigned* best_area, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Stage 3: pairwise regularisers, forward + backward in one launch.
+ * Replaces LocalNormalizedCutLoss.forward (AlternatingDirectionCutLoss.py:71-105:
+ * inner_softmax=1, sigma_space<=0, divide_by_c=1, per_image_loss=0) and
+ * ConstrainToBoundaryLossSingle.forward (AlternatingDirectionBoundaryLoss.py:20-44:
+ * inner_softmax=0, sigma_space>0, divide_by_c=0, per_image_loss=1, one image per b).
+ *
+ *   values (B,C,H,W) f32 : logits (inner_softmax=1) or probabilities
+ *   images (B,3,H,W) f32
+ *   loss_out  1 float (per_image_loss=0: mean over b,h,w as the reference's .mean())
+ *             or B floats (per_image_loss=1: each image's own mean over h,w)
+ *   grad_values nullable (B,C,H,W): d(sum of loss_out * grad_out)/d values;
+ *             NULL = forward only
+ *   grad_out  nullable device pointer to 1 (or B) upstream gradients; NULL = 1.0
+ * ------------------------------------------------------------------------------------- */
+size_t wsdl_pairwise_workspace_bytes(int B, int H, int W);
+
+int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C, int H, int W, int window,
+                          float sigma_color, float sigma_space, int inner_softmax, int divide_by_c,
+                          int per_image_loss, const float* grad_out, float* loss_out, float* grad_values,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* compute_affinities / compute_affinities_single (AlternatingDirectionCutLoss.py:612-637,
+ * AlternatingDirectionBoundaryLoss.py:46-70): images (B,3,H,W) -> out (K,B,H,W) with
+ * K = window*window-1, offset order dy outer / dx inner, centre skipped; out[k] is the
+ * reference's k-th list entry (B,1,H,W).  sigma_space <= 0 drops the spatial term. */
+int wsdl_affinities(const float* images, int B, int H, int W, int window, float sigma_color, float sigma_space,
+                    float* out, void* stream);
+
+/* Scale of a saved gradient by a device scalar (autograd backward of the fused launch, whose
+ * gradient was computed for an upstream gradient of 1): dst[i] = src[i] * scale[per ? i / per : 0].
+ * dst may alias src. */
+int wsdl_scale(const float* src, float* dst, size_t n, const float* scale, size_t per, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSDL_B200_H_ */

@@ -1,0 +1,209 @@
+"""GPU parity: fused cut / boundary loss forward+backward through the C ABI against the oracle (fp64 arbiter)
+and the committed reference outputs; loss and gradient within 1e-5 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_grad_close, assert_loss_close, smooth_images
+from oracle import wsdl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def WF():
+    from weaklysuperviseddl_b200 import functional
+
+    return functional
+
+
+@pytest.fixture(scope="module")
+def W():
+    import weaklysuperviseddl_b200
+
+    return weaklysuperviseddl_b200
+
+
+@pytest.fixture(scope="module")
+def pw(golden_dir):
+    return np.load(os.path.join(golden_dir, "pairwise.npz"))
+
+
+def test_cut_loss_golden(W, pw):
+    logits = torch.from_numpy(pw["logits"]).cuda().requires_grad_(True)
+    img = torch.from_numpy(pw["images"]).cuda()
+    loss = W.LocalNormalizedCutLoss(0.05, 5)(logits, img)
+    assert loss.dim() == 0
+    loss.backward()
+    assert_loss_close(loss, pw["cut_loss"], "cut loss")
+    assert_grad_close(logits.grad, pw["cut_grad"], "cut grad")
+    x = torch.from_numpy(pw["logits"][0]).cuda().requires_grad_(True)   # 3-D auto-batch (CutLoss.py:72-74)
+    loss = W.LocalNormalizedCutLoss(0.05, 5)(x, img[0])
+    loss.backward()
+    assert_loss_close(loss, pw["cut3d_loss"])
+    assert_grad_close(x.grad, pw["cut3d_grad"])
+    x = torch.from_numpy(pw["logits"]).cuda().requires_grad_(True)      # window 3, sigma 0.2
+    loss = W.LocalNormalizedCutLoss(0.2, 3)(x, img)
+    loss.backward()
+    assert_loss_close(loss, pw["cut_w3_loss"])
+    assert_grad_close(x.grad, pw["cut_w3_grad"])
+    x = torch.from_numpy(pw["logits3"]).cuda().requires_grad_(True)     # three classes
+    loss = W.LocalNormalizedCutLoss(0.05, 5)(x, torch.from_numpy(pw["images3"]).cuda())
+    loss.backward()
+    assert_loss_close(loss, pw["cut_c3_loss"])
+    assert_grad_close(x.grad, pw["cut_c3_grad"])
+
+
+def test_boundary_loss_golden(W, pw):
+    probs = torch.softmax(torch.from_numpy(pw["logits"]), dim=1)
+    img = torch.from_numpy(pw["images"]).cuda()
+    mod = W.ConstrainToBoundaryLossSingle(0.1, 5, 5)
+    for b in range(2):
+        x = probs[b].cuda().requires_grad_(True)
+        loss = mod(x, img[b])
+        assert loss.dim() == 0
+        loss.backward()
+        assert_loss_close(loss, pw["boundary_loss"][b])
+        assert_grad_close(x.grad, pw["boundary_grad"][b])
+    x = probs.cuda().requires_grad_(True)                                # batched extension: (B,) losses
+    losses = mod(x, img)
+    losses.sum().backward()
+    assert_loss_close(losses, pw["boundary_loss"])
+    assert_grad_close(x.grad, pw["boundary_grad"])
+
+
+def test_affinities_golden(W, pw):
+    img = torch.from_numpy(pw["images"]).cuda()
+    out = W.compute_affinities(img, 0.1, 5, 5)
+    assert len(out) == 24 and out[0].shape == (2, 1, 40, 36)
+    ours = torch.stack(out, dim=1).squeeze(2).cpu().numpy()
+    ref = pw["affinities_batched"]
+    assert np.abs(ours - ref).max() <= 1e-5 * np.abs(ref).max()
+    rel = np.abs(ours - ref) / np.maximum(ref, 1e-30)
+    assert rel[ref > 1e-30].max() <= 1e-5
+    single = W.ConstrainToBoundaryLossSingle.compute_affinities_single(img[1], 0.1, 5, 5)
+    assert len(single) == 24 and single[0].shape == (1, 40, 36)
+    s = torch.stack(single, 0).squeeze(1).cpu().numpy()
+    assert np.abs(s - pw["affinities_single"]).max() <= 1e-5 * np.abs(pw["affinities_single"]).max()
+
+
+CASES = [
+    # B, C, H, W, window, sigma_color, sigma_space, softmax, divc, per_image
+    (2, 2, 64, 64, 5, 0.05, None, True, True, False),     # all-interior + border tiles
+    (1, 2, 224, 224, 5, 0.05, None, True, True, False),   # config-2 image size, cut
+    (3, 2, 224, 224, 5, 0.1, 5.0, False, False, True),    # config-2 image size, boundary
+    (2, 2, 45, 70, 5, 0.1, 5.0, False, False, True),      # ragged tiles
+    (1, 3, 33, 31, 5, 0.05, None, True, True, False),     # three classes
+    (1, 5, 20, 50, 5, 0.08, 2.0, True, False, False),     # runtime-C kernel, softmax + spatial
+    (2, 2, 19, 23, 3, 0.2, None, True, True, False),      # window 3
+    (1, 2, 40, 40, 7, 0.1, 3.0, False, True, True),       # window 7
+    (1, 1, 16, 16, 5, 0.1, None, False, True, False),     # single class, no softmax
+    (1, 2, 3, 3, 5, 0.1, 5.0, True, True, False),         # smallest legal image for pad=2
+    (1, 8, 12, 9, 5, 0.1, None, True, True, False),       # max classes
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_against_fp64_oracle(WF, case):
+    B, C, H, W_, win, sc, ss, sm, divc, per = CASES[case]
+    gen = torch.Generator().manual_seed(500 + case)
+    vals = torch.randn(B, C, H, W_, generator=gen)
+    if not sm:
+        vals = torch.softmax(vals * 2, dim=1)
+    img = smooth_images(gen, B, H, W_)
+    loss, grad = WF.pairwise_loss_and_grad(vals.cuda(), img.cuda(), win, sc, ss, sm, divc, per)
+    ref_l, ref_g = [], []
+    for b in range(B):
+        L, g = O.pairwise_closed_form(vals[b].numpy(), img[b].numpy(), sc, ss, win, sm, divc)
+        ref_l.append(L)
+        ref_g.append(g)
+    ref_g = np.stack(ref_g)
+    if per:
+        assert_loss_close(loss, np.array(ref_l), f"case {case} loss")
+    else:
+        assert_loss_close(loss, np.mean(ref_l), f"case {case} loss")
+        ref_g = ref_g / B
+    assert_grad_close(grad, ref_g, f"case {case} grad")
+
+
+def test_closed_form_oracle_is_the_reference_math():
+    """The fp64 arbiter used above == autograd through the op-for-op restatement (pinned to the reference)."""
+    gen = torch.Generator().manual_seed(9)
+    vals = torch.randn(1, 2, 17, 13, generator=gen)
+    img = smooth_images(gen, 1, 17, 13)
+    v, g = O.loss_and_grad(O.cut_loss, vals, img, dtype=torch.float64)
+    L, gc = O.pairwise_closed_form(vals[0].numpy(), img[0].numpy(), 0.05, None, 5, True, True)
+    assert abs(L - v.item()) < 1e-12 * abs(v.item()) + 1e-18
+    assert np.abs(gc - g[0].numpy()).max() < 1e-12 * np.abs(gc).max()
+
+
+def test_upstream_gradient_and_forward_only(WF, W):
+    gen = torch.Generator().manual_seed(21)
+    vals = torch.randn(2, 2, 48, 40, generator=gen).cuda()
+    img = smooth_images(gen, 2, 48, 40).cuda()
+    l1, g1 = WF.pairwise_loss_and_grad(vals, img, 5, 0.05, None, True, True, False)
+    go = torch.tensor([0.37], device="cuda")
+    l2, g2 = WF.pairwise_loss_and_grad(vals, img, 5, 0.05, None, True, True, False, grad_out=go)
+    assert torch.equal(l1, l2)
+    assert (g2 - 0.37 * g1).abs().max() <= 1e-6 * g1.abs().max()
+    with torch.no_grad():
+        l3 = W.LocalNormalizedCutLoss()(vals, img)
+    assert torch.equal(l3.reshape(1), l1)
+    # autograd: loss * lambda, backward twice (retain_graph) must not double-scale
+    x = vals.clone().requires_grad_(True)
+    loss = W.LocalNormalizedCutLoss()(x, img) * 0.37
+    loss.backward(retain_graph=True)
+    first = x.grad.clone()
+    x.grad = None
+    loss.backward()
+    assert torch.equal(first, x.grad)
+    assert (first - g2).abs().max() <= 1e-6 * g1.abs().max()
+    # per-image upstream gradients
+    p = torch.softmax(vals, 1)
+    gob = torch.tensor([2.0, -0.5], device="cuda")
+    lb, gb = WF.pairwise_loss_and_grad(p, img, 5, 0.1, 5.0, False, False, True, grad_out=gob)
+    lb1, gb1 = WF.pairwise_loss_and_grad(p, img, 5, 0.1, 5.0, False, False, True)
+    assert (gb - gb1 * gob.view(2, 1, 1, 1)).abs().max() <= 1e-6 * gb1.abs().max()
+
+
+def test_deterministic(WF):
+    gen = torch.Generator().manual_seed(2)
+    vals = torch.randn(4, 2, 224, 224, generator=gen).cuda()
+    img = smooth_images(gen, 4, 224, 224).cuda()
+    a = WF.pairwise_loss_and_grad(vals, img)
+    b = WF.pairwise_loss_and_grad(vals, img)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_config2_full_size_properties(WF):
+    """32x2x224x224 (BASELINE config 2): properties that need no oracle at full size + one image vs fp64."""
+    gen = torch.Generator().manual_seed(1)
+    B, C, H, W_ = 32, 2, 224, 224
+    logits = torch.randn(B, C, H, W_, generator=gen).cuda()
+    img = smooth_images(gen, B, H, W_).cuda()
+    loss, grad = WF.pairwise_loss_and_grad(logits, img, 5, 0.05, None, True, True, False)
+    assert loss.item() > 0
+    # batch mean == mean of per-image losses (the reference's .mean() over b,h,w)
+    per = torch.stack([WF.pairwise_loss_and_grad(logits[b:b + 1], img[b:b + 1])[0] for b in range(B)])
+    assert abs(per.mean().item() - loss.item()) <= 1e-6 * loss.item()
+    # softmax shift invariance: adding a per-pixel constant to all logits changes nothing
+    shift = torch.randn(B, 1, H, W_, generator=torch.Generator().manual_seed(3)).cuda()
+    loss_s, grad_s = WF.pairwise_loss_and_grad(logits + shift, img)
+    assert abs(loss_s.item() - loss.item()) <= 2e-6 * loss.item()
+    # gradient of a softmax-composed loss sums to zero over classes
+    assert grad.sum(dim=1).abs().max().item() <= 1e-6 * grad.abs().max().item()
+    # constant image => affinity 1 everywhere; uniform predictions => zero loss and gradient
+    l0, g0 = WF.pairwise_loss_and_grad(torch.zeros_like(logits), torch.full_like(img, 0.5))
+    assert l0.item() == 0.0 and g0.abs().max().item() == 0.0
+    b = 17
+    L, g = O.pairwise_closed_form(logits[b].cpu().numpy(), img[b].cpu().numpy(), 0.05, None, 5, True, True)
+    assert_loss_close(per[b], L)
+    assert_grad_close(grad[b] * B, g)
+    # boundary loss on the same batch, one launch for 32 images
+    probs = torch.softmax(logits, 1)
+    lb, gb = WF.pairwise_loss_and_grad(probs, img, 5, 0.1, 5.0, False, False, True)
+    L, g = O.pairwise_closed_form(probs[b].cpu().numpy(), img[b].cpu().numpy(), 0.1, 5.0, 5, False, False)
+    assert_loss_close(lb[b], L)
+    assert_grad_close(gb[b], g)

@@ -1,0 +1,87 @@
+// Shared device helpers for the wsdl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/wsdl_b200.h"
+
+#define WSDL_NUM_SMS 148
+
+#define WSDL_LAUNCH_CHECK()                    \
+  do {                                         \
+    cudaError_t e__ = cudaGetLastError();      \
+    if (e__ != cudaSuccess) return (int)e__;   \
+  } while (0)
+
+namespace wsdl {
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (every input byte of the
+// channel-sum is touched exactly once).
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned short ld_stream_u16(const void* p) {
+  unsigned short r;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+// L2-coherent load (bypasses L1): for data another CTA of the same launch has written.
+__device__ __forceinline__ float ld_cg_f32(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned ld_cg_u32(const unsigned* p) { return __ldcg(p); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+
+// element conversions for 16-bit storage types, from the raw 16-bit pattern
+template <int DTYPE>
+__device__ __forceinline__ float bits16_to_f32(unsigned short b);
+template <>
+__device__ __forceinline__ float bits16_to_f32<WSDL_BF16>(unsigned short b) {
+  return __uint_as_float(((unsigned)b) << 16);
+}
+template <>
+__device__ __forceinline__ float bits16_to_f32<WSDL_F16>(unsigned short b) {
+  return __half2float(__ushort_as_half(b));
+}
+
+}  // namespace wsdl

@@ -1,0 +1,239 @@
+"""Tensor-level entry points over the C ABI (include/wsdl_b200.h).  torch is used for device memory and
+streams only; every arithmetic step runs in libwsdl_b200.so.  CUDA tensors are required -- there is no
+CPU path (the CPU restatement under oracle/ is test infrastructure and is never imported here)."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+NEAR_BAND = 1e-6  # north_star: pixels within 1e-6 of the threshold are counted and reported
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _native.WsdlError(f"wsdl_b200: `{name}` must be a CUDA tensor; this hot path has no CPU fallback")
+
+
+def _dense(t: torch.Tensor, align: int = 16) -> torch.Tensor:
+    t = t.detach()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % align:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def layercam_fused(
+    acts: Sequence[torch.Tensor],
+    grads: Sequence[torch.Tensor],
+    out_size: Tuple[int, int] = (224, 224),
+    alpha: float = 1.0,
+    alpha_mode: int = 0,
+    thresh: Optional[float] = None,
+    want_cam: bool = True,
+    want_mask: Optional[bool] = None,
+    near_band: float = NEAR_BAND,
+    near_count: Optional[torch.Tensor] = None,
+):
+    """LayerCAM.py:52-76 (+ PsuedoMasks.py:59-62 when `thresh` is given) in two kernel launches.
+
+    acts/grads: per target layer, (B, C_l, h_l, w_l) CUDA tensors of one dtype (f32 / bf16 / f16).
+    Returns (cam (B,H,W) f32 or None, mask (B,H,W) u8 or None, near_count u64 tensor or None)."""
+    if len(acts) != len(grads) or len(acts) == 0:
+        raise ValueError("need one activation and one gradient per target layer")
+    if want_mask is None:
+        want_mask = thresh is not None
+    if want_mask and thresh is None:
+        raise ValueError("want_mask needs a threshold")
+    dev = acts[0].device
+    dtype = acts[0].dtype
+    if dtype not in _DTYPE_CODE:
+        raise TypeError(f"unsupported dtype {dtype}")
+    A: List[torch.Tensor] = []
+    G: List[torch.Tensor] = []
+    B = acts[0].shape[0]
+    for a, g in zip(acts, grads):
+        _require_cuda(a, "activation")
+        _require_cuda(g, "gradient")
+        if a.dim() != 4 or a.shape != g.shape or a.shape[0] != B:
+            raise ValueError(f"activation/gradient shapes must be (B,C,h,w) and equal, got {tuple(a.shape)} / {tuple(g.shape)}")
+        if a.dtype != dtype or g.dtype != dtype or a.device != dev or g.device != dev:
+            raise TypeError("all activations/gradients must share one dtype and device")
+        A.append(_dense(a))
+        G.append(_dense(g))
+    n = len(A)
+    lib = _native.lib()
+    IntArr = ctypes.c_int * n
+    PtrArr = ctypes.c_void_p * n
+    Cs = IntArr(*[t.shape[1] for t in A])
+    hs = IntArr(*[t.shape[2] for t in A])
+    ws = IntArr(*[t.shape[3] for t in A])
+    code = _DTYPE_CODE[dtype]
+    out_h, out_w = int(out_size[0]), int(out_size[1])
+    with torch.cuda.device(dev):
+        nbytes = lib.wsdl_layercam_workspace_bytes(Cs, hs, ws, n, B, code)
+        if nbytes == 0:
+            raise _native.WsdlError("wsdl_layercam_workspace_bytes rejected the shapes")
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        cam = torch.empty((B, out_h, out_w), dtype=torch.float32, device=dev) if want_cam else None
+        mask = torch.empty((B, out_h, out_w), dtype=torch.uint8, device=dev) if want_mask else None
+        if near_count is None and thresh is not None:
+            near_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        rc = lib.wsdl_layercam_fused(
+            PtrArr(*[t.data_ptr() for t in A]),
+            PtrArr(*[t.data_ptr() for t in G]),
+            Cs, hs, ws, n, B, code, out_h, out_w,
+            float(alpha), int(alpha_mode),
+            float(thresh) if thresh is not None else 0.0,
+            float(near_band),
+            cam.data_ptr() if cam is not None else None,
+            mask.data_ptr() if mask is not None else None,
+            near_count.data_ptr() if (near_count is not None and thresh is not None) else None,
+            workspace.data_ptr(), nbytes, _stream_ptr(dev),
+        )
+    _native.check(rc, "wsdl_layercam_fused")
+    return cam, mask, near_count
+
+
+def threshold_mask(cam: torch.Tensor, thresh: float, near_band: float = NEAR_BAND):
+    """`cam[cam < t] = 0; mask = cam > 0` (PsuedoMasks.py:59-62) without modifying `cam`.
+    Returns (mask u8 like cam, near_count)."""
+    _require_cuda(cam, "cam")
+    c = _dense(cam.float(), 4)
+    mask = torch.empty(c.shape, dtype=torch.uint8, device=c.device)
+    near = torch.zeros(1, dtype=torch.int64, device=c.device)
+    with torch.cuda.device(c.device):
+        rc = _native.lib().wsdl_threshold_mask(c.data_ptr(), c.numel(), float(thresh), float(near_band), mask.data_ptr(),
+                                               near.data_ptr(), _stream_ptr(c.device))
+    _native.check(rc, "wsdl_threshold_mask")
+    return mask, near
+
+
+def _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softmax, divide_by_c, per_image, want_grad,
+                  grad_out=None):
+    B, C, H, W = values.shape
+    dev = values.device
+    lib = _native.lib()
+    with torch.cuda.device(dev):
+        nbytes = lib.wsdl_pairwise_workspace_bytes(B, H, W)
+        workspace = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        loss = torch.empty(B if per_image else 1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(values) if want_grad else None
+        rc = lib.wsdl_pairwise_fwd_bwd(
+            values.data_ptr(), images.data_ptr(), B, C, H, W, int(window), float(sigma_color),
+            float(sigma_space) if sigma_space is not None else 0.0,
+            int(inner_softmax), int(divide_by_c), int(per_image),
+            grad_out.data_ptr() if grad_out is not None else None,
+            loss.data_ptr(), grad.data_ptr() if grad is not None else None,
+            workspace.data_ptr(), nbytes, _stream_ptr(dev),
+        )
+    _native.check(rc, "wsdl_pairwise_fwd_bwd")
+    return loss, grad
+
+
+class _PairwiseLoss(torch.autograd.Function):
+    """One fused launch computes the loss and d loss / d values (for an upstream gradient of 1);
+    backward only rescales the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, values, images, window, sigma_color, sigma_space, inner_softmax, divide_by_c, per_image):
+        need = ctx.needs_input_grad[0]
+        loss, grad = _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softmax, divide_by_c,
+                                   per_image, need)
+        if need:
+            ctx.save_for_backward(grad)
+        ctx.per_image = per_image
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("wsdl_b200: gradient w.r.t. the image is not on the reference's path")
+        (grad,) = ctx.saved_tensors
+        go = grad_loss.detach().to(torch.float32).contiguous()
+        out = torch.empty_like(grad)
+        per = grad[0].numel() if ctx.per_image else 0
+        with torch.cuda.device(grad.device):
+            rc = _native.lib().wsdl_scale(grad.data_ptr(), out.data_ptr(), grad.numel(), go.data_ptr(), per,
+                                          _stream_ptr(grad.device))
+        _native.check(rc, "wsdl_scale")
+        return out, None, None, None, None, None, None, None
+
+
+def _prep_pair(values: torch.Tensor, images: torch.Tensor):
+    _require_cuda(values, "preds")
+    _require_cuda(images, "images")
+    if values.dim() != 4 or images.dim() != 4 or images.shape[1] != 3:
+        raise ValueError(f"expected preds (B,C,H,W) and images (B,3,H,W), got {tuple(values.shape)} / {tuple(images.shape)}")
+    if values.shape[0] != images.shape[0] or values.shape[2:] != images.shape[2:]:
+        raise ValueError("preds and images must agree in batch and spatial size")
+    v = values if (values.dtype == torch.float32 and values.is_contiguous()) else values.float().contiguous()
+    im = images.detach()
+    im = im if (im.dtype == torch.float32 and im.is_contiguous()) else im.float().contiguous()
+    return v, im
+
+
+def pairwise_loss(values, images, window_size=5, sigma_color=0.05, sigma_space=None, inner_softmax=True,
+                  divide_by_c=True, per_image=False):
+    """Differentiable (w.r.t. `values`) pairwise regulariser.  Returns a (1,) tensor, or (B,) when per_image."""
+    v, im = _prep_pair(values, images)
+    return _PairwiseLoss.apply(v, im, int(window_size), float(sigma_color),
+                               float(sigma_space) if sigma_space else 0.0, bool(inner_softmax), bool(divide_by_c),
+                               bool(per_image))
+
+
+def pairwise_loss_and_grad(values, images, window_size=5, sigma_color=0.05, sigma_space=None, inner_softmax=True,
+                           divide_by_c=True, per_image=False, grad_out: Optional[torch.Tensor] = None):
+    """The fused launch itself, outside autograd: returns (loss, d(sum loss*grad_out)/d values)."""
+    v, im = _prep_pair(values.detach(), images)
+    return _pairwise_raw(v, im, int(window_size), float(sigma_color), float(sigma_space) if sigma_space else 0.0,
+                         bool(inner_softmax), bool(divide_by_c), bool(per_image), True, grad_out)
+
+
+def affinities(images: torch.Tensor, sigma_color=0.1, sigma_space=5, window_size=5) -> torch.Tensor:
+    """(B,3,H,W) -> (K,B,1,H,W); entry k is the reference's k-th list element."""
+    _require_cuda(images, "image")
+    im = _dense(images.float(), 4)
+    B, _, H, W = im.shape
+    K = window_size * window_size - 1
+    out = torch.empty((K, B, 1, H, W), dtype=torch.float32, device=im.device)
+    with torch.cuda.device(im.device):
+        rc = _native.lib().wsdl_affinities(im.data_ptr(), B, H, W, int(window_size), float(sigma_color),
+                                           float(sigma_space) if sigma_space else 0.0, out.data_ptr(),
+                                           _stream_ptr(im.device))
+    _native.check(rc, "wsdl_affinities")
+    return out
+
+
+def keep_largest(mask: torch.Tensor, return_area: bool = False):
+    """PsuedoMasks.py:15-21 on the GPU: (B,H,W) or (H,W) u8/bool CUDA mask -> same shape u8 {0,1} holding only
+    the largest 8-connected component (ties: first in raster order)."""
+    _require_cuda(mask, "mask")
+    single = mask.dim() == 2
+    m = mask.unsqueeze(0) if single else mask
+    if m.dim() != 3:
+        raise ValueError("mask must be (H,W) or (B,H,W)")
+    m = (m != 0).to(torch.uint8) if m.dtype != torch.uint8 else m
+    m = m.contiguous()
+    B, H, W = m.shape
+    dev = m.device
+    lib = _native.lib()
+    out = torch.empty_like(m)
+    area = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.wsdl_keep_largest_workspace_bytes(B, H, W)
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = lib.wsdl_keep_largest(m.data_ptr(), B, H, W, out.data_ptr(), area.data_ptr(), workspace.data_ptr(), nbytes,
+                                   _stream_ptr(dev))
+    _native.check(rc, "wsdl_keep_largest")
+    out = out[0] if single else out
+    return (out, area) if return_area else out
