@@ -135,7 +135,7 @@ def run_reference(args):
     import torch
 
     threads = os.cpu_count() or 1
-    sample_B = 4
+    sample_B = 2
     times = []
     for i in range(args.warmup + args.steps):
         _, t = cpu_pairwise_sample(sample_B, 1, threads)
@@ -163,14 +163,18 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:  # defaults that finish within minutes for either arm
+        args.steps = 30 if args.impl == "reference" else 4000
+    if args.warmup is None:
+        args.warmup = 3 if args.impl == "reference" else 200
     if args.impl == "reference":
         return run_reference(args)
 
