@@ -55,6 +55,34 @@ __device__ float axis_multiplicity(int a, int e, int n, int pad, float inv_2ss) 
   return m;
 }
 
+// The last CTA of the launch adds the per-tile partial sums in a fixed order (deterministic), in double.
+__device__ __forceinline__ void pw_final_reduce(const PwParams& P, int tiles) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (P.per_image) {
+    for (int bb = warp; bb < P.B; bb += PW_THREADS / 32) {
+      double acc = 0.0;
+      for (int i = lane; i < tiles; i += 32) acc += (double)ld_cg_f32(P.partial + (size_t)bb * tiles + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) P.loss_out[bb] = (float)(acc * P.kappa);
+    }
+  } else {
+    __shared__ double s_d[PW_THREADS / 32];
+    double acc = 0.0;
+    const int n = tiles * P.B;
+    for (int i = tid; i < n; i += PW_THREADS) acc += (double)ld_cg_f32(P.partial + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_d[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < PW_THREADS / 32; ++i) t += s_d[i];
+      P.loss_out[0] = (float)(t * P.kappa);
+    }
+  }
+}
+
 template <int CT, int PADT>  // CT = 0 / PADT = 0: runtime C (<= 8) / runtime pad (<= 3)
 __global__ void __launch_bounds__(PW_THREADS) pairwise_fwd_bwd_kernel(const __grid_constant__ PwParams P) {
   constexpr int CMAX = CT ? CT : WSDL_MAX_CLASSES;
@@ -224,29 +252,318 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_fwd_bwd_kernel(const __gr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (P.per_image) {
-    for (int bb = warp; bb < P.B; bb += PW_THREADS / 32) {
-      double acc = 0.0;
-      for (int i = lane; i < tiles; i += 32) acc += (double)ld_cg_f32(P.partial + (size_t)bb * tiles + i);
+  pw_final_reduce(P, tiles);
+}
+
+
+// ==========================================================================================
+// Fast path (window 5, C <= 4): thread = 4 horizontally adjacent pixels, 128-bit shared loads.
+//
+// The tile is staged WITH its reflect-padded halo, so the main loop is a plain 24-tap gather with no
+// border logic at all:  S_all(z) = sum_d k(z,z+d) s(d) (p(z) - p~(z+d)),  loss += k s |p(z)-p~(z+d)|^2.
+// Treating every padded position as its own variable, the true gradient is
+//     g(z) = 2 kappa [ 2 S_all(z) + corr(z) ],
+//     corr(z) = - sum_{d: z+d in halo} k s (p(z) - p~(z+d))          (incoming edges exist only from real pixels)
+//               + sum_{u in r^-1(z), u != z} sum_{d: u+d real} k(u,u+d) s(d) (p(z) - p(u+d))   (edges into z's mirror images)
+// corr is non-zero only for pixels within `pad` of the border (7% at 224x224); border CTAs compute it in a
+// compacted pre-pass (lanes run along the border, not across it) and park it in shared memory.
+// ==========================================================================================
+constexpr int PF_PAD = 2;
+constexpr int PF_SW = PW_TW + 2 * PF_PAD;  // 36 floats: 144 B rows keep 16-byte alignment of every 4-pixel run
+constexpr int PF_SH = PW_TH + 2 * PF_PAD;
+constexpr int PF_PLANE = PF_SH * PF_SW;
+
+template <int C>
+__device__ __forceinline__ void pf_corr_item(const PwParams& P, const float* s_img, const float* s_p, float* s_corr,
+                                            int x0, int y0, int zy, int zx) {
+  const int H = P.H, W = P.W;
+  const int so = (zy - y0 + PF_PAD) * PF_SW + (zx - x0 + PF_PAD);
+  const float i0 = s_img[so], i1 = s_img[PF_PLANE + so], i2 = s_img[2 * PF_PLANE + so];
+  float pz[C], acc[C];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) P.loss_out[bb] = (float)(acc * P.kappa);
+  for (int c = 0; c < C; ++c) pz[c] = s_p[c * PF_PLANE + so], acc[c] = 0.f;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      // a/b = 0: the pixel itself; 1: its mirror image across the low border; 2: across the high border
+      const bool va = a == 0 || (a == 1 ? (zy >= 1 && zy <= PF_PAD) : (zy >= H - 1 - PF_PAD && zy <= H - 2));
+      const bool vb = b == 0 || (b == 1 ? (zx >= 1 && zx <= PF_PAD) : (zx >= W - 1 - PF_PAD && zx <= W - 2));
+      if (!va || !vb) continue;
+      const int cy = a == 0 ? zy : (a == 1 ? -zy : 2 * (H - 1) - zy);
+      const int cx = b == 0 ? zx : (b == 1 ? -zx : 2 * (W - 1) - zx);
+      const bool self = (a == 0 && b == 0);
+#pragma unroll 1
+      for (int dy = -PF_PAD; dy <= PF_PAD; ++dy)
+#pragma unroll 1
+        for (int dx = -PF_PAD; dx <= PF_PAD; ++dx) {
+          if (dx == 0 && dy == 0) continue;
+          const int ny = cy + dy, nx = cx + dx;
+          const bool real = (ny >= 0 && ny < H && nx >= 0 && nx < W);
+          if (self == real) continue;  // self: halo neighbours only; mirror image: real neighbours only
+          const int sn = (ny - y0 + PF_PAD) * PF_SW + (nx - x0 + PF_PAD);
+          const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PF_PLANE + sn], d2 = i2 - s_img[2 * PF_PLANE + sn];
+          const float dist = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+          float k = ex2_approx(fmaf(dist, P.kc, (float)(dx * dx + dy * dy) * P.ks_unit));
+          k = self ? -k : k;
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PF_PLANE + sn], acc[c]);
+        }
     }
-  } else {
-    __shared__ double s_d[PW_THREADS / 32];
-    double acc = 0.0;
-    const int n = tiles * P.B;
-    for (int i = tid; i < n; i += PW_THREADS) acc += (double)ld_cg_f32(P.partial + i);
+  const int to = (zy - y0) * PW_TW + (zx - x0);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) s_d[warp] = acc;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int i = 0; i < PW_THREADS / 32; ++i) t += s_d[i];
-      P.loss_out[0] = (float)(t * P.kappa);
+  for (int c = 0; c < C; ++c) s_corr[c * PW_TW * PW_TH + to] = acc[c];
+}
+
+template <int C>
+__global__ void __launch_bounds__(PW_THREADS, (C <= 2 ? 3 : 2)) pairwise_fast_kernel(const __grid_constant__ PwParams P) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_img = smem;                    // [3][PF_SH][PF_SW], reflect-padded
+  float* s_p = s_img + 3 * PF_PLANE;      // [C][PF_SH][PF_SW]
+  float* s_corr = s_p + C * PF_PLANE;     // [C][TH][TW], border CTAs only
+  __shared__ float s_red[PW_THREADS / 32];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y, b = blockIdx.z;
+  const int x0 = tile_x * PW_TW, y0 = tile_y * PW_TH;
+  const int H = P.H, W = P.W;
+  const size_t plane = (size_t)H * W;
+  const float* img = P.images + (size_t)b * 3 * plane;
+  const float* val = P.values + (size_t)b * C * plane;
+
+  // ---- stage tile + reflect halo; softmax on the way in.  All global loads of a thread are issued
+  //      before the first use so that one memory latency covers the whole tile. ----
+  {
+    constexpr int NPOS = PF_SH * PF_SW;
+    constexpr int NIT = (NPOS + PW_THREADS - 1) / PW_THREADS;
+    float vi[NIT][3], vv[NIT][C];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = tid + it * PW_THREADS;
+      const int ty = i / PF_SW, tx = i - ty * PF_SW;
+      int gy = y0 - PF_PAD + ty, gx = x0 - PF_PAD + tx;
+      gy = gy < 0 ? -gy : gy;
+      gy = gy >= H ? 2 * (H - 1) - gy : gy;
+      gx = gx < 0 ? -gx : gx;
+      gx = gx >= W ? 2 * (W - 1) - gx : gx;
+      gy = min(max(gy, 0), H - 1);  // positions past a ragged tile's halo: any valid address, never used
+      gx = min(max(gx, 0), W - 1);
+      const size_t o = (size_t)gy * W + gx;
+      if (i < NPOS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vi[it][c] = __ldg(img + c * plane + o);
+#pragma unroll
+        for (int c = 0; c < C; ++c) vv[it][c] = __ldg(val + c * plane + o);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = tid + it * PW_THREADS;
+      if (i < NPOS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_img[c * PF_PLANE + i] = vi[it][c];
+        float v[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = vv[it][c];
+        if (P.inner_softmax) {
+          float m = v[0];
+#pragma unroll
+          for (int c = 1; c < C; ++c) m = fmaxf(m, v[c]);
+          float s = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            v[c] = ex2_approx((v[c] - m) * LOG2E);
+            s += v[c];
+          }
+          const float inv = __fdiv_rn(1.f, s);
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[c] *= inv;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) s_p[c * PF_PLANE + i] = v[c];
+      }
     }
   }
+  __syncthreads();
+
+  const float ksx1 = P.ks_unit, ksx2 = 4.f * P.ks_unit;  // log2 of the spatial Gaussian along x
+
+  // ---- border CTAs: correction pre-pass over the pixels within PF_PAD of an image border ----
+  const int xe = min(x0 + PW_TW, W), ye = min(y0 + PW_TH, H);  // tile extent inside the image
+  const bool border = (x0 <= PF_PAD) || (y0 <= PF_PAD) || (xe >= W - PF_PAD) || (ye >= H - PF_PAD);
+  if (border) {
+    for (int i = tid; i < C * PW_TW * PW_TH; i += PW_THREADS) s_corr[i] = 0.f;
+    __syncthreads();
+    const int tw = xe - x0, th = ye - y0;
+    // band columns inside the tile: [x0, xl) and [xr, xe);  band rows: [y0, yl) and [yr, ye)
+    const int xl = min(max(PF_PAD + 1, x0), xe), xr = max(min(W - 1 - PF_PAD, xe), xl);
+    const int yl = min(max(PF_PAD + 1, y0), ye), yr = max(min(H - 1 - PF_PAD, ye), yl);
+    const int ncol = (xl - x0) + (xe - xr), nrow = (yl - y0) + (ye - yr);
+    for (int i = tid; i < ncol * th; i += PW_THREADS) {  // lanes run down the band columns
+      const int j = i / th, ty = i - j * th;
+      const int zx = j < (xl - x0) ? x0 + j : xr + (j - (xl - x0));
+      pf_corr_item<C>(P, s_img, s_p, s_corr, x0, y0, y0 + ty, zx);
+    }
+    const int wmid = xr - xl;  // columns not already covered above
+    for (int i = tid; i < nrow * wmid; i += PW_THREADS) {  // lanes run along the band rows
+      const int j = i / wmid, tx = i - j * wmid;
+      const int zy = j < (yl - y0) ? y0 + j : yr + (j - (yl - y0));
+      pf_corr_item<C>(P, s_img, s_p, s_corr, x0, y0, zy, xl + tx);
+    }
+    (void)tw;
+    __syncthreads();
+  }
+
+  // ---- main pass: lane = (run of 4 pixels, row): 8 runs x 4 rows per warp, 8 warps = 32 rows ----
+  const int run = lane & 7, row = warp * 4 + (lane >> 3);
+  const int gy = y0 + row, gx = x0 + run * 4;
+  float g[4][C];
+  float loss_acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[j][c] = 0.f;
+  float ci[3][4], cp[C][4];  // centre pixels
+  {
+    const int so = (row + PF_PAD) * PF_SW + run * 4 + PF_PAD;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ci[c][j] = s_img[c * PF_PLANE + so + j];
+#pragma unroll
+      for (int c = 0; c < C; ++c) cp[c][j] = s_p[c * PF_PLANE + so + j];
+    }
+  }
+#pragma unroll 1
+  for (int ey = -PF_PAD; ey <= PF_PAD; ++ey) {
+    const int so = (row + PF_PAD + ey) * PF_SW + run * 4;  // window columns gx-2 .. gx+5
+    const float ksy = (float)(ey * ey) * P.ks_unit;
+    const float kse[5] = {ksy + ksx2, ksy + ksx1, ksy, ksy + ksx1, ksy + ksx2};
+    float wi[3][8], wp[C][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(s_img + c * PF_PLANE + so);
+      const float4 d = *reinterpret_cast<const float4*>(s_img + c * PF_PLANE + so + 4);
+      wi[c][0] = a.x, wi[c][1] = a.y, wi[c][2] = a.z, wi[c][3] = a.w;
+      wi[c][4] = d.x, wi[c][5] = d.y, wi[c][6] = d.z, wi[c][7] = d.w;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(s_p + c * PF_PLANE + so);
+      const float4 d = *reinterpret_cast<const float4*>(s_p + c * PF_PLANE + so + 4);
+      wp[c][0] = a.x, wp[c][1] = a.y, wp[c][2] = a.z, wp[c][3] = a.w;
+      wp[c][4] = d.x, wp[c][5] = d.y, wp[c][6] = d.z, wp[c][7] = d.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int ex = -PF_PAD; ex <= PF_PAD; ++ex) {
+        const int n = j + PF_PAD + ex;  // window index of the neighbour (the centre tap adds exactly 0)
+        const float d0 = ci[0][j] - wi[0][n], d1 = ci[1][j] - wi[1][n], d2 = ci[2][j] - wi[2][n];
+        const float dist = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+        const float k = ex2_approx(fmaf(dist, P.kc, kse[ex + PF_PAD]));
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float dp = cp[c][j] - wp[c][n];
+          sq = fmaf(dp, dp, sq);
+          g[j][c] = fmaf(k, dp, g[j][c]);
+        }
+        loss_acc = fmaf(k, sq, loss_acc);
+      }
+    }
+  }
+
+  // ---- epilogue: g = 2 kappa (2 S_all + corr), softmax backward, store; loss partial ----
+  const float scale_g = (float)(2.0 * P.kappa) * (P.grad_out ? __ldg(P.grad_out + (P.per_image ? b : 0)) : 1.f);
+  float lsum = 0.f;
+  if (gy < H) {
+    float out[C][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float gg[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        gg[c] = 2.f * g[j][c];
+        if (border) gg[c] += s_corr[c * PW_TW * PW_TH + row * PW_TW + run * 4 + j];
+      }
+      if (P.inner_softmax) {
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) dot = fmaf(cp[c][j], gg[c], dot);
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][j] = scale_g * cp[c][j] * (gg[c] - dot);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][j] = scale_g * gg[c];
+      }
+    }
+    if (gx + 3 < W) lsum = loss_acc;  // all four pixels real (the common case); ragged runs are redone below
+    if (P.grad_values) {
+      float* go = P.grad_values + (size_t)b * C * plane + (size_t)gy * W + gx;
+      const bool vec = (gx + 3 < W) && ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.grad_values) & 15) == 0);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        if (vec) {
+          *reinterpret_cast<float4*>(go + c * plane) = make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gx + j < W) go[c * plane + j] = out[c][j];
+        }
+      }
+    }
+  }
+  if (gy < H && gx < W && gx + 3 >= W) {
+    // ragged run at the right edge: loss of the real pixels only (the tile's extra columns hold clamped data)
+    const int so = (row + PF_PAD) * PF_SW + run * 4 + PF_PAD;
+    for (int j = 0; gx + j < W; ++j)
+      for (int ey = -PF_PAD; ey <= PF_PAD; ++ey)
+        for (int ex = -PF_PAD; ex <= PF_PAD; ++ex) {
+          if (ex == 0 && ey == 0) continue;
+          const int sn = so + j + ey * PF_SW + ex;
+          const float d0 = s_img[so + j] - s_img[sn], d1 = s_img[PF_PLANE + so + j] - s_img[PF_PLANE + sn],
+                      d2 = s_img[2 * PF_PLANE + so + j] - s_img[2 * PF_PLANE + sn];
+          const float k = ex2_approx(fmaf(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)), P.kc, (float)(ex * ex + ey * ey) * P.ks_unit));
+          float sq = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float dp = s_p[c * PF_PLANE + so + j] - s_p[c * PF_PLANE + sn];
+            sq = fmaf(dp, dp, sq);
+          }
+          lsum = fmaf(k, sq, lsum);
+        }
+  }
+
+  lsum = warp_sum(lsum);
+  if (lane == 0) s_red[warp] = lsum;
+  __syncthreads();
+  const int tiles = P.tiles_x * P.tiles_y;
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < PW_THREADS / 32; ++i) t += s_red[i];
+    __stcg(P.partial + (size_t)b * tiles + tile_y * P.tiles_x + tile_x, t);
+    __threadfence();
+    const unsigned n = atomicAdd(P.ticket, 1u);
+    s_last = (n == (unsigned)(tiles * P.B) - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  pw_final_reduce(P, tiles);
+}
+
+template <int C>
+static int pf_launch(const PwParams& P, cudaStream_t s) {
+  const size_t smem = sizeof(float) * ((size_t)(3 + C) * PF_PLANE + (size_t)C * PW_TW * PW_TH);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pairwise_fast_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid(P.tiles_x, P.tiles_y, P.B);
+  pairwise_fast_kernel<C><<<grid, PW_THREADS, smem, s>>>(P);
+  WSDL_LAUNCH_CHECK();
+  return 0;
 }
 
 template <int CT, int PADT>
@@ -359,15 +676,16 @@ extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, i
   P.kappa = 1.0 / (K * N * (divide_by_c ? (double)C : 1.0));
   cudaError_t e = cudaMemsetAsync(P.ticket, 0, 4, s);
   if (e != cudaSuccess) return (int)e;
-  if (pad == 2) {
+  if (pad == 2 && H > 2 * PF_PAD && W > 2 * PF_PAD) {
     switch (C) {
-      case 1: return pw_launch<1, 2>(P, s);
-      case 2: return pw_launch<2, 2>(P, s);
-      case 3: return pw_launch<3, 2>(P, s);
-      case 4: return pw_launch<4, 2>(P, s);
+      case 1: return pf_launch<1>(P, s);
+      case 2: return pf_launch<2>(P, s);
+      case 3: return pf_launch<3>(P, s);
+      case 4: return pf_launch<4>(P, s);
       default: break;
     }
   }
+  if (pad == 2 && C == 2) return pw_launch<2, 2>(P, s);
   return pw_launch<0, 0>(P, s);
 }
 
