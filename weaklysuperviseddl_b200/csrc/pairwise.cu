@@ -13,7 +13,9 @@
 // y ranging over the in-image window around z.  M is separable, M = my(zy,ey)*mx(zx,ex), and equals
 // s(e) whenever z is >= pad pixels from every border, so CTAs whose tile is >= 2*pad from the border
 // take a table-free path.  With an inner softmax, dL/dlogit_c = p_c (g_c - sum_j p_j g_j).
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "pairwise.cuh"
 
 namespace wsdl {
 
@@ -21,30 +23,6 @@ constexpr int PW_TW = 32;       // tile width  (one lane per column)
 constexpr int PW_TH = 32;       // tile height
 constexpr int PW_THREADS = 256; // 8 warps, warp w owns rows w, w+8, w+16, w+24
 constexpr int PW_MAXPAD = 3;    // window <= 7
-constexpr float LOG2E = 1.4426950408889634f;
-
-struct PwParams {
-  const float* values;
-  const float* images;
-  const float* grad_out;  // nullable
-  float* loss_out;
-  float* grad_values;     // nullable
-  float* partial;         // (B * tiles) block partial sums
-  unsigned* ticket;
-  int B, C, H, W, pad;
-  int tiles_x, tiles_y;
-  int inner_softmax, per_image;
-  float kc;        // -log2(e) / (2 sigma_color^2)
-  float ks_unit;   // -log2(e) / (2 sigma_space^2), 0 when there is no spatial term
-  float inv_2ss;   // 1 / (2 sigma_space^2), 0 when there is no spatial term
-  double kappa;    // 1 / (K * N * (C or 1)), N = B*H*W or H*W
-};
-
-__device__ __forceinline__ int reflect_idx(int i, int n) {
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * (n - 1) - i;
-  return i;
-}
 
 // M_axis(a, e; n) = sum_{d=-pad..pad} [reflect(a+d) == a+e] * s1(d); 0 when a or a+e is outside.
 __device__ float axis_multiplicity(int a, int e, int n, int pad, float inv_2ss) {
@@ -56,6 +34,7 @@ __device__ float axis_multiplicity(int a, int e, int n, int pad, float inv_2ss) 
 }
 
 // The last CTA of the launch adds the per-tile partial sums in a fixed order (deterministic), in double.
+template <int BAR_ID = 0>  // 0: __syncthreads(); else a named barrier over the first PW_THREADS threads
 __device__ __forceinline__ void pw_final_reduce(const PwParams& P, int tiles) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (P.per_image) {
@@ -74,7 +53,10 @@ __device__ __forceinline__ void pw_final_reduce(const PwParams& P, int tiles) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) s_d[warp] = acc;
-    __syncthreads();
+    if (BAR_ID == 0)
+      __syncthreads();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(BAR_ID), "r"(PW_THREADS) : "memory");
     if (tid == 0) {
       double t = 0.0;
       for (int i = 0; i < PW_THREADS / 32; ++i) t += s_d[i];
@@ -566,6 +548,7 @@ static int pf_launch(const PwParams& P, cudaStream_t s) {
   return 0;
 }
 
+
 template <int CT, int PADT>
 static size_t pw_smem_bytes() {
   constexpr int CMAX = CT ? CT : WSDL_MAX_CLASSES;
@@ -631,7 +614,10 @@ static size_t pw_align(size_t x) { return (x + 255) / 256 * 256; }
 extern "C" size_t wsdl_pairwise_workspace_bytes(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
   const size_t tiles = (size_t)((W + PW_TW - 1) / PW_TW) * ((H + PW_TH - 1) / PW_TH);
-  return 512 + pw_align((size_t)B * tiles * sizeof(float));
+  size_t floats = (size_t)B * tiles;  // one partial per 32x32 tile (generic / fast kernels)
+  const size_t sym = ps_workspace_floats(B, H, W);
+  if (sym > floats) floats = sym;
+  return 512 + pw_align(floats * sizeof(float));
 }
 
 extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C, int H, int W,
@@ -674,9 +660,14 @@ extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, i
   const double K = (double)window * window - 1.0;
   const double N = (per_image_loss ? 1.0 : (double)B) * (double)H * (double)W;
   P.kappa = 1.0 / (K * N * (divide_by_c ? (double)C : 1.0));
-  cudaError_t e = cudaMemsetAsync(P.ticket, 0, 4, s);
+  cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
   if (e != cudaSuccess) return (int)e;
   if (pad == 2 && H > 2 * PF_PAD && W > 2 * PF_PAD) {
+    static const int no_sym = []() { const char* e = getenv("WSDL_PAIRWISE_NO_SYM"); return (e && e[0] == '1') ? 1 : 0; }();
+    if (!no_sym) {  // pair-symmetric kernel (pairwise_sym.cu): the hot configurations (window 5, C <= 2)
+      const int rc = ps_launch(P, s);
+      if (rc != 1) return rc;
+    }
     switch (C) {
       case 1: return pf_launch<1>(P, s);
       case 2: return pf_launch<2>(P, s);

@@ -1,0 +1,37 @@
+// Parameters and helpers shared by the pairwise-regulariser kernels (pairwise.cu, pairwise_sym.cu).
+#pragma once
+#include "common.cuh"
+
+namespace wsdl {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct PwParams {
+  const float* values;
+  const float* images;
+  const float* grad_out;  // nullable
+  float* loss_out;
+  float* grad_values;     // nullable
+  float* partial;         // block partial sums (layout is the kernel's own)
+  unsigned* ticket;
+  int B, C, H, W, pad;
+  int tiles_x, tiles_y;
+  int inner_softmax, per_image;
+  float kc;        // -log2(e) / (2 sigma_color^2)
+  float ks_unit;   // -log2(e) / (2 sigma_space^2), 0 when there is no spatial term
+  float inv_2ss;   // 1 / (2 sigma_space^2), 0 when there is no spatial term
+  double kappa;    // 1 / (K * N * (C or 1)), N = B*H*W or H*W
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// Pair-symmetric window-5 kernel (pairwise_sym.cu).  ps_launch returns 1 when the shape is not its own
+// (the caller then takes the generic kernels), 0 on success, another value on a CUDA error.
+int ps_launch(const PwParams& P, cudaStream_t s);
+size_t ps_workspace_floats(int B, int H, int W);
+
+}  // namespace wsdl

@@ -1,0 +1,606 @@
+// Pair-symmetric cut / boundary loss (window 5, C <= 2), forward + backward in one launch, sm_100a.
+//
+// Same contract as pairwise.cu (reference: LocalNormalizedCutLoss.forward, TraditionalModel/
+// AlternatingDirectionCutLoss.py:71-105; ConstrainToBoundaryLossSingle.forward,
+// AlternatingDirectionBoundaryLoss.py:20-70) but organised around the instruction count, because on B200 the
+// stencil is bound by the FP32/MUFU issue rate long before HBM (ncu: 24 exp + ~340 FP32 ops per pixel):
+//
+//  * k(z,y) is symmetric, so every unordered pixel pair is evaluated ONCE (12 forward offsets instead of 24 taps):
+//    t = k s (p(z) - p(y)) is added to G(z) and subtracted from G(y).
+//  * The loss is not accumulated per pair: L is a quadratic form in p, so  L = 1/2 sum_z p(z) . dL/dp(z)
+//    (Euler); the kernel forms it from the finished gradient (with p shifted by 1/2: sum_z dL/dp(z) = 0).
+//  * The image is pre-scaled by sqrt(-kc) while staging, so a pair costs 3 FADD + 3 FFMA + 1 MUFU.EX2 for k and
+//    3 C more for the two scatters.
+//
+// Work mapping.  A thread owns a strip of 4 columns and marches down S consecutive rows (a "segment"); the
+// contributions it makes to rows t+1, t+2 live in three rotating accumulator rows in registers, the ones it makes
+// to the 2 columns either side of its strip go to the neighbouring lanes by warp shuffle when a row completes.
+// 16 strips (a half warp) span the 64 staged columns of a tile (60 owned + 2 halo each side), 8 segments span the
+// block's rows; the first two rows of a segment are completed by the two rows its upper neighbour carries over,
+// through shared memory.  A CTA owns a contiguous range of the flattened (image, column tile, row) space, sized on
+// the host so that the launch is exactly one wave; each block pays 2 warm-up rows instead of a halo in y.
+//
+// Borders.  Interior arithmetic treats every reflect-padded position as its own variable holding its mirror
+// source's value, which gives S_all(z) = sum_d k s (p(z) - p~(z+d)).  The true gradient is 2 kappa (2 S_all + corr),
+// corr being non-zero only within 2 px of an image border (see pairwise.cu); border blocks compute corr in a
+// compacted pre-pass, lanes running along the border.
+#include "pairwise.cuh"
+
+namespace wsdl {
+
+constexpr int PS_TW = 60;                      // owned columns per tile
+constexpr int PS_PITCH = 68;                   // smem row: image x0-4 .. x0+63 (2 pad + 2 halo | 60 | 2 halo + 2 pad)
+constexpr int PS_Q = PS_PITCH / 4;             // float4 per staged row
+constexpr int PS_SEGS = 8;                     // row segments per block, one per half warp
+constexpr int PS_THREADS = 16 * PS_SEGS;       // 128
+constexpr int PS_SMAX = 5;                     // rows per segment
+constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 40 centre rows per block: 2 warm-up + 38 owned
+constexpr int PS_ROWS = PS_CENTERS + 2;        // + 2 look-ahead rows
+constexpr int PS_CAP = PS_CENTERS - 2;         // owned rows per block
+constexpr int PS_PLANE = PS_ROWS * PS_PITCH;
+constexpr int PS_CTAS_PER_SM = 3;
+
+struct PsParams {
+  PwParams p;
+  int n_x;          // column tiles per image
+  int rpc;          // flattened rows per CTA
+  int kpi;          // partial-sum slots per image
+  int vec4_ok;      // W % 4 == 0 and 16-byte aligned inputs: float4 staging loads
+  int vec2_ok;      // W % 2 == 0 and 8-byte aligned gradient: float2 stores
+  long long L;      // n_x * H: flattened rows per image
+  long long R_tot;  // B * L
+  float img_scale;  // sqrt(-kc)
+};
+
+template <int C>
+struct PsWin {  // an 8-column window of one staged row: columns 4*strip .. 4*strip+7 of the smem row
+  float i[3][8];
+  float p[C][8];
+};
+
+template <int C>
+__device__ __forceinline__ void ps_load(PsWin<C>& w, const float* s_img, const float* s_p, int off) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(s_img + c * PS_PLANE + off);
+    const float4 b = *reinterpret_cast<const float4*>(s_img + c * PS_PLANE + off + 4);
+    w.i[c][0] = a.x, w.i[c][1] = a.y, w.i[c][2] = a.z, w.i[c][3] = a.w;
+    w.i[c][4] = b.x, w.i[c][5] = b.y, w.i[c][6] = b.z, w.i[c][7] = b.w;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(s_p + c * PS_PLANE + off);
+    const float4 b = *reinterpret_cast<const float4*>(s_p + c * PS_PLANE + off + 4);
+    w.p[c][0] = a.x, w.p[c][1] = a.y, w.p[c][2] = a.z, w.p[c][3] = a.w;
+    w.p[c][4] = b.x, w.p[c][5] = b.y, w.p[c][6] = b.z, w.p[c][7] = b.w;
+  }
+}
+
+// one unordered pair: k = 2^(ks - |I'(a) - I'(b)|^2);  G(a) += k (p(a) - p(b));  G(b) -= k (p(a) - p(b))
+template <int C>
+__device__ __forceinline__ void ps_pair(float (&ga)[C], float (&gb)[C], const PsWin<C>& a, int ia, const PsWin<C>& b,
+                                        int ib, float ks) {
+  const float d0 = a.i[0][ia] - b.i[0][ib], d1 = a.i[1][ia] - b.i[1][ib], d2 = a.i[2][ia] - b.i[2][ib];
+  const float k = ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, ks))));
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float dp = a.p[c][ia] - b.p[c][ib];
+    ga[c] = fmaf(k, dp, ga[c]);
+    gb[c] = fmaf(-k, dp, gb[c]);
+  }
+}
+
+// All 12 forward pairs of the 4 centres of row t (accumulator X), partners in rows t (X), t+1 (Y), t+2 (Z).
+template <int C>
+__device__ __forceinline__ void ps_step(float (&X)[8][C], float (&Y)[8][C], float (&Z)[8][C], float (&pc)[4][C],
+                                        const float* s_img, const float* s_p, int off, const float (&ks)[9]) {
+  PsWin<C> c;
+  ps_load<C>(c, s_img, s_p, off);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) pc[j][cc] = c.p[cc][2 + j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ps_pair<C>(X[2 + j], X[3 + j], c, 2 + j, c, 3 + j, ks[1]);
+    ps_pair<C>(X[2 + j], X[4 + j], c, 2 + j, c, 4 + j, ks[4]);
+  }
+  PsWin<C> n;
+  ps_load<C>(n, s_img, s_p, off + PS_PITCH);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) ps_pair<C>(X[2 + j], Y[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks[dx * dx + 1]);
+  ps_load<C>(n, s_img, s_p, off + 2 * PS_PITCH);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) ps_pair<C>(X[2 + j], Z[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks[dx * dx + 4]);
+}
+
+// A finished accumulator row: the two columns either side of the strip belong to the neighbouring lanes.
+template <int C>
+__device__ __forceinline__ void ps_exchange(const float (&X)[8][C], float (&own)[4][C], int strip) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float r0 = __shfl_down_sync(0xffffffffu, X[0][c], 1), r1 = __shfl_down_sync(0xffffffffu, X[1][c], 1);
+    float l0 = __shfl_up_sync(0xffffffffu, X[6][c], 1), l1 = __shfl_up_sync(0xffffffffu, X[7][c], 1);
+    if (strip == 15) r0 = 0.f, r1 = 0.f;
+    if (strip == 0) l0 = 0.f, l1 = 0.f;
+    own[0][c] = X[2][c] + l0;
+    own[1][c] = X[3][c] + l1;
+    own[2][c] = X[4][c] + r0;
+    own[3][c] = X[5][c] + r1;
+  }
+}
+
+struct PsBlk {
+  int b, x0, ys, n, nc;
+  bool border;
+  float scale_g;
+};
+
+// corr slot of a coordinate: 0..2 for the low band, 3..5 for the high band, -1 outside (needs n >= 6)
+__device__ __forceinline__ int ps_band_slot(int v, int n) { return v <= 2 ? v : (v >= n - 3 ? v - (n - 6) : -1); }
+
+// Gradient of 4 finished pixels of centre row t: g = 2 kappa (2 G + corr), softmax backward, store; loss term.
+template <int C, bool SOFTMAX>
+__device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t, int strip, const float (&G)[4][C],
+                                        const float (&pc)[4][C], const float* s_corr_r, const float* s_corr_c,
+                                        float& lsum) {
+  const int H = Q.p.H, W = Q.p.W;
+  const int y = K.ys - 2 + t;
+  const int xs = K.x0 - 2 + 4 * strip;  // image column of j = 0
+  const int rs = K.border ? ps_band_slot(y, H) : -1;
+  float out[C][4];
+  bool ok[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = 4 * strip + j;  // staged column: 0,1 and 62,63 are halo
+    const int x = xs + j;
+    ok[j] = (col >= 2) && (col < 2 + PS_TW) && (x < W);
+    float gg[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) gg[c] = 2.f * G[j][c];
+    if (K.border && ok[j]) {
+      const int cs = ps_band_slot(x, W);
+      if (rs >= 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) gg[c] += s_corr_r[(rs * C + c) * 64 + col];
+      } else if (cs >= 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) gg[c] += s_corr_c[(cs * C + c) * PS_CAP + (t - 2)];
+      }
+    }
+    if (ok[j]) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) lsum = fmaf(pc[j][c] - 0.5f, gg[c], lsum);
+    }
+    if (SOFTMAX) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dot = fmaf(pc[j][c], gg[c], dot);
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[c][j] = K.scale_g * pc[j][c] * (gg[c] - dot);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) out[c][j] = K.scale_g * gg[c];
+    }
+  }
+  if (Q.p.grad_values) {
+    const size_t plane = (size_t)H * W;
+    float* go = Q.p.grad_values + (size_t)K.b * C * plane + (size_t)y * W + xs;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (Q.vec2_ok) {  // xs is even, so (xs, xs+1) and (xs+2, xs+3) are inside or outside W together
+        if (ok[0]) *reinterpret_cast<float2*>(go + c * plane) = make_float2(out[c][0], out[c][1]);
+        if (ok[2]) *reinterpret_cast<float2*>(go + c * plane + 2) = make_float2(out[c][2], out[c][3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ok[j]) go[c * plane + j] = out[c][j];
+      }
+    }
+  }
+}
+
+// corr(z) for one band pixel (pairwise.cu derives it): minus the edges from z into halo positions, plus the edges
+// from real pixels into z's mirror images.  Reads the staged (pre-scaled, reflect-filled) tile.  The partners of
+// each term form rectangles of the 5x5 window, so the loops below visit exactly the pairs that contribute:
+//   self   : rows of the window outside the image (all 5 columns), then, for the rows inside, the columns outside;
+//   mirror : the window of the mirror image clipped to the image.
+template <int C>
+__device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_img, const float* s_p, int ys, int x0,
+                                            int zy, int zx, float* dst, int dstride) {
+  const int H = Q.p.H, W = Q.p.W;
+  const int oy = ys - 2, ox = x0 - 4;
+  const int so = (zy - oy) * PS_PITCH + (zx - ox);
+  const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
+  float pz[C], acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
+  // rows / columns of z's own window that lie inside the image
+  const int ry0 = max(-2, -zy), ry1 = min(2, H - 1 - zy), rx0 = max(-2, -zx), rx1 = min(2, W - 1 - zx);
+  const int my = (zy >= 1 && zy <= 2) ? -zy : ((zy >= H - 3 && zy <= H - 2) ? 2 * (H - 1) - zy : zy);  // mirror row or zy
+  const int mx = (zx >= 1 && zx <= 2) ? -zx : ((zx >= W - 3 && zx <= W - 2) ? 2 * (W - 1) - zx : zx);
+#pragma unroll 1
+  for (int r = 0; r < 7; ++r) {
+    // r = 0,1: self, window rows above / below the image;  2,3: self, columns left / right of the image (rows inside)
+    // r = 4: mirror in y;  5: mirror in x;  6: mirror in both
+    int cy = zy, cx = zx, dy0, dy1, dx0, dx1;
+    if (r == 0) dy0 = -2, dy1 = ry0 - 1, dx0 = -2, dx1 = 2;
+    else if (r == 1) dy0 = ry1 + 1, dy1 = 2, dx0 = -2, dx1 = 2;
+    else if (r == 2) dy0 = ry0, dy1 = ry1, dx0 = -2, dx1 = rx0 - 1;
+    else if (r == 3) dy0 = ry0, dy1 = ry1, dx0 = rx1 + 1, dx1 = 2;
+    else {
+      cy = (r == 5) ? zy : my;
+      cx = (r == 4) ? zx : mx;
+      const bool valid = (r == 4) ? (my != zy) : (r == 5 ? (mx != zx) : (my != zy && mx != zx));
+      dy0 = max(-2, -cy), dy1 = valid ? min(2, H - 1 - cy) : -3;
+      dx0 = max(-2, -cx), dx1 = min(2, W - 1 - cx);
+    }
+    const float sign = r < 4 ? -1.f : 1.f;
+#pragma unroll 1
+    for (int dy = dy0; dy <= dy1; ++dy)
+#pragma unroll 1
+      for (int dx = dx0; dx <= dx1; ++dx) {
+        const int sn = (cy + dy - oy) * PS_PITCH + (cx + dx - ox);
+        const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+        const float k =
+            sign * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, (float)(dx * dx + dy * dy) * Q.p.ks_unit))));
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) dst[c * dstride] = acc[c];
+}
+
+// ---- staging: rows ys-2 .. ys+n+1 (reflected), columns x0-4 .. x0+63 (reflected); softmax and image scale ----
+template <int C>
+struct PsItem {
+  float4 vi[3];
+  float4 vv[C];
+};
+
+template <int C>
+__device__ __forceinline__ void ps_stage_load(const PsParams& Q, PsItem<C>& it, const float* img, const float* val,
+                                              int x0, int ys, int item) {
+  const int H = Q.p.H, W = Q.p.W;
+  const size_t plane = (size_t)H * W;
+  const int t = item / PS_Q, q = item - t * PS_Q;
+  int y = ys - 2 + t;
+  y = y < 0 ? -y : y;
+  y = y >= H ? 2 * (H - 1) - y : y;
+  y = min(max(y, 0), H - 1);
+  const int xb = x0 - 4 + 4 * q;
+  if (Q.vec4_ok && xb >= 0 && xb + 3 < W) {
+    const size_t o = (size_t)y * W + xb;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) it.vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
+#pragma unroll
+    for (int c = 0; c < C; ++c) it.vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
+  } else {
+    size_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int x = xb + e;
+      x = x < 0 ? -x : x;
+      x = x >= W ? 2 * (W - 1) - x : x;
+      x = min(max(x, 0), W - 1);  // pad columns past the halo: any valid address, never used for owned results
+      o[e] = (size_t)y * W + x;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      it.vi[c] = make_float4(__ldg(img + c * plane + o[0]), __ldg(img + c * plane + o[1]), __ldg(img + c * plane + o[2]),
+                             __ldg(img + c * plane + o[3]));
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      it.vv[c] = make_float4(__ldg(val + c * plane + o[0]), __ldg(val + c * plane + o[1]), __ldg(val + c * plane + o[2]),
+                             __ldg(val + c * plane + o[3]));
+  }
+}
+
+template <int C, bool SOFTMAX>
+__device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C>& it, float* s_img, float* s_p,
+                                               int item) {
+  const int so = item * 4;  // == t * PS_PITCH + 4 * q
+  const float sc = Q.img_scale;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) =
+        make_float4(it.vi[c].x * sc, it.vi[c].y * sc, it.vi[c].z * sc, it.vi[c].w * sc);
+  float v[C][4];
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c][0] = it.vv[c].x, v[c][1] = it.vv[c].y, v[c][2] = it.vv[c].z, v[c][3] = it.vv[c].w;
+  if (SOFTMAX) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float m = v[0][e];
+#pragma unroll
+      for (int c = 1; c < C; ++c) m = fmaxf(m, v[c][e]);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        v[c][e] = ex2_approx((v[c][e] - m) * LOG2E);
+        s += v[c][e];
+      }
+      const float inv = rcp_approx(s);
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c][e] *= inv;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    *reinterpret_cast<float4*>(s_p + c * PS_PLANE + so) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+}
+
+template <int C>
+__device__ __forceinline__ void ps_zero(float (&X)[8][C]) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+#pragma unroll
+    for (int c = 0; c < C; ++c) X[w][c] = 0.f;
+}
+
+template <int C, bool SOFTMAX>
+__global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kernel(const __grid_constant__ PsParams Q) {
+  extern __shared__ __align__(16) float ps_smem[];
+  float* s_img = ps_smem;                                  // [3][PS_ROWS][PS_PITCH], pre-scaled
+  float* s_p = s_img + 3 * PS_PLANE;                       // [C][PS_ROWS][PS_PITCH]
+  float* s_head = s_p + C * PS_PLANE;                      // [7][2][C][64]: first two rows of segments 1..7, own part
+  float* s_carry = s_head + (PS_SEGS - 1) * 2 * C * 64;    // [7][2][C][64]: the same rows, upper neighbour's part
+  float* s_corr_r = s_carry + (PS_SEGS - 1) * 2 * C * 64;  // [6][C][64]: corr of the band rows
+  float* s_corr_c = s_corr_r + 6 * C * 64;                 // [6][C][PS_CAP]: corr of the band columns
+  __shared__ float s_red[PS_THREADS / 32];
+  __shared__ double s_dred[PS_THREADS / 32];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg = warp * 2 + (lane >> 4), strip = lane & 15;
+  const int H = Q.p.H, W = Q.p.W;
+  const size_t plane = (size_t)H * W;
+  float ks[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) ks[i] = (float)i * Q.p.ks_unit;
+
+  long long r = (long long)blockIdx.x * Q.rpc;
+  const long long r_end = min(r + (long long)Q.rpc, Q.R_tot);
+  int cur_b = -1;
+  float lsum = 0.f;
+
+  auto flush = [&](int b) {  // CTA-uniform: one partial per (image, CTA)
+    const float w = warp_sum(lsum);
+    if (lane == 0) s_red[warp] = w;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < PS_THREADS / 32; ++i) t += s_red[i];
+      const long long c_lo = ((long long)b * Q.L) / Q.rpc;
+      __stcg(Q.p.partial + (size_t)b * Q.kpi + (size_t)((long long)blockIdx.x - c_lo), t);
+    }
+    __syncthreads();
+    lsum = 0.f;
+  };
+
+  while (r < r_end) {
+    PsBlk K;
+    {
+      const long long col = r / H;
+      K.ys = (int)(r - col * H);
+      K.b = (int)(col / Q.n_x);
+      K.x0 = (int)(col - (long long)K.b * Q.n_x) * PS_TW;
+      K.n = (int)min(min(r_end - r, (long long)(H - K.ys)), (long long)PS_CAP);
+      K.nc = K.n + 2;
+    }
+    if (K.b != cur_b) {
+      if (cur_b >= 0) flush(cur_b);
+      cur_b = K.b;
+    }
+    const int xe = min(K.x0 + PS_TW, W);  // owned columns [x0, xe)
+    K.border = (K.x0 == 0) || (xe - 1 >= W - 3) || (K.ys <= 2) || (K.ys + K.n - 1 >= H - 3);
+    K.scale_g = (float)(2.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
+
+    __syncthreads();  // the previous block's readers of the tile are done
+    {
+      const float* img = Q.p.images + (size_t)K.b * 3 * plane;
+      const float* val = Q.p.values + (size_t)K.b * C * plane;
+      const int items = (K.n + 4) * PS_Q;
+      for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
+        PsItem<C> u0, u1, u2;
+        ps_stage_load<C>(Q, u0, img, val, K.x0, K.ys, it);
+        if (it + PS_THREADS < items) ps_stage_load<C>(Q, u1, img, val, K.x0, K.ys, it + PS_THREADS);
+        if (it + 2 * PS_THREADS < items) ps_stage_load<C>(Q, u2, img, val, K.x0, K.ys, it + 2 * PS_THREADS);
+        ps_stage_store<C, SOFTMAX>(Q, u0, s_img, s_p, it);
+        if (it + PS_THREADS < items) ps_stage_store<C, SOFTMAX>(Q, u1, s_img, s_p, it + PS_THREADS);
+        if (it + 2 * PS_THREADS < items) ps_stage_store<C, SOFTMAX>(Q, u2, s_img, s_p, it + 2 * PS_THREADS);
+      }
+    }
+    __syncthreads();
+
+    if (K.border) {  // corr of the band pixels this block owns
+      for (int i = tid; i < 6 * PS_TW; i += PS_THREADS) {  // band rows, lanes along x
+        const int rs = i / PS_TW, cx = i - rs * PS_TW;
+        const int y = rs < 3 ? rs : H - 6 + rs, x = K.x0 + cx;
+        if (y >= K.ys && y < K.ys + K.n && x < xe)
+          ps_corr_item<C>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_r + rs * C * 64 + cx + 2, 64);
+      }
+      for (int i = tid; i < 6 * K.n; i += PS_THREADS) {  // band columns, lanes along y
+        const int cs = i / K.n, ty = i - cs * K.n;
+        const int x = cs < 3 ? cs : W - 6 + cs, y = K.ys + ty;
+        if (x >= K.x0 && x < xe && ps_band_slot(y, H) < 0)
+          ps_corr_item<C>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_c + cs * C * PS_CAP + ty, PS_CAP);
+      }
+      __syncthreads();
+    }
+
+    // ---- march ----
+    const int S = max(2, (K.nc + PS_SEGS - 1) / PS_SEGS);
+    const int t0 = seg * S, t1 = min(t0 + S, K.nc);
+    if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
+      float A[8][C], Bq[8][C], Cq[8][C];
+      ps_zero<C>(A), ps_zero<C>(Bq), ps_zero<C>(Cq);
+
+      // one copy of the step in the instruction stream (the body is ~11 KB); the accumulator rows rotate by moves
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {
+        const int t = t0 + s;
+        const bool act = t < t1;
+        float pc[4][C], own[4][C];
+        if (act) ps_step<C>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
+        ps_exchange<C>(A, own, strip);
+        if (act) {
+          if (s >= 2) {
+            ps_emit<C, SOFTMAX>(Q, K, t, strip, own, pc, s_corr_r, s_corr_c, lsum);
+          } else if (seg > 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+              *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * C + c) * 64 + 4 * strip) =
+                  make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+#pragma unroll
+          for (int c = 0; c < C; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
+      }
+      {  // rows t0+S, t0+S+1 belong to the next segment: hand over what this one contributed to them
+        float oy[4][C], oz[4][C];
+        ps_exchange<C>(A, oy, strip);
+        ps_exchange<C>(Bq, oz, strip);
+        if (seg < PS_SEGS - 1) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (t0 + S < K.nc)
+              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * C + c) * 64 + 4 * strip) =
+                  make_float4(oy[0][c], oy[1][c], oy[2][c], oy[3][c]);
+            if (t0 + S + 1 < K.nc)
+              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * C + c) * 64 + 4 * strip) =
+                  make_float4(oz[0][c], oz[1][c], oz[2][c], oz[3][c]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- the first two rows of segments 1..7: own part + the upper neighbour's carry ----
+    if (seg > 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int t = t0 + i;
+        if (t < t1) {
+          float G[4][C], pc[4][C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * C + c) * 64 + 4 * strip);
+            const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + i) * C + c) * 64 + 4 * strip);
+            G[0][c] = h.x + k.x, G[1][c] = h.y + k.y, G[2][c] = h.z + k.z, G[3][c] = h.w + k.w;
+            const float2 p01 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 2);
+            const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
+            pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
+          }
+          ps_emit<C, SOFTMAX>(Q, K, t, strip, G, pc, s_corr_r, s_corr_c, lsum);
+        }
+      }
+    }
+    r += K.n;
+  }
+  if (cur_b >= 0) flush(cur_b);
+
+  // ---- the last CTA adds the per-(image, CTA) partials in a fixed order, in double ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned n = atomicAdd(Q.p.ticket, 1u);
+    s_last = (n == gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double wtot = 0.0;
+  for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {
+    const long long c_lo = ((long long)b * Q.L) / Q.rpc, c_hi = (((long long)b + 1) * Q.L - 1) / Q.rpc;
+    const int cnt = (int)(c_hi - c_lo + 1);
+    double acc = 0.0;
+    for (int i = lane; i < cnt; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)b * Q.kpi + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (Q.p.per_image) {
+      if (lane == 0) Q.p.loss_out[b] = (float)(acc * Q.p.kappa);
+    } else {
+      wtot += acc;
+    }
+  }
+  if (!Q.p.per_image) {
+    if (lane == 0) s_dred[warp] = wtot;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < PS_THREADS / 32; ++i) t += s_dred[i];
+      Q.p.loss_out[0] = (float)(t * Q.p.kappa);
+    }
+  }
+}
+
+template <int C>
+static constexpr size_t ps_smem_bytes() {
+  return sizeof(float) * ((size_t)(3 + C) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * C * 64 + 6 * (size_t)C * 64 +
+                          6 * (size_t)C * PS_CAP);
+}
+
+struct PsGeom {
+  int n_x, rpc, kpi, grid;
+  long long L, R_tot;
+};
+
+static PsGeom ps_geometry(int B, int H, int W) {
+  PsGeom g;
+  g.n_x = (W + PS_TW - 1) / PS_TW;
+  g.L = (long long)g.n_x * H;
+  g.R_tot = g.L * B;
+  const long long slots = (long long)WSDL_NUM_SMS * PS_CTAS_PER_SM;
+  long long rpc = (g.R_tot + slots - 1) / slots;
+  if (rpc < 6) rpc = 6;  // a block of fewer rows is all warm-up
+  g.rpc = (int)(rpc > 0x3fffffff ? 0x3fffffff : rpc);
+  g.grid = (int)((g.R_tot + g.rpc - 1) / g.rpc);
+  g.kpi = (int)(g.L / g.rpc) + 2;
+  return g;
+}
+
+size_t ps_workspace_floats(int B, int H, int W) {
+  const PsGeom g = ps_geometry(B, H, W);
+  return (size_t)B * g.kpi;
+}
+
+template <int C, bool SOFTMAX>
+static int ps_launch_t(const PsParams& Q, int grid, cudaStream_t s) {
+  constexpr size_t smem = ps_smem_bytes<C>();
+  static bool attr_set = false;  // idempotent; a race only repeats the call
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  pairwise_sym_kernel<C, SOFTMAX><<<grid, PS_THREADS, smem, s>>>(Q);
+  WSDL_LAUNCH_CHECK();
+  return 0;
+}
+
+int ps_launch(const PwParams& P, cudaStream_t s) {
+  if (P.pad != 2 || P.C < 1 || P.C > 2 || P.H < 6 || P.W < 6) return 1;
+  const PsGeom g = ps_geometry(P.B, P.H, P.W);
+  if (g.R_tot / g.rpc > 0x7ffffff0LL) return 1;
+  PsParams Q;
+  Q.p = P;
+  Q.n_x = g.n_x, Q.rpc = g.rpc, Q.kpi = g.kpi, Q.L = g.L, Q.R_tot = g.R_tot;
+  Q.vec4_ok = ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0);
+  Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
+  Q.img_scale = sqrtf(-P.kc);
+  if (P.C == 2) return P.inner_softmax ? ps_launch_t<2, true>(Q, g.grid, s) : ps_launch_t<2, false>(Q, g.grid, s);
+  return P.inner_softmax ? ps_launch_t<1, true>(Q, g.grid, s) : ps_launch_t<1, false>(Q, g.grid, s);
+}
+
+}  // namespace wsdl
