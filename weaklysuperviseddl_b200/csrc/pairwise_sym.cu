@@ -11,6 +11,8 @@
 //    (Euler); the kernel forms it from the finished gradient (with p shifted by 1/2: sum_z dL/dp(z) = 0).
 //  * The image is pre-scaled by sqrt(-kc) while staging, so a pair costs 3 FADD + 3 FFMA + 1 MUFU.EX2 for k and
 //    3 C more for the two scatters.
+//  * Two classes behind a softmax (the reference's binary segmentation) satisfy p1 = 1 - p0, so G1 = -G0: only
+//    channel 0 is staged and accumulated (CS = 1 "stored channel"), and dL/dlogit0 = -dL/dlogit1 = 4 kappa p0 p1 G0.
 //
 // Work mapping.  A thread owns a strip of 4 columns and marches down S consecutive rows (a "segment"); the
 // contributions it makes to rows t+1, t+2 live in three rotating accumulator rows in registers, the ones it makes
@@ -38,7 +40,6 @@ constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 40 centre rows per block: 2 wa
 constexpr int PS_ROWS = PS_CENTERS + 2;        // + 2 look-ahead rows
 constexpr int PS_CAP = PS_CENTERS - 2;         // owned rows per block
 constexpr int PS_PLANE = PS_ROWS * PS_PITCH;
-constexpr int PS_CTAS_PER_SM = 3;
 
 struct PsParams {
   PwParams p;
@@ -137,88 +138,101 @@ __device__ __forceinline__ void ps_exchange(const float (&X)[8][C], float (&own)
 struct PsBlk {
   int b, x0, ys, n, nc;
   bool border;
-  float scale_g;
+  float scale2;  // 4 kappa * upstream gradient: g = scale2 * (G + corr/2)
 };
 
 // corr slot of a coordinate: 0..2 for the low band, 3..5 for the high band, -1 outside (needs n >= 6)
 __device__ __forceinline__ int ps_band_slot(int v, int n) { return v <= 2 ? v : (v >= n - 3 ? v - (n - 6) : -1); }
 
-// Gradient of 4 finished pixels of centre row t: g = 2 kappa (2 G + corr), softmax backward, store; loss term.
-template <int C, bool SOFTMAX>
-__device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t, int strip, const float (&G)[4][C],
-                                        const float (&pc)[4][C], const float* s_corr_r, const float* s_corr_c,
-                                        float& lsum) {
+// Gradient of 4 finished pixels of centre row t: dL/dp = scale2 (G + corr/2), softmax backward, store; the loss is
+// 2 kappa sum (p - 1/2) (G + corr/2), accumulated without its factor.  C = classes, CS = stored channels.
+template <int C, int CS, bool SOFTMAX>
+__device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t, int strip, int okmask,
+                                        const float (&G)[4][CS], const float (&pc)[4][CS], const float* s_corr_r,
+                                        const float* s_corr_c, float& lsum) {
   const int H = Q.p.H, W = Q.p.W;
   const int y = K.ys - 2 + t;
   const int xs = K.x0 - 2 + 4 * strip;  // image column of j = 0
-  const int rs = K.border ? ps_band_slot(y, H) : -1;
+  float g[4][CS];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c = 0; c < CS; ++c) g[j][c] = G[j][c];
+  if (K.border) {  // block-uniform
+    const int rs = ps_band_slot(y, H);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((okmask >> j) & 1) {
+        const int cs = ps_band_slot(xs + j, W);
+        if (rs >= 0) {
+#pragma unroll
+          for (int c = 0; c < CS; ++c) g[j][c] += s_corr_r[(rs * CS + c) * 64 + 4 * strip + j];
+        } else if (cs >= 0) {
+#pragma unroll
+          for (int c = 0; c < CS; ++c) g[j][c] += s_corr_c[(cs * CS + c) * PS_CAP + (t - 2)];
+        }
+      }
+  }
   float out[C][4];
-  bool ok[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int col = 4 * strip + j;  // staged column: 0,1 and 62,63 are halo
-    const int x = xs + j;
-    ok[j] = (col >= 2) && (col < 2 + PS_TW) && (x < W);
-    float gg[C];
+    float l;
+    if (CS != C) {  // two classes behind a softmax: p1 = 1 - p0, G1 = -G0
+      const float p0 = pc[j][0], p1 = 1.f - p0;
+      l = (p0 - p1) * g[j][0];
+      out[0][j] = K.scale2 * 2.f * p0 * p1 * g[j][0];
+      out[C - 1][j] = -out[0][j];
+    } else {
+      l = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) gg[c] = 2.f * G[j][c];
-    if (K.border && ok[j]) {
-      const int cs = ps_band_slot(x, W);
-      if (rs >= 0) {
+      for (int c = 0; c < CS; ++c) l = fmaf(pc[j][c] - 0.5f, g[j][c], l);
+      if (SOFTMAX) {
+        float dot = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) gg[c] += s_corr_r[(rs * C + c) * 64 + col];
-      } else if (cs >= 0) {
+        for (int c = 0; c < CS; ++c) dot = fmaf(pc[j][c], g[j][c], dot);
 #pragma unroll
-        for (int c = 0; c < C; ++c) gg[c] += s_corr_c[(cs * C + c) * PS_CAP + (t - 2)];
+        for (int c = 0; c < CS; ++c) out[c][j] = K.scale2 * pc[j][c] * (g[j][c] - dot);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CS; ++c) out[c][j] = K.scale2 * g[j][c];
       }
     }
-    if (ok[j]) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) lsum = fmaf(pc[j][c] - 0.5f, gg[c], lsum);
-    }
-    if (SOFTMAX) {
-      float dot = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) dot = fmaf(pc[j][c], gg[c], dot);
-#pragma unroll
-      for (int c = 0; c < C; ++c) out[c][j] = K.scale_g * pc[j][c] * (gg[c] - dot);
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) out[c][j] = K.scale_g * gg[c];
-    }
+    if ((okmask >> j) & 1) lsum += l;
   }
   if (Q.p.grad_values) {
     const size_t plane = (size_t)H * W;
     float* go = Q.p.grad_values + (size_t)K.b * C * plane + (size_t)y * W + xs;
+    if (Q.vec2_ok) {  // xs is even, so (xs, xs+1) and (xs+2, xs+3) are inside or outside W together
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      if (Q.vec2_ok) {  // xs is even, so (xs, xs+1) and (xs+2, xs+3) are inside or outside W together
-        if (ok[0]) *reinterpret_cast<float2*>(go + c * plane) = make_float2(out[c][0], out[c][1]);
-        if (ok[2]) *reinterpret_cast<float2*>(go + c * plane + 2) = make_float2(out[c][2], out[c][3]);
-      } else {
+      for (int c = 0; c < C; ++c) {
+        if (okmask & 1) *reinterpret_cast<float2*>(go + c * plane) = make_float2(out[c][0], out[c][1]);
+        if (okmask & 4) *reinterpret_cast<float2*>(go + c * plane + 2) = make_float2(out[c][2], out[c][3]);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (ok[j]) go[c * plane + j] = out[c][j];
-      }
+          if ((okmask >> j) & 1) go[c * plane + j] = out[c][j];
     }
   }
 }
 
-// corr(z) for one band pixel (pairwise.cu derives it): minus the edges from z into halo positions, plus the edges
-// from real pixels into z's mirror images.  Reads the staged (pre-scaled, reflect-filled) tile.  The partners of
-// each term form rectangles of the 5x5 window, so the loops below visit exactly the pairs that contribute:
+// corr(z)/2 for one band pixel (pairwise.cu derives corr): minus the edges from z into halo positions, plus the
+// edges from real pixels into z's mirror images.  Reads the staged (pre-scaled, reflect-filled) tile.  The partners
+// of each term form rectangles of the 5x5 window, so the loops below visit exactly the pairs that contribute:
 //   self   : rows of the window outside the image (all 5 columns), then, for the rows inside, the columns outside;
 //   mirror : the window of the mirror image clipped to the image.
-template <int C>
+template <int CS>
 __device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_img, const float* s_p, int ys, int x0,
                                             int zy, int zx, float* dst, int dstride) {
   const int H = Q.p.H, W = Q.p.W;
   const int oy = ys - 2, ox = x0 - 4;
   const int so = (zy - oy) * PS_PITCH + (zx - ox);
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
-  float pz[C], acc[C];
+  float pz[CS], acc[CS];
 #pragma unroll
-  for (int c = 0; c < C; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
+  for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
   // rows / columns of z's own window that lie inside the image
   const int ry0 = max(-2, -zy), ry1 = min(2, H - 1 - zy), rx0 = max(-2, -zx), rx1 = min(2, W - 1 - zx);
   const int my = (zy >= 1 && zy <= 2) ? -zy : ((zy >= H - 3 && zy <= H - 2) ? 2 * (H - 1) - zy : zy);  // mirror row or zy
@@ -239,72 +253,36 @@ __device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_i
       dy0 = max(-2, -cy), dy1 = valid ? min(2, H - 1 - cy) : -3;
       dx0 = max(-2, -cx), dx1 = min(2, W - 1 - cx);
     }
-    const float sign = r < 4 ? -1.f : 1.f;
+    if (dy1 < dy0 || dx1 < dx0) continue;
+    const float sign = r < 4 ? -0.5f : 0.5f;
 #pragma unroll 1
-    for (int dy = dy0; dy <= dy1; ++dy)
+    for (int dy = dy0; dy <= dy1; ++dy) {
+      const int srow = (cy + dy - oy) * PS_PITCH + (cx - ox);
+      const float ksy = (float)(dy * dy) * Q.p.ks_unit;
 #pragma unroll 1
       for (int dx = dx0; dx <= dx1; ++dx) {
-        const int sn = (cy + dy - oy) * PS_PITCH + (cx + dx - ox);
+        const int sn = srow + dx;
         const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
-        const float k =
-            sign * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, (float)(dx * dx + dy * dy) * Q.p.ks_unit))));
+        const float k = sign * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, fmaf((float)(dx * dx), Q.p.ks_unit, ksy)))));
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
+        for (int c = 0; c < CS; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
       }
+    }
   }
 #pragma unroll
-  for (int c = 0; c < C; ++c) dst[c * dstride] = acc[c];
+  for (int c = 0; c < CS; ++c) dst[c * dstride] = acc[c];
 }
 
-// ---- staging: rows ys-2 .. ys+n+1 (reflected), columns x0-4 .. x0+63 (reflected); softmax and image scale ----
+// ---- staging: rows ys-2 .. ys+n+1 (reflected), columns x0-4 .. x0+63; softmax and image scale on the way in ----
 template <int C>
 struct PsItem {
   float4 vi[3];
   float4 vv[C];
 };
 
-template <int C>
-__device__ __forceinline__ void ps_stage_load(const PsParams& Q, PsItem<C>& it, const float* img, const float* val,
-                                              int x0, int ys, int item) {
-  const int H = Q.p.H, W = Q.p.W;
-  const size_t plane = (size_t)H * W;
-  const int t = item / PS_Q, q = item - t * PS_Q;
-  int y = ys - 2 + t;
-  y = y < 0 ? -y : y;
-  y = y >= H ? 2 * (H - 1) - y : y;
-  y = min(max(y, 0), H - 1);
-  const int xb = x0 - 4 + 4 * q;
-  if (Q.vec4_ok && xb >= 0 && xb + 3 < W) {
-    const size_t o = (size_t)y * W + xb;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) it.vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
-#pragma unroll
-    for (int c = 0; c < C; ++c) it.vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
-  } else {
-    size_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      int x = xb + e;
-      x = x < 0 ? -x : x;
-      x = x >= W ? 2 * (W - 1) - x : x;
-      x = min(max(x, 0), W - 1);  // pad columns past the halo: any valid address, never used for owned results
-      o[e] = (size_t)y * W + x;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      it.vi[c] = make_float4(__ldg(img + c * plane + o[0]), __ldg(img + c * plane + o[1]), __ldg(img + c * plane + o[2]),
-                             __ldg(img + c * plane + o[3]));
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      it.vv[c] = make_float4(__ldg(val + c * plane + o[0]), __ldg(val + c * plane + o[1]), __ldg(val + c * plane + o[2]),
-                             __ldg(val + c * plane + o[3]));
-  }
-}
-
-template <int C, bool SOFTMAX>
+template <int C, int CS, bool SOFTMAX>
 __device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C>& it, float* s_img, float* s_p,
-                                               int item) {
-  const int so = item * 4;  // == t * PS_PITCH + 4 * q
+                                               int so) {
   const float sc = Q.img_scale;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -313,7 +291,10 @@ __device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C
   float v[C][4];
 #pragma unroll
   for (int c = 0; c < C; ++c) v[c][0] = it.vv[c].x, v[c][1] = it.vv[c].y, v[c][2] = it.vv[c].z, v[c][3] = it.vv[c].w;
-  if (SOFTMAX) {
+  if (CS != C) {  // p0 = 1 / (1 + e^(v1 - v0))
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[0][e] = rcp_approx(1.f + ex2_approx((v[1][e] - v[0][e]) * LOG2E));
+  } else if (SOFTMAX) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float m = v[0][e];
@@ -331,27 +312,71 @@ __device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C
     }
   }
 #pragma unroll
-  for (int c = 0; c < C; ++c)
+  for (int c = 0; c < CS; ++c)
     *reinterpret_cast<float4*>(s_p + c * PS_PLANE + so) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
 }
 
+__device__ __forceinline__ int ps_reflect_row(int y, int H) {
+  y = y < 0 ? -y : y;
+  y = y >= H ? 2 * (H - 1) - y : y;
+  return min(max(y, 0), H - 1);
+}
+
+// any W / alignment: element-wise loads with the reflection applied to the address
 template <int C>
-__device__ __forceinline__ void ps_zero(float (&X)[8][C]) {
+__device__ __noinline__ void ps_stage_load_slow(const PsParams& Q, PsItem<C>& it, const float* img, const float* val,
+                                                int x0, int ys, int item) {
+  const int H = Q.p.H, W = Q.p.W;
+  const size_t plane = (size_t)H * W;
+  const int t = item / PS_Q, q = item - t * PS_Q;
+  const int y = ps_reflect_row(ys - 2 + t, H);
+  const int xb = x0 - 4 + 4 * q;
+  float vi[3][4], vv[C][4];
+#pragma unroll 1
+  for (int e = 0; e < 4; ++e) {
+    int x = xb + e;
+    x = x < 0 ? -x : x;
+    x = x >= W ? 2 * (W - 1) - x : x;
+    x = min(max(x, 0), W - 1);  // pad columns past the halo: any valid address, never used for owned results
+    const size_t o = (size_t)y * W + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) vi[c][e] = __ldg(img + c * plane + o);
+#pragma unroll
+    for (int c = 0; c < C; ++c) vv[c][e] = __ldg(val + c * plane + o);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) it.vi[c] = make_float4(vi[c][0], vi[c][1], vi[c][2], vi[c][3]);
+#pragma unroll
+  for (int c = 0; c < C; ++c) it.vv[c] = make_float4(vv[c][0], vv[c][1], vv[c][2], vv[c][3]);
+}
+
+template <int CS>
+__device__ __forceinline__ void ps_zero(float (&X)[8][CS]) {
 #pragma unroll
   for (int w = 0; w < 8; ++w)
 #pragma unroll
-    for (int c = 0; c < C; ++c) X[w][c] = 0.f;
+    for (int c = 0; c < CS; ++c) X[w][c] = 0.f;
 }
 
 template <int C, bool SOFTMAX>
-__global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kernel(const __grid_constant__ PsParams Q) {
+struct PsCfg {
+  static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // stored channels
+  static constexpr int CTAS = CS == 1 ? 4 : 3;            // resident CTAs per SM (shared memory and registers)
+  static constexpr size_t smem_floats =
+      (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * 64 + 6 * (size_t)CS * PS_CAP;
+};
+
+template <int C, bool SOFTMAX>
+__global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
+    pairwise_sym_kernel(const __grid_constant__ PsParams Q) {
+  constexpr int CS = PsCfg<C, SOFTMAX>::CS;
   extern __shared__ __align__(16) float ps_smem[];
-  float* s_img = ps_smem;                                  // [3][PS_ROWS][PS_PITCH], pre-scaled
-  float* s_p = s_img + 3 * PS_PLANE;                       // [C][PS_ROWS][PS_PITCH]
-  float* s_head = s_p + C * PS_PLANE;                      // [7][2][C][64]: first two rows of segments 1..7, own part
-  float* s_carry = s_head + (PS_SEGS - 1) * 2 * C * 64;    // [7][2][C][64]: the same rows, upper neighbour's part
-  float* s_corr_r = s_carry + (PS_SEGS - 1) * 2 * C * 64;  // [6][C][64]: corr of the band rows
-  float* s_corr_c = s_corr_r + 6 * C * 64;                 // [6][C][PS_CAP]: corr of the band columns
+  float* s_img = ps_smem;                                   // [3][PS_ROWS][PS_PITCH], pre-scaled
+  float* s_p = s_img + 3 * PS_PLANE;                        // [CS][PS_ROWS][PS_PITCH]
+  float* s_head = s_p + CS * PS_PLANE;                      // [7][2][CS][64]: first two rows of segments 1..7, own part
+  float* s_carry = s_head + (PS_SEGS - 1) * 2 * CS * 64;    // [7][2][CS][64]: the same rows, upper neighbour's part
+  float* s_corr_r = s_carry + (PS_SEGS - 1) * 2 * CS * 64;  // [6][CS][64]: corr/2 of the band rows
+  float* s_corr_c = s_corr_r + 6 * CS * 64;                 // [6][CS][PS_CAP]: corr/2 of the band columns
   __shared__ float s_red[PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
   __shared__ int s_last;
@@ -378,7 +403,7 @@ __global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kerne
 #pragma unroll
       for (int i = 0; i < PS_THREADS / 32; ++i) t += s_red[i];
       const long long c_lo = ((long long)b * Q.L) / Q.rpc;
-      __stcg(Q.p.partial + (size_t)b * Q.kpi + (size_t)((long long)blockIdx.x - c_lo), t);
+      __stcg(Q.p.partial + (size_t)b * Q.kpi + (size_t)((long long)blockIdx.x - c_lo), 2.f * t);
     }
     __syncthreads();
     lsum = 0.f;
@@ -398,39 +423,92 @@ __global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kerne
       if (cur_b >= 0) flush(cur_b);
       cur_b = K.b;
     }
-    const int xe = min(K.x0 + PS_TW, W);  // owned columns [x0, xe)
-    K.border = (K.x0 == 0) || (xe - 1 >= W - 3) || (K.ys <= 2) || (K.ys + K.n - 1 >= H - 3);
-    K.scale_g = (float)(2.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
+    const int xe = min(K.x0 + PS_TW, W), ye = K.ys + K.n;  // owned pixels [x0, xe) x [ys, ye)
+    K.border = (K.x0 == 0) || (xe - 1 >= W - 3) || (K.ys <= 2) || (ye - 1 >= H - 3);
+    K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
+    int okmask = 0;  // which of this thread's 4 columns are owned pixels of the image
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = 4 * strip + j;  // staged column: 0,1 and 62,63 are halo
+      if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
+    }
 
     __syncthreads();  // the previous block's readers of the tile are done
     {
       const float* img = Q.p.images + (size_t)K.b * 3 * plane;
       const float* val = Q.p.values + (size_t)K.b * C * plane;
       const int items = (K.n + 4) * PS_Q;
-      for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
-        PsItem<C> u0, u1, u2;
-        ps_stage_load<C>(Q, u0, img, val, K.x0, K.ys, it);
-        if (it + PS_THREADS < items) ps_stage_load<C>(Q, u1, img, val, K.x0, K.ys, it + PS_THREADS);
-        if (it + 2 * PS_THREADS < items) ps_stage_load<C>(Q, u2, img, val, K.x0, K.ys, it + 2 * PS_THREADS);
-        ps_stage_store<C, SOFTMAX>(Q, u0, s_img, s_p, it);
-        if (it + PS_THREADS < items) ps_stage_store<C, SOFTMAX>(Q, u1, s_img, s_p, it + PS_THREADS);
-        if (it + 2 * PS_THREADS < items) ps_stage_store<C, SOFTMAX>(Q, u2, s_img, s_p, it + 2 * PS_THREADS);
+      if (Q.vec4_ok) {
+        // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image; the two halo
+        // columns outside are mirrored from shared memory below
+#pragma unroll 1
+        for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
+          PsItem<C> u[3];
+          int so[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int item = it + k * PS_THREADS;
+            const int t = item / PS_Q, q = item - t * PS_Q;
+            const int xb = K.x0 - 4 + 4 * q;
+            so[k] = (item < items) ? item * 4 : -1;
+            const bool in = (item < items) && xb >= 0 && xb < W;
+            if (in) {
+              const size_t o = (size_t)ps_reflect_row(K.ys - 2 + t, H) * W + xb;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) u[k].vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
+#pragma unroll
+              for (int c = 0; c < C; ++c) u[k].vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) u[k].vi[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int c = 0; c < C; ++c) u[k].vv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (so[k] >= 0) ps_stage_store<C, CS, SOFTMAX>(Q, u[k], s_img, s_p, so[k]);
+        }
+        if (K.x0 == 0 || K.x0 + PS_TW + 2 > W) {  // mirror the halo columns that lie outside the image
+          __syncthreads();
+          const int nrows = K.n + 4;
+          for (int i = tid; i < nrows * 4 * (3 + CS); i += PS_THREADS) {
+            const int ch = i / (nrows * 4), rem = i - ch * nrows * 4;
+            const int t = rem >> 2, e = rem & 3;
+            const int x = (e < 2) ? e - 2 : W + (e - 2);             // -2, -1, W, W+1
+            const int xm = (e < 2) ? -x : 2 * (W - 1) - x;           // mirror source
+            const int cdst = x - (K.x0 - 4), csrc = xm - (K.x0 - 4);  // staged columns
+            if (cdst >= 2 && cdst < 66 && csrc >= 0 && csrc < PS_PITCH) {
+              float* pl = (ch < 3) ? s_img + ch * PS_PLANE : s_p + (ch - 3) * PS_PLANE;
+              pl[t * PS_PITCH + cdst] = pl[t * PS_PITCH + csrc];
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int it = tid; it < items; it += PS_THREADS) {
+          PsItem<C> u;
+          ps_stage_load_slow<C>(Q, u, img, val, K.x0, K.ys, it);
+          ps_stage_store<C, CS, SOFTMAX>(Q, u, s_img, s_p, it * 4);
+        }
       }
     }
     __syncthreads();
 
-    if (K.border) {  // corr of the band pixels this block owns
-      for (int i = tid; i < 6 * PS_TW; i += PS_THREADS) {  // band rows, lanes along x
-        const int rs = i / PS_TW, cx = i - rs * PS_TW;
-        const int y = rs < 3 ? rs : H - 6 + rs, x = K.x0 + cx;
-        if (y >= K.ys && y < K.ys + K.n && x < xe)
-          ps_corr_item<C>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_r + rs * C * 64 + cx + 2, 64);
+    if (K.border) {  // corr/2 of the band pixels this block owns
+      const int tw = xe - K.x0;
+      const int nlo_r = max(0, min(3, ye) - K.ys), hi_r0 = max(H - 3, K.ys), nhi_r = max(0, ye - hi_r0);
+      for (int i = tid; i < (nlo_r + nhi_r) * tw; i += PS_THREADS) {  // band rows, lanes along x
+        const int k = i / tw, cx = i - k * tw;
+        const int y = k < nlo_r ? K.ys + k : hi_r0 + (k - nlo_r);
+        ps_corr_item<CS>(Q, s_img, s_p, K.ys, K.x0, y, K.x0 + cx, s_corr_r + ps_band_slot(y, H) * CS * 64 + cx + 2, 64);
       }
-      for (int i = tid; i < 6 * K.n; i += PS_THREADS) {  // band columns, lanes along y
-        const int cs = i / K.n, ty = i - cs * K.n;
-        const int x = cs < 3 ? cs : W - 6 + cs, y = K.ys + ty;
-        if (x >= K.x0 && x < xe && ps_band_slot(y, H) < 0)
-          ps_corr_item<C>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_c + cs * C * PS_CAP + ty, PS_CAP);
+      const int yl = max(K.ys, 3), nr = max(0, min(ye, H - 3) - yl);  // rows outside the row band
+      const int nlo_c = max(0, min(3, xe) - K.x0), hi_c0 = max(W - 3, K.x0), nhi_c = max(0, xe - hi_c0);
+      for (int i = tid; i < (nlo_c + nhi_c) * nr; i += PS_THREADS) {  // band columns, lanes along y
+        const int k = i / nr, ty = i - k * nr;
+        const int x = k < nlo_c ? K.x0 + k : hi_c0 + (k - nlo_c), y = yl + ty;
+        ps_corr_item<CS>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_c + ps_band_slot(x, W) * CS * PS_CAP + (y - K.ys), PS_CAP);
       }
       __syncthreads();
     }
@@ -439,44 +517,43 @@ __global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kerne
     const int S = max(2, (K.nc + PS_SEGS - 1) / PS_SEGS);
     const int t0 = seg * S, t1 = min(t0 + S, K.nc);
     if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
-      float A[8][C], Bq[8][C], Cq[8][C];
-      ps_zero<C>(A), ps_zero<C>(Bq), ps_zero<C>(Cq);
-
+      float A[8][CS], Bq[8][CS], Cq[8][CS];
+      ps_zero<CS>(A), ps_zero<CS>(Bq), ps_zero<CS>(Cq);
       // one copy of the step in the instruction stream (the body is ~11 KB); the accumulator rows rotate by moves
 #pragma unroll 1
       for (int s = 0; s < S; ++s) {
         const int t = t0 + s;
         const bool act = t < t1;
-        float pc[4][C], own[4][C];
-        if (act) ps_step<C>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
-        ps_exchange<C>(A, own, strip);
+        float pc[4][CS], own[4][CS];
+        if (act) ps_step<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
+        ps_exchange<CS>(A, own, strip);
         if (act) {
           if (s >= 2) {
-            ps_emit<C, SOFTMAX>(Q, K, t, strip, own, pc, s_corr_r, s_corr_c, lsum);
+            ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_corr_r, s_corr_c, lsum);
           } else if (seg > 0) {
 #pragma unroll
-            for (int c = 0; c < C; ++c)
-              *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * C + c) * 64 + 4 * strip) =
+            for (int c = 0; c < CS; ++c)
+              *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * CS + c) * 64 + 4 * strip) =
                   make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
           }
         }
 #pragma unroll
         for (int w = 0; w < 8; ++w)
 #pragma unroll
-          for (int c = 0; c < C; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
+          for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
       }
       {  // rows t0+S, t0+S+1 belong to the next segment: hand over what this one contributed to them
-        float oy[4][C], oz[4][C];
-        ps_exchange<C>(A, oy, strip);
-        ps_exchange<C>(Bq, oz, strip);
+        float oy[4][CS], oz[4][CS];
+        ps_exchange<CS>(A, oy, strip);
+        ps_exchange<CS>(Bq, oz, strip);
         if (seg < PS_SEGS - 1) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
+          for (int c = 0; c < CS; ++c) {
             if (t0 + S < K.nc)
-              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * C + c) * 64 + 4 * strip) =
+              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip) =
                   make_float4(oy[0][c], oy[1][c], oy[2][c], oy[3][c]);
             if (t0 + S + 1 < K.nc)
-              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * C + c) * 64 + 4 * strip) =
+              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip) =
                   make_float4(oz[0][c], oz[1][c], oz[2][c], oz[3][c]);
           }
         }
@@ -486,21 +563,21 @@ __global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kerne
 
     // ---- the first two rows of segments 1..7: own part + the upper neighbour's carry ----
     if (seg > 0) {
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 2; ++i) {
         const int t = t0 + i;
         if (t < t1) {
-          float G[4][C], pc[4][C];
+          float G[4][CS], pc[4][CS];
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * C + c) * 64 + 4 * strip);
-            const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + i) * C + c) * 64 + 4 * strip);
+          for (int c = 0; c < CS; ++c) {
+            const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
+            const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
             G[0][c] = h.x + k.x, G[1][c] = h.y + k.y, G[2][c] = h.z + k.z, G[3][c] = h.w + k.w;
             const float2 p01 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 2);
             const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
             pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
           }
-          ps_emit<C, SOFTMAX>(Q, K, t, strip, G, pc, s_corr_r, s_corr_c, lsum);
+          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_corr_r, s_corr_c, lsum);
         }
       }
     }
@@ -544,23 +621,17 @@ __global__ void __launch_bounds__(PS_THREADS, PS_CTAS_PER_SM) pairwise_sym_kerne
   }
 }
 
-template <int C>
-static constexpr size_t ps_smem_bytes() {
-  return sizeof(float) * ((size_t)(3 + C) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * C * 64 + 6 * (size_t)C * 64 +
-                          6 * (size_t)C * PS_CAP);
-}
-
 struct PsGeom {
   int n_x, rpc, kpi, grid;
   long long L, R_tot;
 };
 
-static PsGeom ps_geometry(int B, int H, int W) {
+static PsGeom ps_geometry(int B, int H, int W, int ctas_per_sm) {
   PsGeom g;
   g.n_x = (W + PS_TW - 1) / PS_TW;
   g.L = (long long)g.n_x * H;
   g.R_tot = g.L * B;
-  const long long slots = (long long)WSDL_NUM_SMS * PS_CTAS_PER_SM;
+  const long long slots = (long long)WSDL_NUM_SMS * ctas_per_sm;
   long long rpc = (g.R_tot + slots - 1) / slots;
   if (rpc < 6) rpc = 6;  // a block of fewer rows is all warm-up
   g.rpc = (int)(rpc > 0x3fffffff ? 0x3fffffff : rpc);
@@ -570,13 +641,17 @@ static PsGeom ps_geometry(int B, int H, int W) {
 }
 
 size_t ps_workspace_floats(int B, int H, int W) {
-  const PsGeom g = ps_geometry(B, H, W);
-  return (size_t)B * g.kpi;
+  const PsGeom g3 = ps_geometry(B, H, W, 3), g4 = ps_geometry(B, H, W, 4);
+  const size_t a = (size_t)B * g3.kpi, b = (size_t)B * g4.kpi;
+  return a > b ? a : b;
 }
 
 template <int C, bool SOFTMAX>
-static int ps_launch_t(const PsParams& Q, int grid, cudaStream_t s) {
-  constexpr size_t smem = ps_smem_bytes<C>();
+static int ps_launch_t(PsParams& Q, cudaStream_t s) {
+  constexpr size_t smem = PsCfg<C, SOFTMAX>::smem_floats * sizeof(float);
+  const PsGeom g = ps_geometry(Q.p.B, Q.p.H, Q.p.W, PsCfg<C, SOFTMAX>::CTAS);
+  if (g.R_tot / g.rpc > 0x7ffffff0LL) return 1;
+  Q.n_x = g.n_x, Q.rpc = g.rpc, Q.kpi = g.kpi, Q.L = g.L, Q.R_tot = g.R_tot;
   static bool attr_set = false;  // idempotent; a race only repeats the call
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -584,23 +659,20 @@ static int ps_launch_t(const PsParams& Q, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  pairwise_sym_kernel<C, SOFTMAX><<<grid, PS_THREADS, smem, s>>>(Q);
+  pairwise_sym_kernel<C, SOFTMAX><<<g.grid, PS_THREADS, smem, s>>>(Q);
   WSDL_LAUNCH_CHECK();
   return 0;
 }
 
 int ps_launch(const PwParams& P, cudaStream_t s) {
   if (P.pad != 2 || P.C < 1 || P.C > 2 || P.H < 6 || P.W < 6) return 1;
-  const PsGeom g = ps_geometry(P.B, P.H, P.W);
-  if (g.R_tot / g.rpc > 0x7ffffff0LL) return 1;
   PsParams Q;
   Q.p = P;
-  Q.n_x = g.n_x, Q.rpc = g.rpc, Q.kpi = g.kpi, Q.L = g.L, Q.R_tot = g.R_tot;
   Q.vec4_ok = ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0);
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
-  if (P.C == 2) return P.inner_softmax ? ps_launch_t<2, true>(Q, g.grid, s) : ps_launch_t<2, false>(Q, g.grid, s);
-  return P.inner_softmax ? ps_launch_t<1, true>(Q, g.grid, s) : ps_launch_t<1, false>(Q, g.grid, s);
+  if (P.C == 2) return P.inner_softmax ? ps_launch_t<2, true>(Q, s) : ps_launch_t<2, false>(Q, s);
+  return P.inner_softmax ? ps_launch_t<1, true>(Q, s) : ps_launch_t<1, false>(Q, s);
 }
 
 }  // namespace wsdl
