@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+        cmd = [nvcc, *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *os.environ.get("WSDL_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

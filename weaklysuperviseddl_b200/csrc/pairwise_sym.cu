@@ -220,9 +220,11 @@ __device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t
 
 // corr(z)/2 for one band pixel (pairwise.cu derives corr): minus the edges from z into halo positions, plus the
 // edges from real pixels into z's mirror images.  Reads the staged (pre-scaled, reflect-filled) tile.  The partners
-// of each term form rectangles of the 5x5 window, so the loops below visit exactly the pairs that contribute:
+// of each term form rectangles of the 5x5 window:
 //   self   : rows of the window outside the image (all 5 columns), then, for the rows inside, the columns outside;
-//   mirror : the window of the mirror image clipped to the image.
+//   mirror : the window of the mirror image clipped to the image,
+// so the loops visit exactly the pairs that contribute, four at a time (the pass is latency bound: the other warps
+// of the CTA wait for it at a barrier).
 template <int CS>
 __device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_img, const float* s_p, int ys, int x0,
                                             int zy, int zx, float* dst, int dstride) {
@@ -230,9 +232,13 @@ __device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_i
   const int oy = ys - 2, ox = x0 - 4;
   const int so = (zy - oy) * PS_PITCH + (zx - ox);
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
-  float pz[CS], acc[CS];
+  float pz[CS], acc[4][CS];
 #pragma unroll
-  for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
+  for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int c = 0; c < CS; ++c) acc[u][c] = 0.f;
   // rows / columns of z's own window that lie inside the image
   const int ry0 = max(-2, -zy), ry1 = min(2, H - 1 - zy), rx0 = max(-2, -zx), rx1 = min(2, W - 1 - zx);
   const int my = (zy >= 1 && zy <= 2) ? -zy : ((zy >= H - 3 && zy <= H - 2) ? 2 * (H - 1) - zy : zy);  // mirror row or zy
@@ -255,22 +261,30 @@ __device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_i
     }
     if (dy1 < dy0 || dx1 < dx0) continue;
     const float sign = r < 4 ? -0.5f : 0.5f;
+    const int base = (cy - oy) * PS_PITCH + (cx - ox);
+    int dy = dy0, dx = dx0;
 #pragma unroll 1
-    for (int dy = dy0; dy <= dy1; ++dy) {
-      const int srow = (cy + dy - oy) * PS_PITCH + (cx - ox);
-      const float ksy = (float)(dy * dy) * Q.p.ks_unit;
-#pragma unroll 1
-      for (int dx = dx0; dx <= dx1; ++dx) {
-        const int sn = srow + dx;
-        const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
-        const float k = sign * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, fmaf((float)(dx * dx), Q.p.ks_unit, ksy)))));
+    while (dy <= dy1) {
+      int sn[4];
+      float kk[4];
 #pragma unroll
-        for (int c = 0; c < CS; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
+      for (int u = 0; u < 4; ++u) {  // the next four partners in raster order of the rectangle
+        const bool ok = dy <= dy1;
+        sn[u] = ok ? base + dy * PS_PITCH + dx : so;
+        kk[u] = ok ? fmaf((float)(dx * dx + dy * dy), Q.p.ks_unit, 0.f) : -1e30f;  // 2^-inf = 0 past the end
+        if (++dx > dx1) dx = dx0, ++dy;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d0 = i0 - s_img[sn[u]], d1 = i1 - s_img[PS_PLANE + sn[u]], d2 = i2 - s_img[2 * PS_PLANE + sn[u]];
+        const float k = sign * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, kk[u]))));
+#pragma unroll
+        for (int c = 0; c < CS; ++c) acc[u][c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn[u]], acc[u][c]);
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < CS; ++c) dst[c * dstride] = acc[c];
+  for (int c = 0; c < CS; ++c) dst[c * dstride] = (acc[0][c] + acc[1][c]) + (acc[2][c] + acc[3][c]);
 }
 
 // ---- staging: rows ys-2 .. ys+n+1 (reflected), columns x0-4 .. x0+63; softmax and image scale on the way in ----
@@ -366,6 +380,10 @@ struct PsCfg {
       (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * 64 + 6 * (size_t)CS * PS_CAP;
 };
 
+#ifdef WSDL_PS_TRACE
+__device__ unsigned long long ps_trace_buf[8192 * 4];
+#endif
+
 template <int C, bool SOFTMAX>
 __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     pairwise_sym_kernel(const __grid_constant__ PsParams Q) {
@@ -389,6 +407,11 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #pragma unroll
   for (int i = 0; i < 9; ++i) ks[i] = (float)i * Q.p.ks_unit;
 
+#ifdef WSDL_PS_TRACE
+  unsigned long long tr_t0 = 0, tr_t1 = 0;
+  long long tr_corr = 0;
+  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+#endif
   long long r = (long long)blockIdx.x * Q.rpc;
   const long long r_end = min(r + (long long)Q.rpc, Q.R_tot);
   int cur_b = -1;
@@ -409,6 +432,20 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     lsum = 0.f;
   };
 
+  {  // pull this CTA's whole input range towards L2 now; only the first (short) block waits on HBM
+    const int nrows = (int)(r_end - r);
+    for (int i = tid; i < nrows * (3 + C) * 3; i += PS_THREADS) {
+      const int rr = i / ((3 + C) * 3), rem = i - rr * (3 + C) * 3, ch = rem / 3, ln = rem - ch * 3;
+      const long long col = (r + rr) / H;
+      const int y = (int)(r + rr - col * H), b = (int)(col / Q.n_x);
+      const int xa = max((int)(col - (long long)b * Q.n_x) * PS_TW - 4, 0) + 32 * ln;  // 128-byte steps along the row
+      if (xa < W) {
+        const float* base = ch < 3 ? Q.p.images + ((size_t)b * 3 + ch) * plane : Q.p.values + ((size_t)b * C + ch - 3) * plane;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)y * W + xa));
+      }
+    }
+  }
+
   while (r < r_end) {
     PsBlk K;
     {
@@ -416,7 +453,10 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       K.ys = (int)(r - col * H);
       K.b = (int)(col / Q.n_x);
       K.x0 = (int)(col - (long long)K.b * Q.n_x) * PS_TW;
-      K.n = (int)min(min(r_end - r, (long long)(H - K.ys)), (long long)PS_CAP);
+      // this CTA's rows of the column, cut into blocks of at most PS_CAP rows with the short one FIRST: its tile
+      // arrives quickly and its march overlaps the HBM traffic of the L2 prefetch issued above
+      const int rem = (int)min(r_end - r, (long long)(H - K.ys));
+      K.n = rem - ((rem - 1) / PS_CAP) * PS_CAP;
       K.nc = K.n + 2;
     }
     if (K.b != cur_b) {
@@ -441,6 +481,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       if (Q.vec4_ok) {
         // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image; the two halo
         // columns outside are mirrored from shared memory below
+        int t = tid / PS_Q, q = tid - t * PS_Q;  // item = t * PS_Q + q, advanced incrementally below
 #pragma unroll 1
         for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
           PsItem<C> u[3];
@@ -448,7 +489,6 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int item = it + k * PS_THREADS;
-            const int t = item / PS_Q, q = item - t * PS_Q;
             const int xb = K.x0 - 4 + 4 * q;
             so[k] = (item < items) ? item * 4 : -1;
             const bool in = (item < items) && xb >= 0 && xb < W;
@@ -464,6 +504,8 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #pragma unroll
               for (int c = 0; c < C; ++c) u[k].vv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            t += PS_THREADS / PS_Q, q += PS_THREADS % PS_Q;  // next item of this thread: + PS_THREADS
+            if (q >= PS_Q) q -= PS_Q, ++t;
           }
 #pragma unroll
           for (int k = 0; k < 3; ++k)
@@ -495,6 +537,9 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     }
     __syncthreads();
 
+#ifdef WSDL_PS_TRACE
+    long long tr_c0 = clock64();
+#endif
     if (K.border) {  // corr/2 of the band pixels this block owns
       const int tw = xe - K.x0;
       const int nlo_r = max(0, min(3, ye) - K.ys), hi_r0 = max(H - 3, K.ys), nhi_r = max(0, ye - hi_r0);
@@ -505,14 +550,18 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       }
       const int yl = max(K.ys, 3), nr = max(0, min(ye, H - 3) - yl);  // rows outside the row band
       const int nlo_c = max(0, min(3, xe) - K.x0), hi_c0 = max(W - 3, K.x0), nhi_c = max(0, xe - hi_c0);
-      for (int i = tid; i < (nlo_c + nhi_c) * nr; i += PS_THREADS) {  // band columns, lanes along y
-        const int k = i / nr, ty = i - k * nr;
+      const int ncb = nlo_c + nhi_c;
+      for (int i = tid; i < ncb * nr; i += PS_THREADS) {  // band columns: column fastest (few bank conflicts)
+        const int ty = i / ncb, k = i - ty * ncb;
         const int x = k < nlo_c ? K.x0 + k : hi_c0 + (k - nlo_c), y = yl + ty;
         ps_corr_item<CS>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_c + ps_band_slot(x, W) * CS * PS_CAP + (y - K.ys), PS_CAP);
       }
       __syncthreads();
     }
 
+#ifdef WSDL_PS_TRACE
+    if (tid == 0) tr_corr += clock64() - tr_c0;
+#endif
     // ---- march ----
     const int S = max(2, (K.nc + PS_SEGS - 1) / PS_SEGS);
     const int t0 = seg * S, t1 = min(t0 + S, K.nc);
@@ -588,6 +637,14 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   // ---- the last CTA adds the per-(image, CTA) partials in a fixed order, in double ----
   __threadfence();
   __syncthreads();
+#ifdef WSDL_PS_TRACE
+  if (tid == 0 && blockIdx.x < 8192) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
+    ps_trace_buf[blockIdx.x * 4 + 0] = tr_t0, ps_trace_buf[blockIdx.x * 4 + 1] = tr_t1, ps_trace_buf[blockIdx.x * 4 + 2] = smid, ps_trace_buf[blockIdx.x * 4 + 3] = (unsigned long long)tr_corr;
+  }
+#endif
   if (tid == 0) {
     const unsigned n = atomicAdd(Q.p.ticket, 1u);
     s_last = (n == gridDim.x - 1u);
@@ -676,3 +733,9 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
 }
 
 }  // namespace wsdl
+
+#ifdef WSDL_PS_TRACE
+extern "C" int wsdl_ps_trace_read(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, wsdl::ps_trace_buf, (size_t)n * 4 * sizeof(unsigned long long));
+}
+#endif
