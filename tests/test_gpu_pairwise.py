@@ -102,6 +102,16 @@ CASES = [
     (1, 1, 16, 16, 5, 0.1, None, False, True, False),     # single class, no softmax
     (1, 2, 3, 3, 5, 0.1, 5.0, True, True, False),         # smallest legal image for pad=2
     (1, 8, 12, 9, 5, 0.1, None, True, True, False),       # max classes
+    # pair-symmetric kernel (window 5, C <= 2): border multiplicities, band columns, ragged widths
+    (1, 2, 6, 6, 5, 0.1, 1.0, True, True, False),         # smallest image of the sym kernel: every pixel is in a band
+    (1, 2, 6, 6, 5, 0.1, None, False, False, True),
+    (2, 2, 7, 9, 5, 0.1, 0.7, False, False, True),        # small gamma: gamma^4 ~ 0.017
+    (1, 2, 50, 62, 5, 0.1, 5.0, False, False, True),      # right band straddles two column tiles (59 | 60, 61)
+    (1, 2, 50, 61, 5, 0.05, None, True, True, False),     # odd width: scalar staging / stores
+    (2, 1, 41, 63, 5, 0.1, 2.0, False, True, False),      # one stored channel without softmax
+    (1, 2, 100, 120, 5, 0.1, 5.0, True, False, True),     # softmax + spatial term, two full tiles
+    (1, 2, 90, 122, 5, 0.1, 5.0, False, False, True),     # 2-column last tile: its left halo centres feed tile 1
+    (3, 2, 39, 44, 5, 0.05, None, True, True, False),     # several images per CTA range, rows split mid-image
 ]
 
 

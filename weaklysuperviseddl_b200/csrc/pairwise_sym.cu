@@ -22,10 +22,16 @@
 // through shared memory.  A CTA owns a contiguous range of the flattened (image, column tile, row) space, sized on
 // the host so that the launch is exactly one wave; each block pays 2 warm-up rows instead of a halo in y.
 //
-// Borders.  Interior arithmetic treats every reflect-padded position as its own variable holding its mirror
-// source's value, which gives S_all(z) = sum_d k s (p(z) - p~(z+d)).  The true gradient is 2 kappa (2 S_all + corr),
-// corr being non-zero only within 2 px of an image border (see pairwise.cu); border blocks compute corr in a
-// compacted pre-pass, lanes running along the border.
+// Borders.  Reflect padding only changes how often a pair of REAL pixels is counted: grouping the reference's
+// sum over (centre, offset) by the pixel the reflected offset lands on gives
+//     L = kappa sum_{a,b} Wy(ya->yb) Wx(xa->xb) kc(a,b) |p(a)-p(b)|^2,   W(u->v) = sum_{d=-2..2} [r(u+d) == v] gamma^(d^2),
+// kc the colour-only affinity and gamma = exp(-1/(2 sigma_space^2)) (1 for the cut loss).  Away from the borders the
+// unordered pair weight Wy Wx + Wy' Wx' is the interior 2 gamma^|d|^2; within 3 px of a border it is a multiple of it:
+//   * rows: pairs {0,1}, {0,2} (and {H-1,H-2}, {H-1,H-3}) count 3/2, pairs inside row 1 (H-2) count 1+gamma^4.  The
+//     march adds log2 of that factor to the exponent of k, per row step -- no extra instruction per pair;
+//   * columns (and the corners, where the weight is not a product): a short pre-pass over the band pixels of a tile
+//     adds (true weight - weight the march applies) kc (p(a)-p(b)) for the <= 24 partners of each, into shared memory.
+// Positions outside the image are staged with a sentinel colour, so k underflows to exactly 0 for them.
 #include "pairwise.cuh"
 
 namespace wsdl {
@@ -51,6 +57,16 @@ struct PsParams {
   long long L;      // n_x * H: flattened rows per image
   long long R_tot;  // B * L
   float img_scale;  // sqrt(-kc)
+  float g1, g4;     // gamma, gamma^4 (gamma = exp(-1 / (2 sigma_space^2)), 1 without a spatial term)
+  float l32, l1g;   // log2(3/2), log2(1 + gamma^4): row-border pair multiplicities as exponent offsets
+};
+
+constexpr float PS_SENTINEL = 1e15f;  // staged colour (channel 0) of positions outside the image: 2^-(1e30) = 0
+
+struct PsKs {  // exponent offsets of one row step: spatial term + row-border multiplicity
+  float a1, a4;           // partner in the same row, dx^2 = 1, 4
+  float b0, b1, b4;       // one row down,  dx^2 = 0, 1, 4
+  float c0, c1, c4;       // two rows down
 };
 
 template <int C>
@@ -94,7 +110,7 @@ __device__ __forceinline__ void ps_pair(float (&ga)[C], float (&gb)[C], const Ps
 // All 12 forward pairs of the 4 centres of row t (accumulator X), partners in rows t (X), t+1 (Y), t+2 (Z).
 template <int C>
 __device__ __forceinline__ void ps_step(float (&X)[8][C], float (&Y)[8][C], float (&Z)[8][C], float (&pc)[4][C],
-                                        const float* s_img, const float* s_p, int off, const float (&ks)[9]) {
+                                        const float* s_img, const float* s_p, int off, const PsKs& ks) {
   PsWin<C> c;
   ps_load<C>(c, s_img, s_p, off);
 #pragma unroll
@@ -103,20 +119,22 @@ __device__ __forceinline__ void ps_step(float (&X)[8][C], float (&Y)[8][C], floa
     for (int cc = 0; cc < C; ++cc) pc[j][cc] = c.p[cc][2 + j];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    ps_pair<C>(X[2 + j], X[3 + j], c, 2 + j, c, 3 + j, ks[1]);
-    ps_pair<C>(X[2 + j], X[4 + j], c, 2 + j, c, 4 + j, ks[4]);
+    ps_pair<C>(X[2 + j], X[3 + j], c, 2 + j, c, 3 + j, ks.a1);
+    ps_pair<C>(X[2 + j], X[4 + j], c, 2 + j, c, 4 + j, ks.a4);
   }
   PsWin<C> n;
   ps_load<C>(n, s_img, s_p, off + PS_PITCH);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) ps_pair<C>(X[2 + j], Y[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks[dx * dx + 1]);
+    for (int dx = -2; dx <= 2; ++dx)
+      ps_pair<C>(X[2 + j], Y[2 + j + dx], c, 2 + j, n, 2 + j + dx, dx == 0 ? ks.b0 : (dx * dx == 1 ? ks.b1 : ks.b4));
   ps_load<C>(n, s_img, s_p, off + 2 * PS_PITCH);
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int dx = -2; dx <= 2; ++dx) ps_pair<C>(X[2 + j], Z[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks[dx * dx + 4]);
+    for (int dx = -2; dx <= 2; ++dx)
+      ps_pair<C>(X[2 + j], Z[2 + j + dx], c, 2 + j, n, 2 + j + dx, dx == 0 ? ks.c0 : (dx * dx == 1 ? ks.c1 : ks.c4));
 }
 
 // A finished accumulator row: the two columns either side of the strip belong to the neighbouring lanes.
@@ -137,19 +155,19 @@ __device__ __forceinline__ void ps_exchange(const float (&X)[8][C], float (&own)
 
 struct PsBlk {
   int b, x0, ys, n, nc;
-  bool border;
-  float scale2;  // 4 kappa * upstream gradient: g = scale2 * (G + corr/2)
+  bool xband;    // the tile owns pixels within 3 columns of the left / right image border
+  float scale2;  // 4 kappa * upstream gradient: g = scale2 * (G + xfix)
 };
 
-// corr slot of a coordinate: 0..2 for the low band, 3..5 for the high band, -1 outside (needs n >= 6)
+// band slot of a coordinate: 0..2 for the low band, 3..5 for the high band, -1 outside (needs n >= 6)
 __device__ __forceinline__ int ps_band_slot(int v, int n) { return v <= 2 ? v : (v >= n - 3 ? v - (n - 6) : -1); }
 
-// Gradient of 4 finished pixels of centre row t: dL/dp = scale2 (G + corr/2), softmax backward, store; the loss is
-// 2 kappa sum (p - 1/2) (G + corr/2), accumulated without its factor.  C = classes, CS = stored channels.
+// Gradient of 4 finished pixels of centre row t: dL/dp = scale2 (G + xfix), softmax backward, store; the loss is
+// 2 kappa sum (p - 1/2) (G + xfix), accumulated without its factor.  C = classes, CS = stored channels.
 template <int C, int CS, bool SOFTMAX>
 __device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t, int strip, int okmask,
-                                        const float (&G)[4][CS], const float (&pc)[4][CS], const float* s_corr_r,
-                                        const float* s_corr_c, float& lsum) {
+                                        const float (&G)[4][CS], const float (&pc)[4][CS], const float* s_xfix,
+                                        float& lsum) {
   const int H = Q.p.H, W = Q.p.W;
   const int y = K.ys - 2 + t;
   const int xs = K.x0 - 2 + 4 * strip;  // image column of j = 0
@@ -158,18 +176,14 @@ __device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int c = 0; c < CS; ++c) g[j][c] = G[j][c];
-  if (K.border) {  // block-uniform
-    const int rs = ps_band_slot(y, H);
+  if (K.xband) {  // block-uniform
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if ((okmask >> j) & 1) {
         const int cs = ps_band_slot(xs + j, W);
-        if (rs >= 0) {
+        if (cs >= 0) {
 #pragma unroll
-          for (int c = 0; c < CS; ++c) g[j][c] += s_corr_r[(rs * CS + c) * 64 + 4 * strip + j];
-        } else if (cs >= 0) {
-#pragma unroll
-          for (int c = 0; c < CS; ++c) g[j][c] += s_corr_c[(cs * CS + c) * PS_CAP + (t - 2)];
+          for (int c = 0; c < CS; ++c) g[j][c] += s_xfix[(cs * CS + c) * PS_CAP + (t - 2)];
         }
       }
   }
@@ -218,76 +232,71 @@ __device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t
   }
 }
 
-// corr(z)/2 for one band pixel (pairwise.cu derives corr): minus the edges from z into halo positions, plus the
-// edges from real pixels into z's mirror images.  Reads the staged (pre-scaled, reflect-filled) tile.  The partners
-// of each term form rectangles of the 5x5 window:
-//   self   : rows of the window outside the image (all 5 columns), then, for the rows inside, the columns outside;
-//   mirror : the window of the mirror image clipped to the image,
-// so the loops visit exactly the pairs that contribute, four at a time (the pass is latency bound: the other warps
-// of the CTA wait for it at a barrier).
+// gamma^(k^2) for k = 0, 1, 2
+__device__ __forceinline__ float ps_gpow(int k, float g1, float g4) { return k == 0 ? 1.f : (k == 1 ? g1 : g4); }
+
+// W(u -> v) = sum_{d=-2..2} [reflect(u + d) == v] gamma^(d^2) for u inside [0, n), n >= 6; 0 for v outside (closed
+// form of pairwise.cu's axis_multiplicity for pad 2).
+__device__ __forceinline__ float ps_w1d(int u, int v, int n, float g1, float g4) {
+  if (v < 0 || v >= n) return 0.f;
+  const int d = abs(v - u), s = u + v, e = 2 * (n - 1) - s;
+  float w = d <= 2 ? ps_gpow(d, g1, g4) : 0.f;
+  if (v >= 1 && s <= 2) w += ps_gpow(s, g1, g4);      // offset -s lands on -v, which reflects to v
+  if (v <= n - 2 && e <= 2) w += ps_gpow(e, g1, g4);  // offset +e lands on 2(n-1) - v
+  return w;
+}
+
+// multiplicity the march applies to a pair of rows (relative to the interior 2 gamma^|d|^2): see ps_row_ks
+__device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
+  const int lo = min(ya, yb), d = abs(ya - yb);
+  if (d == 0) return (lo == 1 || lo == H - 2) ? 1.f + g4 : 1.f;
+  return (lo == 0 || lo + d == H - 1) ? 1.5f : 1.f;
+}
+
+// xfix(a) for one band pixel a = (zy, zx): sum over its in-image window partners b of
+// (true pair weight - weight applied by the march) / 2 * kc(a,b) (p(a) - p(b)).  Reads the staged tile.
 template <int CS>
-__device__ __forceinline__ void ps_corr_item(const PsParams& Q, const float* s_img, const float* s_p, int ys, int x0,
+__device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_img, const float* s_p, int ys, int x0,
                                             int zy, int zx, float* dst, int dstride) {
   const int H = Q.p.H, W = Q.p.W;
-  const int oy = ys - 2, ox = x0 - 4;
-  const int so = (zy - oy) * PS_PITCH + (zx - ox);
+  const float g1 = Q.g1, g4 = Q.g4;
+  const int so = (zy - (ys - 2)) * PS_PITCH + (zx - (x0 - 4));
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
-  float pz[CS], acc[4][CS];
+  float pz[CS], acc[CS];
 #pragma unroll
-  for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so];
+  for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
+  float wxf[5], wxb[5];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int c = 0; c < CS; ++c) acc[u][c] = 0.f;
-  // rows / columns of z's own window that lie inside the image
-  const int ry0 = max(-2, -zy), ry1 = min(2, H - 1 - zy), rx0 = max(-2, -zx), rx1 = min(2, W - 1 - zx);
-  const int my = (zy >= 1 && zy <= 2) ? -zy : ((zy >= H - 3 && zy <= H - 2) ? 2 * (H - 1) - zy : zy);  // mirror row or zy
-  const int mx = (zx >= 1 && zx <= 2) ? -zx : ((zx >= W - 3 && zx <= W - 2) ? 2 * (W - 1) - zx : zx);
+  for (int j = 0; j < 5; ++j) {
+    const int xb = zx + j - 2;
+    wxf[j] = ps_w1d(zx, xb, W, g1, g4);
+    wxb[j] = (xb >= 0 && xb < W) ? ps_w1d(xb, zx, W, g1, g4) : 0.f;
+  }
 #pragma unroll 1
-  for (int r = 0; r < 7; ++r) {
-    // r = 0,1: self, window rows above / below the image;  2,3: self, columns left / right of the image (rows inside)
-    // r = 4: mirror in y;  5: mirror in x;  6: mirror in both
-    int cy = zy, cx = zx, dy0, dy1, dx0, dx1;
-    if (r == 0) dy0 = -2, dy1 = ry0 - 1, dx0 = -2, dx1 = 2;
-    else if (r == 1) dy0 = ry1 + 1, dy1 = 2, dx0 = -2, dx1 = 2;
-    else if (r == 2) dy0 = ry0, dy1 = ry1, dx0 = -2, dx1 = rx0 - 1;
-    else if (r == 3) dy0 = ry0, dy1 = ry1, dx0 = rx1 + 1, dx1 = 2;
-    else {
-      cy = (r == 5) ? zy : my;
-      cx = (r == 4) ? zx : mx;
-      const bool valid = (r == 4) ? (my != zy) : (r == 5 ? (mx != zx) : (my != zy && mx != zx));
-      dy0 = max(-2, -cy), dy1 = valid ? min(2, H - 1 - cy) : -3;
-      dx0 = max(-2, -cx), dx1 = min(2, W - 1 - cx);
-    }
-    if (dy1 < dy0 || dx1 < dx0) continue;
-    const float sign = r < 4 ? -0.5f : 0.5f;
-    const int base = (cy - oy) * PS_PITCH + (cx - ox);
-    int dy = dy0, dx = dx0;
-#pragma unroll 1
-    while (dy <= dy1) {
-      int sn[4];
-      float kk[4];
+  for (int i = 0; i < 5; ++i) {
+    const int yb = zy + i - 2;
+    if (yb < 0 || yb >= H) continue;
+    const float wyf = ps_w1d(zy, yb, H, g1, g4), wyb = ps_w1d(yb, zy, H, g1, g4);
+    const float wm = 2.f * ps_gpow(abs(i - 2), g1, g4) * ps_row_mult(zy, yb, H, g4);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // the next four partners in raster order of the rectangle
-        const bool ok = dy <= dy1;
-        sn[u] = ok ? base + dy * PS_PITCH + dx : so;
-        kk[u] = ok ? fmaf((float)(dx * dx + dy * dy), Q.p.ks_unit, 0.f) : -1e30f;  // 2^-inf = 0 past the end
-        if (++dx > dx1) dx = dx0, ++dy;
-      }
+    for (int j = 0; j < 5; ++j) {
+      const float wmj = wm * ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
+      const float diff = 0.5f * (fmaf(wyf, wxf[j], wyb * wxb[j]) - wmj);
+      // self / partner outside the image (k is 0 in the march too) / the weight the march applies is the true one
+      if ((i == 2 && j == 2) || wxf[j] == 0.f || fabsf(diff) <= 1e-6f * wmj) continue;
+      const int sn = so + (i - 2) * PS_PITCH + (j - 2);
+      const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+      const float k = diff * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0)));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float d0 = i0 - s_img[sn[u]], d1 = i1 - s_img[PS_PLANE + sn[u]], d2 = i2 - s_img[2 * PS_PLANE + sn[u]];
-        const float k = sign * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, kk[u]))));
-#pragma unroll
-        for (int c = 0; c < CS; ++c) acc[u][c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn[u]], acc[u][c]);
-      }
+      for (int c = 0; c < CS; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
     }
   }
 #pragma unroll
-  for (int c = 0; c < CS; ++c) dst[c * dstride] = (acc[0][c] + acc[1][c]) + (acc[2][c] + acc[3][c]);
+  for (int c = 0; c < CS; ++c) dst[c * dstride] = acc[c];
 }
 
-// ---- staging: rows ys-2 .. ys+n+1 (reflected), columns x0-4 .. x0+63; softmax and image scale on the way in ----
+// ---- staging: rows ys-2 .. ys+n+1, columns x0-4 .. x0+63; softmax and image scale on the way in; positions outside
+// the image get the sentinel colour (and p = 0) ----
 template <int C>
 struct PsItem {
   float4 vi[3];
@@ -295,13 +304,20 @@ struct PsItem {
 };
 
 template <int C, int CS, bool SOFTMAX>
-__device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C>& it, float* s_img, float* s_p,
-                                               int so) {
+__device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C>& it, unsigned outside, float* s_img,
+                                               float* s_p, int so) {
   const float sc = Q.img_scale;
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
-    *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) =
-        make_float4(it.vi[c].x * sc, it.vi[c].y * sc, it.vi[c].z * sc, it.vi[c].w * sc);
+  for (int c = 0; c < 3; ++c) {
+    float4 o = make_float4(it.vi[c].x * sc, it.vi[c].y * sc, it.vi[c].z * sc, it.vi[c].w * sc);
+    if (c == 0 && outside) {  // bit e: element e lies outside the image
+      if (outside & 1) o.x = PS_SENTINEL;
+      if (outside & 2) o.y = PS_SENTINEL;
+      if (outside & 4) o.z = PS_SENTINEL;
+      if (outside & 8) o.w = PS_SENTINEL;
+    }
+    *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = o;
+  }
   float v[C][4];
 #pragma unroll
   for (int c = 0; c < C; ++c) v[c][0] = it.vv[c].x, v[c][1] = it.vv[c].y, v[c][2] = it.vv[c].z, v[c][3] = it.vv[c].w;
@@ -330,33 +346,35 @@ __device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C
     *reinterpret_cast<float4*>(s_p + c * PS_PLANE + so) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
 }
 
-__device__ __forceinline__ int ps_reflect_row(int y, int H) {
-  y = y < 0 ? -y : y;
-  y = y >= H ? 2 * (H - 1) - y : y;
-  return min(max(y, 0), H - 1);
+template <int C>
+__device__ __forceinline__ void ps_item_outside(PsItem<C>& it) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) it.vi[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < C; ++c) it.vv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// any W / alignment: element-wise loads with the reflection applied to the address
+// any W / alignment: element-wise loads
 template <int C>
-__device__ __noinline__ void ps_stage_load_slow(const PsParams& Q, PsItem<C>& it, const float* img, const float* val,
-                                                int x0, int ys, int item) {
+__device__ __noinline__ void ps_stage_load_slow(const PsParams& Q, PsItem<C>& it, unsigned& outside, const float* img,
+                                                const float* val, int x0, int ys, int item) {
   const int H = Q.p.H, W = Q.p.W;
   const size_t plane = (size_t)H * W;
   const int t = item / PS_Q, q = item - t * PS_Q;
-  const int y = ps_reflect_row(ys - 2 + t, H);
+  const int y = ys - 2 + t;
   const int xb = x0 - 4 + 4 * q;
   float vi[3][4], vv[C][4];
+  outside = 0;
 #pragma unroll 1
   for (int e = 0; e < 4; ++e) {
-    int x = xb + e;
-    x = x < 0 ? -x : x;
-    x = x >= W ? 2 * (W - 1) - x : x;
-    x = min(max(x, 0), W - 1);  // pad columns past the halo: any valid address, never used for owned results
-    const size_t o = (size_t)y * W + x;
+    const int x = xb + e;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    const size_t o = in ? (size_t)y * W + x : 0;
+    if (!in) outside |= 1u << e;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) vi[c][e] = __ldg(img + c * plane + o);
+    for (int c = 0; c < 3; ++c) vi[c][e] = in ? __ldg(img + c * plane + o) : 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) vv[c][e] = __ldg(val + c * plane + o);
+    for (int c = 0; c < C; ++c) vv[c][e] = in ? __ldg(val + c * plane + o) : 0.f;
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) it.vi[c] = make_float4(vi[c][0], vi[c][1], vi[c][2], vi[c][3]);
@@ -377,7 +395,7 @@ struct PsCfg {
   static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // stored channels
   static constexpr int CTAS = CS == 1 ? 4 : 3;            // resident CTAs per SM (shared memory and registers)
   static constexpr size_t smem_floats =
-      (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * 64 + 6 * (size_t)CS * PS_CAP;
+      (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP;
 };
 
 #ifdef WSDL_PS_TRACE
@@ -393,8 +411,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   float* s_p = s_img + 3 * PS_PLANE;                        // [CS][PS_ROWS][PS_PITCH]
   float* s_head = s_p + CS * PS_PLANE;                      // [7][2][CS][64]: first two rows of segments 1..7, own part
   float* s_carry = s_head + (PS_SEGS - 1) * 2 * CS * 64;    // [7][2][CS][64]: the same rows, upper neighbour's part
-  float* s_corr_r = s_carry + (PS_SEGS - 1) * 2 * CS * 64;  // [6][CS][64]: corr/2 of the band rows
-  float* s_corr_c = s_corr_r + 6 * CS * 64;                 // [6][CS][PS_CAP]: corr/2 of the band columns
+  float* s_xfix = s_carry + (PS_SEGS - 1) * 2 * CS * 64;    // [6][CS][PS_CAP]: weight correction of the band columns
   __shared__ float s_red[PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
   __shared__ int s_last;
@@ -403,9 +420,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   const int seg = warp * 2 + (lane >> 4), strip = lane & 15;
   const int H = Q.p.H, W = Q.p.W;
   const size_t plane = (size_t)H * W;
-  float ks[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) ks[i] = (float)i * Q.p.ks_unit;
+  const float ksu = Q.p.ks_unit;
 
 #ifdef WSDL_PS_TRACE
   unsigned long long tr_t0 = 0, tr_t1 = 0;
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       cur_b = K.b;
     }
     const int xe = min(K.x0 + PS_TW, W), ye = K.ys + K.n;  // owned pixels [x0, xe) x [ys, ye)
-    K.border = (K.x0 == 0) || (xe - 1 >= W - 3) || (K.ys <= 2) || (ye - 1 >= H - 3);
+    K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
     K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
     int okmask = 0;  // which of this thread's 4 columns are owned pixels of the image
 #pragma unroll
@@ -479,59 +494,43 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       const float* val = Q.p.values + (size_t)K.b * C * plane;
       const int items = (K.n + 4) * PS_Q;
       if (Q.vec4_ok) {
-        // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image; the two halo
-        // columns outside are mirrored from shared memory below
+        // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image
         int t = tid / PS_Q, q = tid - t * PS_Q;  // item = t * PS_Q + q, advanced incrementally below
 #pragma unroll 1
         for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
           PsItem<C> u[3];
           int so[3];
+          unsigned out[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int item = it + k * PS_THREADS;
-            const int xb = K.x0 - 4 + 4 * q;
+            const int xb = K.x0 - 4 + 4 * q, y = K.ys - 2 + t;
             so[k] = (item < items) ? item * 4 : -1;
-            const bool in = (item < items) && xb >= 0 && xb < W;
+            const bool in = (item < items) && xb >= 0 && xb < W && y >= 0 && y < H;
+            out[k] = in ? 0u : 15u;
             if (in) {
-              const size_t o = (size_t)ps_reflect_row(K.ys - 2 + t, H) * W + xb;
+              const size_t o = (size_t)y * W + xb;
 #pragma unroll
               for (int c = 0; c < 3; ++c) u[k].vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
 #pragma unroll
               for (int c = 0; c < C; ++c) u[k].vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
             } else {
-#pragma unroll
-              for (int c = 0; c < 3; ++c) u[k].vi[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int c = 0; c < C; ++c) u[k].vv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+              ps_item_outside<C>(u[k]);
             }
             t += PS_THREADS / PS_Q, q += PS_THREADS % PS_Q;  // next item of this thread: + PS_THREADS
             if (q >= PS_Q) q -= PS_Q, ++t;
           }
 #pragma unroll
           for (int k = 0; k < 3; ++k)
-            if (so[k] >= 0) ps_stage_store<C, CS, SOFTMAX>(Q, u[k], s_img, s_p, so[k]);
-        }
-        if (K.x0 == 0 || K.x0 + PS_TW + 2 > W) {  // mirror the halo columns that lie outside the image
-          __syncthreads();
-          const int nrows = K.n + 4;
-          for (int i = tid; i < nrows * 4 * (3 + CS); i += PS_THREADS) {
-            const int ch = i / (nrows * 4), rem = i - ch * nrows * 4;
-            const int t = rem >> 2, e = rem & 3;
-            const int x = (e < 2) ? e - 2 : W + (e - 2);             // -2, -1, W, W+1
-            const int xm = (e < 2) ? -x : 2 * (W - 1) - x;           // mirror source
-            const int cdst = x - (K.x0 - 4), csrc = xm - (K.x0 - 4);  // staged columns
-            if (cdst >= 2 && cdst < 66 && csrc >= 0 && csrc < PS_PITCH) {
-              float* pl = (ch < 3) ? s_img + ch * PS_PLANE : s_p + (ch - 3) * PS_PLANE;
-              pl[t * PS_PITCH + cdst] = pl[t * PS_PITCH + csrc];
-            }
-          }
+            if (so[k] >= 0) ps_stage_store<C, CS, SOFTMAX>(Q, u[k], out[k], s_img, s_p, so[k]);
         }
       } else {
 #pragma unroll 1
         for (int it = tid; it < items; it += PS_THREADS) {
           PsItem<C> u;
-          ps_stage_load_slow<C>(Q, u, img, val, K.x0, K.ys, it);
-          ps_stage_store<C, CS, SOFTMAX>(Q, u, s_img, s_p, it * 4);
+          unsigned out;
+          ps_stage_load_slow<C>(Q, u, out, img, val, K.x0, K.ys, it);
+          ps_stage_store<C, CS, SOFTMAX>(Q, u, out, s_img, s_p, it * 4);
         }
       }
     }
@@ -540,21 +539,13 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #ifdef WSDL_PS_TRACE
     long long tr_c0 = clock64();
 #endif
-    if (K.border) {  // corr/2 of the band pixels this block owns
-      const int tw = xe - K.x0;
-      const int nlo_r = max(0, min(3, ye) - K.ys), hi_r0 = max(H - 3, K.ys), nhi_r = max(0, ye - hi_r0);
-      for (int i = tid; i < (nlo_r + nhi_r) * tw; i += PS_THREADS) {  // band rows, lanes along x
-        const int k = i / tw, cx = i - k * tw;
-        const int y = k < nlo_r ? K.ys + k : hi_r0 + (k - nlo_r);
-        ps_corr_item<CS>(Q, s_img, s_p, K.ys, K.x0, y, K.x0 + cx, s_corr_r + ps_band_slot(y, H) * CS * 64 + cx + 2, 64);
-      }
-      const int yl = max(K.ys, 3), nr = max(0, min(ye, H - 3) - yl);  // rows outside the row band
-      const int nlo_c = max(0, min(3, xe) - K.x0), hi_c0 = max(W - 3, K.x0), nhi_c = max(0, xe - hi_c0);
-      const int ncb = nlo_c + nhi_c;
-      for (int i = tid; i < ncb * nr; i += PS_THREADS) {  // band columns: column fastest (few bank conflicts)
+    if (K.xband) {  // weight correction of the band pixels this block owns (columns 0..2 and W-3..W-1)
+      const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
+      const int ncb = nlo + nhi;
+      for (int i = tid; i < ncb * K.n; i += PS_THREADS) {  // column fastest
         const int ty = i / ncb, k = i - ty * ncb;
-        const int x = k < nlo_c ? K.x0 + k : hi_c0 + (k - nlo_c), y = yl + ty;
-        ps_corr_item<CS>(Q, s_img, s_p, K.ys, K.x0, y, x, s_corr_c + ps_band_slot(x, W) * CS * PS_CAP + (y - K.ys), PS_CAP);
+        const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo);
+        ps_xfix_item<CS>(Q, s_img, s_p, K.ys, K.x0, K.ys + ty, x, s_xfix + ps_band_slot(x, W) * CS * PS_CAP + ty, PS_CAP);
       }
       __syncthreads();
     }
@@ -574,11 +565,22 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
         const int t = t0 + s;
         const bool act = t < t1;
         float pc[4][CS], own[4][CS];
-        if (act) ps_step<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
+        if (act) {
+          // exponent offsets of this centre row: spatial term + multiplicity of the row pairs at the top / bottom border
+          const int y = K.ys - 2 + t;
+          const float l0 = (y == 1 || y == H - 2) ? Q.l1g : 0.f;
+          const float l1 = (y == 0 || y == H - 2) ? Q.l32 : 0.f;
+          const float l2 = (y == 0 || y == H - 3) ? Q.l32 : 0.f;
+          PsKs ks;
+          ks.a1 = ksu + l0, ks.a4 = 4.f * ksu + l0;
+          ks.b0 = ksu + l1, ks.b1 = 2.f * ksu + l1, ks.b4 = 5.f * ksu + l1;
+          ks.c0 = 4.f * ksu + l2, ks.c1 = 5.f * ksu + l2, ks.c4 = 8.f * ksu + l2;
+          ps_step<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
+        }
         ps_exchange<CS>(A, own, strip);
         if (act) {
           if (s >= 2) {
-            ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_corr_r, s_corr_c, lsum);
+            ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_xfix, lsum);
           } else if (seg > 0) {
 #pragma unroll
             for (int c = 0; c < CS; ++c)
@@ -626,7 +628,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
             const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
             pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
           }
-          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_corr_r, s_corr_c, lsum);
+          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_xfix, lsum);
         }
       }
     }
@@ -728,6 +730,8 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   Q.vec4_ok = ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0);
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
+  Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
+  Q.l32 = log2f(1.5f), Q.l1g = log2f(1.f + Q.g4);
   if (P.C == 2) return P.inner_softmax ? ps_launch_t<2, true>(Q, s) : ps_launch_t<2, false>(Q, s);
   return P.inner_softmax ? ps_launch_t<1, true>(Q, s) : ps_launch_t<1, false>(Q, s);
 }
