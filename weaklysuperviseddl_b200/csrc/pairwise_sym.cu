@@ -19,8 +19,9 @@
 // to the 2 columns either side of its strip go to the neighbouring lanes by warp shuffle when a row completes.
 // 16 strips (a half warp) span the 64 staged columns of a tile (60 owned + 2 halo each side), 8 segments span the
 // block's rows; the first two rows of a segment are completed by the two rows its upper neighbour carries over,
-// through shared memory.  A CTA owns a contiguous range of the flattened (image, column tile, row) space, sized on
-// the host so that the launch is exactly one wave; each block pays 2 warm-up rows instead of a halo in y.
+// through shared memory.  A CTA is one block: up to 38 rows of one 60-column tile of one image (grid = row blocks x
+// column tiles x images, a few CTAs per SM slot so that the staging of one overlaps the march of the others); it
+// pays 2 warm-up rows instead of a halo in y.
 //
 // Borders.  Reflect padding only changes how often a pair of REAL pixels is counted: grouping the reference's
 // sum over (centre, offset) by the pixel the reflected offset lands on gives
@@ -50,12 +51,9 @@ constexpr int PS_PLANE = PS_ROWS * PS_PITCH;
 struct PsParams {
   PwParams p;
   int n_x;          // column tiles per image
-  int rpc;          // flattened rows per CTA
-  int kpi;          // partial-sum slots per image
+  int nb;           // row blocks per column tile; grid = (nb, n_x, B)
   int vec4_ok;      // W % 4 == 0 and 16-byte aligned inputs: float4 staging loads
   int vec2_ok;      // W % 2 == 0 and 8-byte aligned gradient: float2 stores
-  long long L;      // n_x * H: flattened rows per image
-  long long R_tot;  // B * L
   float img_scale;  // sqrt(-kc)
   float g1, g4;     // gamma, gamma^4 (gamma = exp(-1 / (2 sigma_space^2)), 1 without a spatial term)
   float l32, l1g;   // log2(3/2), log2(1 + gamma^4): row-border pair multiplicities as exponent offsets
@@ -254,11 +252,12 @@ __device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
 }
 
 // xfix(a) for one band pixel a = (zy, zx): sum over its in-image window partners b of
-// (true pair weight - weight applied by the march) / 2 * kc(a,b) (p(a) - p(b)).  Reads the staged tile.
+// (true pair weight - weight applied by the march) / 2 * kc(a,b) (p(a) - p(b)).  Reads the staged tile; s_wx holds
+// Wx(zx -> zx + j - 2) and Wx(zx + j - 2 -> zx), j = 0..4, for the band slot of zx.
 template <int CS>
-__device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_img, const float* s_p, int ys, int x0,
-                                            int zy, int zx, float* dst, int dstride) {
-  const int H = Q.p.H, W = Q.p.W;
+__device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_img, const float* s_p, const float* s_wx,
+                                            int ys, int x0, int zy, int zx, float* dst, int dstride) {
+  const int H = Q.p.H;
   const float g1 = Q.g1, g4 = Q.g4;
   const int so = (zy - (ys - 2)) * PS_PITCH + (zx - (x0 - 4));
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
@@ -267,23 +266,31 @@ __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_i
   for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
   float wxf[5], wxb[5];
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const int xb = zx + j - 2;
-    wxf[j] = ps_w1d(zx, xb, W, g1, g4);
-    wxb[j] = (xb >= 0 && xb < W) ? ps_w1d(xb, zx, W, g1, g4) : 0.f;
+  for (int j = 0; j < 5; ++j) wxf[j] = s_wx[j], wxb[j] = s_wx[5 + j];
+  // row weights: forward, backward, and what the march applies (2 gamma^dy^2 times its row multiplicity)
+  float wyf[5], wyb[5], wym[5];
+  if (zy >= 5 && zy <= H - 6) {  // every partner row is clear of the row bands
+#pragma unroll
+    for (int i = 0; i < 5; ++i) wyf[i] = wyb[i] = ps_gpow(i < 2 ? 2 - i : i - 2, g1, g4), wym[i] = 2.f * wyf[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int yb = zy + i - 2;
+      const bool in = yb >= 0 && yb < H;
+      wyf[i] = in ? ps_w1d(zy, yb, H, g1, g4) : 0.f;
+      wyb[i] = in ? ps_w1d(yb, zy, H, g1, g4) : 0.f;
+      wym[i] = in ? 2.f * ps_gpow(i < 2 ? 2 - i : i - 2, g1, g4) * ps_row_mult(zy, yb, H, g4) : 0.f;
+    }
   }
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 5; ++i) {
-    const int yb = zy + i - 2;
-    if (yb < 0 || yb >= H) continue;
-    const float wyf = ps_w1d(zy, yb, H, g1, g4), wyb = ps_w1d(yb, zy, H, g1, g4);
-    const float wm = 2.f * ps_gpow(abs(i - 2), g1, g4) * ps_row_mult(zy, yb, H, g4);
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      const float wmj = wm * ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
-      const float diff = 0.5f * (fmaf(wyf, wxf[j], wyb * wxb[j]) - wmj);
-      // self / partner outside the image (k is 0 in the march too) / the weight the march applies is the true one
-      if ((i == 2 && j == 2) || wxf[j] == 0.f || fabsf(diff) <= 1e-6f * wmj) continue;
+      if (i == 2 && j == 2) continue;
+      const float wmj = wym[i] * ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
+      const float diff = 0.5f * (fmaf(wyf[i], wxf[j], wyb[i] * wxb[j]) - wmj);
+      // partner outside the image (k is 0 in the march too) / the weight the march applies is the true one
+      if (wxf[j] == 0.f || wyf[i] == 0.f || fabsf(diff) <= 1e-6f * wmj) continue;
       const int sn = so + (i - 2) * PS_PITCH + (j - 2);
       const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
       const float k = diff * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0)));
@@ -394,14 +401,26 @@ template <int C, bool SOFTMAX>
 struct PsCfg {
   static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // stored channels
   static constexpr int CTAS = CS == 1 ? 4 : 3;            // resident CTAs per SM (shared memory and registers)
-  static constexpr size_t smem_floats =
-      (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP;
+  static constexpr size_t smem_floats = (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 +
+                                        6 * (size_t)CS * PS_CAP + 6 * 10;
 };
 
-#ifdef WSDL_PS_TRACE
-__device__ unsigned long long ps_trace_buf[8192 * 4];
+#ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_ctas.py): per-CTA timestamps of the phase boundaries
+__device__ unsigned long long ps_trace_buf[8192 * 8];
+#define PS_TR(slot)                                                                   \
+  do {                                                                                \
+    const unsigned cta__ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+    if (threadIdx.x == 0 && cta__ < 8192) {                                           \
+      unsigned long long t__;                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                         \
+      ps_trace_buf[cta__ * 8 + (slot)] = t__;                                         \
+    }                                                                                 \
+  } while (0)
+#else
+#define PS_TR(slot)
 #endif
 
+// One CTA = one block: rows [ys, ys + n) of one 60-column tile of one image, n <= PS_CAP.
 template <int C, bool SOFTMAX>
 __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     pairwise_sym_kernel(const __grid_constant__ PsParams Q) {
@@ -412,6 +431,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   float* s_head = s_p + CS * PS_PLANE;                      // [7][2][CS][64]: first two rows of segments 1..7, own part
   float* s_carry = s_head + (PS_SEGS - 1) * 2 * CS * 64;    // [7][2][CS][64]: the same rows, upper neighbour's part
   float* s_xfix = s_carry + (PS_SEGS - 1) * 2 * CS * 64;    // [6][CS][PS_CAP]: weight correction of the band columns
+  float* s_wx = s_xfix + 6 * CS * PS_CAP;                   // [6][2][5]: column weights of the 6 band slots
   __shared__ float s_red[PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
   __shared__ int s_last;
@@ -421,18 +441,178 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   const int H = Q.p.H, W = Q.p.W;
   const size_t plane = (size_t)H * W;
   const float ksu = Q.p.ks_unit;
+  PS_TR(0);
 
-#ifdef WSDL_PS_TRACE
-  unsigned long long tr_t0 = 0, tr_t1 = 0;
-  long long tr_corr = 0;
-  if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
-#endif
-  long long r = (long long)blockIdx.x * Q.rpc;
-  const long long r_end = min(r + (long long)Q.rpc, Q.R_tot);
-  int cur_b = -1;
+  PsBlk K;
+  K.b = blockIdx.z;
+  K.x0 = blockIdx.y * PS_TW;
+  K.ys = (int)(((long long)blockIdx.x * H) / Q.nb);
+  K.n = (int)(((long long)(blockIdx.x + 1) * H) / Q.nb) - K.ys;
+  K.nc = K.n + 2;
+  const int xe = min(K.x0 + PS_TW, W);  // owned pixels [x0, xe) x [ys, ys + n)
+  K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
+  K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
+  int okmask = 0;  // which of this thread's 4 columns are owned pixels of the image
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = 4 * strip + j;  // staged column: 0,1 and 62,63 are halo
+    if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
+  }
   float lsum = 0.f;
 
-  auto flush = [&](int b) {  // CTA-uniform: one partial per (image, CTA)
+  // ---- stage ----
+  {
+    const float* img = Q.p.images + (size_t)K.b * 3 * plane;
+    const float* val = Q.p.values + (size_t)K.b * C * plane;
+    const int items = (K.n + 4) * PS_Q;
+    if (Q.vec4_ok) {
+      // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image
+      int t = tid / PS_Q, q = tid - t * PS_Q;  // item = t * PS_Q + q, advanced incrementally below
+#pragma unroll 1
+      for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
+        PsItem<C> u[3];
+        int so[3];
+        unsigned out[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int item = it + k * PS_THREADS;
+          const int xb = K.x0 - 4 + 4 * q, y = K.ys - 2 + t;
+          so[k] = (item < items) ? item * 4 : -1;
+          const bool in = (item < items) && xb >= 0 && xb < W && y >= 0 && y < H;
+          out[k] = in ? 0u : 15u;
+          if (in) {
+            const size_t o = (size_t)y * W + xb;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) u[k].vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
+#pragma unroll
+            for (int c = 0; c < C; ++c) u[k].vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
+          } else {
+            ps_item_outside<C>(u[k]);
+          }
+          t += PS_THREADS / PS_Q, q += PS_THREADS % PS_Q;  // next item of this thread: + PS_THREADS
+          if (q >= PS_Q) q -= PS_Q, ++t;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (so[k] >= 0) ps_stage_store<C, CS, SOFTMAX>(Q, u[k], out[k], s_img, s_p, so[k]);
+      }
+    } else {
+#pragma unroll 1
+      for (int it = tid; it < items; it += PS_THREADS) {
+        PsItem<C> u;
+        unsigned out;
+        ps_stage_load_slow<C>(Q, u, out, img, val, K.x0, K.ys, it);
+        ps_stage_store<C, CS, SOFTMAX>(Q, u, out, s_img, s_p, it * 4);
+      }
+    }
+    if (K.xband && tid < 60) {  // column weights of the band slots: Wx(x -> x + j - 2), Wx(x + j - 2 -> x)
+      const int slot = tid / 10, rem = tid - slot * 10, j = rem % 5;
+      const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
+      float w = 0.f;
+      if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, Q.g1, Q.g4) : ps_w1d(xb, x, W, Q.g1, Q.g4);
+      s_wx[tid] = w;
+    }
+  }
+  __syncthreads();
+  PS_TR(1);
+
+  if (K.xband) {  // weight correction of the band pixels this block owns (columns 0..2 and W-3..W-1)
+    const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
+    const int ncb = nlo + nhi;
+    for (int i = tid; i < ncb * K.n; i += PS_THREADS) {  // column fastest
+      const int ty = i / ncb, k = i - ty * ncb;
+      const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo);
+      const int slot = ps_band_slot(x, W);
+      ps_xfix_item<CS>(Q, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, K.ys + ty, x, s_xfix + slot * CS * PS_CAP + ty, PS_CAP);
+    }
+    __syncthreads();
+  }
+  PS_TR(2);
+
+  // ---- march ----
+  const int S = max(2, (K.nc + PS_SEGS - 1) / PS_SEGS);
+  const int t0 = seg * S, t1 = min(t0 + S, K.nc);
+  if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
+    float A[8][CS], Bq[8][CS], Cq[8][CS];
+    ps_zero<CS>(A), ps_zero<CS>(Bq), ps_zero<CS>(Cq);
+    // one copy of the step in the instruction stream (the body is ~11 KB); the accumulator rows rotate by moves
+#pragma unroll 1
+    for (int s = 0; s < S; ++s) {
+      const int t = t0 + s;
+      const bool act = t < t1;
+      float pc[4][CS], own[4][CS];
+      if (act) {
+        // exponent offsets of this centre row: spatial term + multiplicity of the row pairs at the top / bottom border
+        const int y = K.ys - 2 + t;
+        const float l0 = (y == 1 || y == H - 2) ? Q.l1g : 0.f;
+        const float l1 = (y == 0 || y == H - 2) ? Q.l32 : 0.f;
+        const float l2 = (y == 0 || y == H - 3) ? Q.l32 : 0.f;
+        PsKs ks;
+        ks.a1 = ksu + l0, ks.a4 = 4.f * ksu + l0;
+        ks.b0 = ksu + l1, ks.b1 = 2.f * ksu + l1, ks.b4 = 5.f * ksu + l1;
+        ks.c0 = 4.f * ksu + l2, ks.c1 = 5.f * ksu + l2, ks.c4 = 8.f * ksu + l2;
+        ps_step<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
+      }
+      ps_exchange<CS>(A, own, strip);
+      if (act) {
+        if (s >= 2) {
+          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_xfix, lsum);
+        } else if (seg > 0) {
+#pragma unroll
+          for (int c = 0; c < CS; ++c)
+            *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * CS + c) * 64 + 4 * strip) =
+                make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
+    }
+    {  // rows t0+S, t0+S+1 belong to the next segment: hand over what this one contributed to them
+      float oy[4][CS], oz[4][CS];
+      ps_exchange<CS>(A, oy, strip);
+      ps_exchange<CS>(Bq, oz, strip);
+      if (seg < PS_SEGS - 1) {
+#pragma unroll
+        for (int c = 0; c < CS; ++c) {
+          if (t0 + S < K.nc)
+            *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip) =
+                make_float4(oy[0][c], oy[1][c], oy[2][c], oy[3][c]);
+          if (t0 + S + 1 < K.nc)
+            *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip) =
+                make_float4(oz[0][c], oz[1][c], oz[2][c], oz[3][c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  PS_TR(3);
+
+  // ---- the first two rows of segments 1..7: own part + the upper neighbour's carry ----
+  if (seg > 0) {
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const int t = t0 + i;
+      if (t < t1) {
+        float G[4][CS], pc[4][CS];
+#pragma unroll
+        for (int c = 0; c < CS; ++c) {
+          const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
+          const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
+          G[0][c] = h.x + k.x, G[1][c] = h.y + k.y, G[2][c] = h.z + k.z, G[3][c] = h.w + k.w;
+          const float2 p01 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 2);
+          const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
+          pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
+        }
+        ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_xfix, lsum);
+      }
+    }
+  }
+
+  // ---- one loss partial per CTA; the last CTA adds them per image in a fixed order, in double ----
+  const int kpi = Q.nb * Q.n_x;  // CTAs (= partials) per image
+  {
     const float w = warp_sum(lsum);
     if (lane == 0) s_red[warp] = w;
     __syncthreads();
@@ -440,226 +620,30 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       float t = 0.f;
 #pragma unroll
       for (int i = 0; i < PS_THREADS / 32; ++i) t += s_red[i];
-      const long long c_lo = ((long long)b * Q.L) / Q.rpc;
-      __stcg(Q.p.partial + (size_t)b * Q.kpi + (size_t)((long long)blockIdx.x - c_lo), 2.f * t);
+      __stcg(Q.p.partial + (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x, 2.f * t);
+      __threadfence();
+      const unsigned n = atomicAdd(Q.p.ticket, 1u);
+      s_last = (n == gridDim.x * gridDim.y * gridDim.z - 1u);
     }
     __syncthreads();
-    lsum = 0.f;
-  };
-
-  {  // pull this CTA's whole input range towards L2 now; only the first (short) block waits on HBM
-    const int nrows = (int)(r_end - r);
-    for (int i = tid; i < nrows * (3 + C) * 3; i += PS_THREADS) {
-      const int rr = i / ((3 + C) * 3), rem = i - rr * (3 + C) * 3, ch = rem / 3, ln = rem - ch * 3;
-      const long long col = (r + rr) / H;
-      const int y = (int)(r + rr - col * H), b = (int)(col / Q.n_x);
-      const int xa = max((int)(col - (long long)b * Q.n_x) * PS_TW - 4, 0) + 32 * ln;  // 128-byte steps along the row
-      if (xa < W) {
-        const float* base = ch < 3 ? Q.p.images + ((size_t)b * 3 + ch) * plane : Q.p.values + ((size_t)b * C + ch - 3) * plane;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)y * W + xa));
-      }
-    }
   }
-
-  while (r < r_end) {
-    PsBlk K;
-    {
-      const long long col = r / H;
-      K.ys = (int)(r - col * H);
-      K.b = (int)(col / Q.n_x);
-      K.x0 = (int)(col - (long long)K.b * Q.n_x) * PS_TW;
-      // this CTA's rows of the column, cut into blocks of at most PS_CAP rows with the short one FIRST: its tile
-      // arrives quickly and its march overlaps the HBM traffic of the L2 prefetch issued above
-      const int rem = (int)min(r_end - r, (long long)(H - K.ys));
-      K.n = rem - ((rem - 1) / PS_CAP) * PS_CAP;
-      K.nc = K.n + 2;
-    }
-    if (K.b != cur_b) {
-      if (cur_b >= 0) flush(cur_b);
-      cur_b = K.b;
-    }
-    const int xe = min(K.x0 + PS_TW, W), ye = K.ys + K.n;  // owned pixels [x0, xe) x [ys, ye)
-    K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
-    K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
-    int okmask = 0;  // which of this thread's 4 columns are owned pixels of the image
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = 4 * strip + j;  // staged column: 0,1 and 62,63 are halo
-      if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
-    }
-
-    __syncthreads();  // the previous block's readers of the tile are done
-    {
-      const float* img = Q.p.images + (size_t)K.b * 3 * plane;
-      const float* val = Q.p.values + (size_t)K.b * C * plane;
-      const int items = (K.n + 4) * PS_Q;
-      if (Q.vec4_ok) {
-        // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image
-        int t = tid / PS_Q, q = tid - t * PS_Q;  // item = t * PS_Q + q, advanced incrementally below
-#pragma unroll 1
-        for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
-          PsItem<C> u[3];
-          int so[3];
-          unsigned out[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const int item = it + k * PS_THREADS;
-            const int xb = K.x0 - 4 + 4 * q, y = K.ys - 2 + t;
-            so[k] = (item < items) ? item * 4 : -1;
-            const bool in = (item < items) && xb >= 0 && xb < W && y >= 0 && y < H;
-            out[k] = in ? 0u : 15u;
-            if (in) {
-              const size_t o = (size_t)y * W + xb;
-#pragma unroll
-              for (int c = 0; c < 3; ++c) u[k].vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
-#pragma unroll
-              for (int c = 0; c < C; ++c) u[k].vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
-            } else {
-              ps_item_outside<C>(u[k]);
-            }
-            t += PS_THREADS / PS_Q, q += PS_THREADS % PS_Q;  // next item of this thread: + PS_THREADS
-            if (q >= PS_Q) q -= PS_Q, ++t;
-          }
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (so[k] >= 0) ps_stage_store<C, CS, SOFTMAX>(Q, u[k], out[k], s_img, s_p, so[k]);
-        }
-      } else {
-#pragma unroll 1
-        for (int it = tid; it < items; it += PS_THREADS) {
-          PsItem<C> u;
-          unsigned out;
-          ps_stage_load_slow<C>(Q, u, out, img, val, K.x0, K.ys, it);
-          ps_stage_store<C, CS, SOFTMAX>(Q, u, out, s_img, s_p, it * 4);
-        }
-      }
-    }
-    __syncthreads();
-
+  PS_TR(4);
 #ifdef WSDL_PS_TRACE
-    long long tr_c0 = clock64();
-#endif
-    if (K.xband) {  // weight correction of the band pixels this block owns (columns 0..2 and W-3..W-1)
-      const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
-      const int ncb = nlo + nhi;
-      for (int i = tid; i < ncb * K.n; i += PS_THREADS) {  // column fastest
-        const int ty = i / ncb, k = i - ty * ncb;
-        const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo);
-        ps_xfix_item<CS>(Q, s_img, s_p, K.ys, K.x0, K.ys + ty, x, s_xfix + ps_band_slot(x, W) * CS * PS_CAP + ty, PS_CAP);
-      }
-      __syncthreads();
+  {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (tid == 0 && cta < 8192) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      ps_trace_buf[cta * 8 + 7] = smid;
     }
-
-#ifdef WSDL_PS_TRACE
-    if (tid == 0) tr_corr += clock64() - tr_c0;
-#endif
-    // ---- march ----
-    const int S = max(2, (K.nc + PS_SEGS - 1) / PS_SEGS);
-    const int t0 = seg * S, t1 = min(t0 + S, K.nc);
-    if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
-      float A[8][CS], Bq[8][CS], Cq[8][CS];
-      ps_zero<CS>(A), ps_zero<CS>(Bq), ps_zero<CS>(Cq);
-      // one copy of the step in the instruction stream (the body is ~11 KB); the accumulator rows rotate by moves
-#pragma unroll 1
-      for (int s = 0; s < S; ++s) {
-        const int t = t0 + s;
-        const bool act = t < t1;
-        float pc[4][CS], own[4][CS];
-        if (act) {
-          // exponent offsets of this centre row: spatial term + multiplicity of the row pairs at the top / bottom border
-          const int y = K.ys - 2 + t;
-          const float l0 = (y == 1 || y == H - 2) ? Q.l1g : 0.f;
-          const float l1 = (y == 0 || y == H - 2) ? Q.l32 : 0.f;
-          const float l2 = (y == 0 || y == H - 3) ? Q.l32 : 0.f;
-          PsKs ks;
-          ks.a1 = ksu + l0, ks.a4 = 4.f * ksu + l0;
-          ks.b0 = ksu + l1, ks.b1 = 2.f * ksu + l1, ks.b4 = 5.f * ksu + l1;
-          ks.c0 = 4.f * ksu + l2, ks.c1 = 5.f * ksu + l2, ks.c4 = 8.f * ksu + l2;
-          ps_step<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
-        }
-        ps_exchange<CS>(A, own, strip);
-        if (act) {
-          if (s >= 2) {
-            ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_xfix, lsum);
-          } else if (seg > 0) {
-#pragma unroll
-            for (int c = 0; c < CS; ++c)
-              *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * CS + c) * 64 + 4 * strip) =
-                  make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
-          }
-        }
-#pragma unroll
-        for (int w = 0; w < 8; ++w)
-#pragma unroll
-          for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
-      }
-      {  // rows t0+S, t0+S+1 belong to the next segment: hand over what this one contributed to them
-        float oy[4][CS], oz[4][CS];
-        ps_exchange<CS>(A, oy, strip);
-        ps_exchange<CS>(Bq, oz, strip);
-        if (seg < PS_SEGS - 1) {
-#pragma unroll
-          for (int c = 0; c < CS; ++c) {
-            if (t0 + S < K.nc)
-              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip) =
-                  make_float4(oy[0][c], oy[1][c], oy[2][c], oy[3][c]);
-            if (t0 + S + 1 < K.nc)
-              *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip) =
-                  make_float4(oz[0][c], oz[1][c], oz[2][c], oz[3][c]);
-          }
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- the first two rows of segments 1..7: own part + the upper neighbour's carry ----
-    if (seg > 0) {
-#pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        const int t = t0 + i;
-        if (t < t1) {
-          float G[4][CS], pc[4][CS];
-#pragma unroll
-          for (int c = 0; c < CS; ++c) {
-            const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
-            const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
-            G[0][c] = h.x + k.x, G[1][c] = h.y + k.y, G[2][c] = h.z + k.z, G[3][c] = h.w + k.w;
-            const float2 p01 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 2);
-            const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
-            pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
-          }
-          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_xfix, lsum);
-        }
-      }
-    }
-    r += K.n;
-  }
-  if (cur_b >= 0) flush(cur_b);
-
-  // ---- the last CTA adds the per-(image, CTA) partials in a fixed order, in double ----
-  __threadfence();
-  __syncthreads();
-#ifdef WSDL_PS_TRACE
-  if (tid == 0 && blockIdx.x < 8192) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
-    ps_trace_buf[blockIdx.x * 4 + 0] = tr_t0, ps_trace_buf[blockIdx.x * 4 + 1] = tr_t1, ps_trace_buf[blockIdx.x * 4 + 2] = smid, ps_trace_buf[blockIdx.x * 4 + 3] = (unsigned long long)tr_corr;
   }
 #endif
-  if (tid == 0) {
-    const unsigned n = atomicAdd(Q.p.ticket, 1u);
-    s_last = (n == gridDim.x - 1u);
-  }
-  __syncthreads();
   if (!s_last) return;
   __threadfence();
   double wtot = 0.0;
   for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {
-    const long long c_lo = ((long long)b * Q.L) / Q.rpc, c_hi = (((long long)b + 1) * Q.L - 1) / Q.rpc;
-    const int cnt = (int)(c_hi - c_lo + 1);
     double acc = 0.0;
-    for (int i = lane; i < cnt; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)b * Q.kpi + i);
+    for (int i = lane; i < kpi; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)b * kpi + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (Q.p.per_image) {
@@ -680,37 +664,37 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   }
 }
 
-struct PsGeom {
-  int n_x, rpc, kpi, grid;
-  long long L, R_tot;
-};
-
-static PsGeom ps_geometry(int B, int H, int W, int ctas_per_sm) {
-  PsGeom g;
-  g.n_x = (W + PS_TW - 1) / PS_TW;
-  g.L = (long long)g.n_x * H;
-  g.R_tot = g.L * B;
-  const long long slots = (long long)WSDL_NUM_SMS * ctas_per_sm;
-  long long rpc = (g.R_tot + slots - 1) / slots;
-  if (rpc < 6) rpc = 6;  // a block of fewer rows is all warm-up
-  g.rpc = (int)(rpc > 0x3fffffff ? 0x3fffffff : rpc);
-  g.grid = (int)((g.R_tot + g.rpc - 1) / g.rpc);
-  g.kpi = (int)(g.L / g.rpc) + 2;
-  return g;
+// Row blocks per column tile: at most PS_CAP rows each; among the next few candidates the count with the lowest
+// modelled time = (march steps per block + fixed cost of a block, in steps) x blocks an SM works through (a launch
+// below two blocks per SM is latency bound: more, shorter blocks keep winning there).
+static int ps_row_blocks(int B, int H, int W) {
+  const int n_x = (W + PS_TW - 1) / PS_TW;
+  const int nb_min = (H + PS_CAP - 1) / PS_CAP;
+  int best = nb_min;
+  double best_cost = 1e300;
+  for (int nb = nb_min; nb <= nb_min + 12; ++nb) {
+    const int n = (H + nb - 1) / nb;  // rows of the largest block
+    if (n < 6 && nb > nb_min) break;
+    const int S = (n + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n + 2 + PS_SEGS - 1) / PS_SEGS;
+    const double per_sm = (double)B * n_x * nb / WSDL_NUM_SMS;
+    const double rounds = per_sm < 2.0 ? 2.0 : (double)(long long)(per_sm + 0.999999);
+    const double cost = (S + 1.5) * rounds;
+    if (cost < best_cost - 1e-9) best_cost = cost, best = nb;
+  }
+  return best;
 }
 
 size_t ps_workspace_floats(int B, int H, int W) {
-  const PsGeom g3 = ps_geometry(B, H, W, 3), g4 = ps_geometry(B, H, W, 4);
-  const size_t a = (size_t)B * g3.kpi, b = (size_t)B * g4.kpi;
-  return a > b ? a : b;
+  const int n_x = (W + PS_TW - 1) / PS_TW;
+  return (size_t)B * n_x * ps_row_blocks(B, H, W);
 }
 
 template <int C, bool SOFTMAX>
 static int ps_launch_t(PsParams& Q, cudaStream_t s) {
   constexpr size_t smem = PsCfg<C, SOFTMAX>::smem_floats * sizeof(float);
-  const PsGeom g = ps_geometry(Q.p.B, Q.p.H, Q.p.W, PsCfg<C, SOFTMAX>::CTAS);
-  if (g.R_tot / g.rpc > 0x7ffffff0LL) return 1;
-  Q.n_x = g.n_x, Q.rpc = g.rpc, Q.kpi = g.kpi, Q.L = g.L, Q.R_tot = g.R_tot;
+  Q.n_x = (Q.p.W + PS_TW - 1) / PS_TW;
+  Q.nb = ps_row_blocks(Q.p.B, Q.p.H, Q.p.W);
+  if (Q.nb > 65535 || Q.n_x > 65535 || Q.p.B > 65535) return 1;
   static bool attr_set = false;  // idempotent; a race only repeats the call
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -718,7 +702,7 @@ static int ps_launch_t(PsParams& Q, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  pairwise_sym_kernel<C, SOFTMAX><<<g.grid, PS_THREADS, smem, s>>>(Q);
+  pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem, s>>>(Q);
   WSDL_LAUNCH_CHECK();
   return 0;
 }
@@ -740,6 +724,6 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
 
 #ifdef WSDL_PS_TRACE
 extern "C" int wsdl_ps_trace_read(unsigned long long* host, int n) {
-  return (int)cudaMemcpyFromSymbol(host, wsdl::ps_trace_buf, (size_t)n * 4 * sizeof(unsigned long long));
+  return (int)cudaMemcpyFromSymbol(host, wsdl::ps_trace_buf, (size_t)n * 8 * sizeof(unsigned long long));
 }
 #endif
