@@ -9,19 +9,26 @@
 //    t = k s (p(z) - p(y)) is added to G(z) and subtracted from G(y).
 //  * The loss is not accumulated per pair: L is a quadratic form in p, so  L = 1/2 sum_z p(z) . dL/dp(z)
 //    (Euler); the kernel forms it from the finished gradient (with p shifted by 1/2: sum_z dL/dp(z) = 0).
-//  * The image is pre-scaled by sqrt(-kc) while staging, so a pair costs 3 FADD + 3 FFMA + 1 MUFU.EX2 for k and
+//  * The image is pre-scaled by sqrt(-kc) in shared memory, so a pair costs 3 FADD + 3 FFMA + 1 MUFU.EX2 for k and
 //    3 C more for the two scatters.
 //  * Two classes behind a softmax (the reference's binary segmentation) satisfy p1 = 1 - p0, so G1 = -G0: only
-//    channel 0 is staged and accumulated (CS = 1 "stored channel"), and dL/dlogit0 = -dL/dlogit1 = 4 kappa p0 p1 G0.
+//    channel 0 is accumulated (CS = 1 "stored channel"), and dL/dlogit0 = -dL/dlogit1 = 4 kappa p0 p1 G0.
 //
 // Work mapping.  A thread owns a strip of 4 columns and marches down S consecutive rows (a "segment"); the
 // contributions it makes to rows t+1, t+2 live in three rotating accumulator rows in registers, the ones it makes
 // to the 2 columns either side of its strip go to the neighbouring lanes by warp shuffle when a row completes.
 // 16 strips (a half warp) span the 64 staged columns of a tile (60 owned + 2 halo each side), 8 segments span the
 // block's rows; the first two rows of a segment are completed by the two rows its upper neighbour carries over,
-// through shared memory.  A CTA is one block: up to 38 rows of one 60-column tile of one image (grid = row blocks x
-// column tiles x images, a few CTAs per SM slot so that the staging of one overlaps the march of the others); it
+// through shared memory.  A CTA is one block: up to 30 rows of one 60-column tile of one image (grid = row blocks x
+// column tiles x images, a few CTAs per SM slot so that the loads of one overlap the march of the others); it
 // pays 2 warm-up rows instead of a halo in y.
+//
+// Staging.  One thread issues a TMA tile load per input plane (cp.async.bulk.tensor.3d, box = 68 columns x all rows
+// of the block, out-of-image positions zero-filled by the hardware) and every warp sleeps on the mbarrier.  Each warp
+// then converts ITS rows in place (image * sqrt(-kc), logits -> probabilities, sentinel colour outside the image),
+// hands its first two rows to the warp above through a named barrier, and starts marching: there is no CTA-wide
+// barrier between the load and the march.  Inputs that TMA cannot address (W % 4 != 0, unaligned base) are loaded
+// by the warps themselves, element by element, into the same layout.
 //
 // Borders.  Reflect padding only changes how often a pair of REAL pixels is counted: grouping the reference's
 // sum over (centre, offset) by the pixel the reflected offset lands on gives
@@ -30,9 +37,14 @@
 // unordered pair weight Wy Wx + Wy' Wx' is the interior 2 gamma^|d|^2; within 3 px of a border it is a multiple of it:
 //   * rows: pairs {0,1}, {0,2} (and {H-1,H-2}, {H-1,H-3}) count 3/2, pairs inside row 1 (H-2) count 1+gamma^4.  The
 //     march adds log2 of that factor to the exponent of k, per row step -- no extra instruction per pair;
-//   * columns (and the corners, where the weight is not a product): a short pre-pass over the band pixels of a tile
-//     adds (true weight - weight the march applies) kc (p(a)-p(b)) for the <= 24 partners of each, into shared memory.
-// Positions outside the image are staged with a sentinel colour, so k underflows to exactly 0 for them.
+//   * columns (and the corners, where the weight is not a product): after the march, a short pass over the band
+//     pixels of a border tile adds (true weight - weight the march applied) kc (p(a)-p(b)) for the <= 24 partners of
+//     each to the stored gradient (the gradient and the loss are linear in G).
+// Positions outside the image carry a sentinel colour, so k underflows to exactly 0 for them.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "pairwise.cuh"
 
 namespace wsdl {
@@ -42,17 +54,19 @@ constexpr int PS_PITCH = 68;                   // smem row: image x0-4 .. x0+63 
 constexpr int PS_Q = PS_PITCH / 4;             // float4 per staged row
 constexpr int PS_SEGS = 8;                     // row segments per block, one per half warp
 constexpr int PS_THREADS = 16 * PS_SEGS;       // 128
-constexpr int PS_SMAX = 5;                     // rows per segment
-constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 40 centre rows per block: 2 warm-up + 38 owned
+constexpr int PS_SMAX = 4;                     // rows per segment
+constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 32 centre rows per block: 2 warm-up + 30 owned
 constexpr int PS_ROWS = PS_CENTERS + 2;        // + 2 look-ahead rows
 constexpr int PS_CAP = PS_CENTERS - 2;         // owned rows per block
-constexpr int PS_PLANE = PS_ROWS * PS_PITCH;
+constexpr int PS_PLANE = (PS_ROWS * PS_PITCH + 31) / 32 * 32;  // floats; planes start 128-byte aligned (TMA)
 
 struct PsParams {
   PwParams p;
   int n_x;          // column tiles per image
   int nb;           // row blocks per column tile; grid = (nb, n_x, B)
-  int vec4_ok;      // W % 4 == 0 and 16-byte aligned inputs: float4 staging loads
+  int S;            // rows per segment of this launch: ceil((rows of the largest block + 2) / 8), >= 2
+  int use_tma;      // W % 4 == 0, 16-byte aligned inputs, tensor maps encoded
+  unsigned stagger_ns;  // hold-back of the first wave's tile loads, per CTA already resident on the SM
   int vec2_ok;      // W % 2 == 0 and 8-byte aligned gradient: float2 stores
   float img_scale;  // sqrt(-kc)
   float g1, g4;     // gamma, gamma^4 (gamma = exp(-1 / (2 sigma_space^2)), 1 without a spatial term)
@@ -62,9 +76,9 @@ struct PsParams {
 constexpr float PS_SENTINEL = 1e15f;  // staged colour (channel 0) of positions outside the image: 2^-(1e30) = 0
 
 struct PsKs {  // exponent offsets of one row step: spatial term + row-border multiplicity
-  float a1, a4;           // partner in the same row, dx^2 = 1, 4
-  float b0, b1, b4;       // one row down,  dx^2 = 0, 1, 4
-  float c0, c1, c4;       // two rows down
+  float a1, a4;      // partner in the same row, dx^2 = 1, 4
+  float b0, b1, b4;  // one row down,  dx^2 = 0, 1, 4
+  float c0, c1, c4;  // two rows down
 };
 
 template <int C>
@@ -154,61 +168,63 @@ __device__ __forceinline__ void ps_exchange(const float (&X)[8][C], float (&own)
 struct PsBlk {
   int b, x0, ys, n, nc;
   bool xband;    // the tile owns pixels within 3 columns of the left / right image border
-  float scale2;  // 4 kappa * upstream gradient: g = scale2 * (G + xfix)
+  float scale2;  // 4 kappa * upstream gradient: dL/dp = scale2 * G
 };
 
 // band slot of a coordinate: 0..2 for the low band, 3..5 for the high band, -1 outside (needs n >= 6)
 __device__ __forceinline__ int ps_band_slot(int v, int n) { return v <= 2 ? v : (v >= n - 3 ? v - (n - 6) : -1); }
 
-// Gradient of 4 finished pixels of centre row t: dL/dp = scale2 (G + xfix), softmax backward, store; the loss is
-// 2 kappa sum (p - 1/2) (G + xfix), accumulated without its factor.  C = classes, CS = stored channels.
+// One pixel: dL/dvalue from G (linear in G: softmax backward included), and its term of 2 kappa sum (p - 1/2) G.
+template <int C, int CS, bool SOFTMAX>
+__device__ __forceinline__ float ps_pixel_grad(float scale2, const float (&p)[CS], const float (&g)[CS], float (&out)[C]) {
+  float l;
+  if (CS != C) {  // two classes behind a softmax: p1 = 1 - p0, G1 = -G0
+    const float p0 = p[0], p1 = 1.f - p0;
+    l = (p0 - p1) * g[0];
+    out[0] = scale2 * 2.f * p0 * p1 * g[0];
+    out[C - 1] = -out[0];
+  } else {
+    l = 0.f;
+#pragma unroll
+    for (int c = 0; c < CS; ++c) l = fmaf(p[c] - 0.5f, g[c], l);
+    if (SOFTMAX) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) dot = fmaf(p[c], g[c], dot);
+#pragma unroll
+      for (int c = 0; c < CS; ++c) out[c] = scale2 * p[c] * (g[c] - dot);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CS; ++c) out[c] = scale2 * g[c];
+    }
+  }
+  return l;
+}
+
+// Gradient of 4 finished pixels of centre row t: store, and accumulate the loss term.
 template <int C, int CS, bool SOFTMAX>
 __device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t, int strip, int okmask,
-                                        const float (&G)[4][CS], const float (&pc)[4][CS], const float* s_xfix,
-                                        float& lsum) {
+                                        const float (&G)[4][CS], const float (&pc)[4][CS], float* s_gband, float& lsum) {
   const int H = Q.p.H, W = Q.p.W;
   const int y = K.ys - 2 + t;
   const int xs = K.x0 - 2 + 4 * strip;  // image column of j = 0
-  float g[4][CS];
+  if (K.xband) {  // block-uniform: the band-column pass finishes these pixels from their G
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+      const int slot = ps_band_slot(xs + j, W);
+      if (((okmask >> j) & 1) && slot >= 0) {
 #pragma unroll
-    for (int c = 0; c < CS; ++c) g[j][c] = G[j][c];
-  if (K.xband) {  // block-uniform
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if ((okmask >> j) & 1) {
-        const int cs = ps_band_slot(xs + j, W);
-        if (cs >= 0) {
-#pragma unroll
-          for (int c = 0; c < CS; ++c) g[j][c] += s_xfix[(cs * CS + c) * PS_CAP + (t - 2)];
-        }
+        for (int c = 0; c < CS; ++c) s_gband[(slot * CS + c) * PS_CAP + (t - 2)] = G[j][c];
       }
+    }
   }
   float out[C][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float l;
-    if (CS != C) {  // two classes behind a softmax: p1 = 1 - p0, G1 = -G0
-      const float p0 = pc[j][0], p1 = 1.f - p0;
-      l = (p0 - p1) * g[j][0];
-      out[0][j] = K.scale2 * 2.f * p0 * p1 * g[j][0];
-      out[C - 1][j] = -out[0][j];
-    } else {
-      l = 0.f;
+    float o[C];
+    const float l = ps_pixel_grad<C, CS, SOFTMAX>(K.scale2, pc[j], G[j], o);
 #pragma unroll
-      for (int c = 0; c < CS; ++c) l = fmaf(pc[j][c] - 0.5f, g[j][c], l);
-      if (SOFTMAX) {
-        float dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < CS; ++c) dot = fmaf(pc[j][c], g[j][c], dot);
-#pragma unroll
-        for (int c = 0; c < CS; ++c) out[c][j] = K.scale2 * pc[j][c] * (g[j][c] - dot);
-      } else {
-#pragma unroll
-        for (int c = 0; c < CS; ++c) out[c][j] = K.scale2 * g[j][c];
-      }
-    }
+    for (int c = 0; c < C; ++c) out[c][j] = o[c];
     if ((okmask >> j) & 1) lsum += l;
   }
   if (Q.p.grad_values) {
@@ -244,7 +260,7 @@ __device__ __forceinline__ float ps_w1d(int u, int v, int n, float g1, float g4)
   return w;
 }
 
-// multiplicity the march applies to a pair of rows (relative to the interior 2 gamma^|d|^2): see ps_row_ks
+// multiplicity the march applies to a pair of rows (relative to the interior 2 gamma^|d|^2): see the row step
 __device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
   const int lo = min(ya, yb), d = abs(ya - yb);
   if (d == 0) return (lo == 1 || lo == H - 2) ? 1.f + g4 : 1.f;
@@ -256,12 +272,11 @@ __device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
 // Wx(zx -> zx + j - 2) and Wx(zx + j - 2 -> zx), j = 0..4, for the band slot of zx.
 template <int CS>
 __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_img, const float* s_p, const float* s_wx,
-                                            int ys, int x0, int zy, int zx, float* dst, int dstride) {
+                                            int ys, int x0, int zy, int zx, float (&acc)[CS], float (&pz)[CS]) {
   const int H = Q.p.H;
   const float g1 = Q.g1, g4 = Q.g4;
   const int so = (zy - (ys - 2)) * PS_PITCH + (zx - (x0 - 4));
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
-  float pz[CS], acc[CS];
 #pragma unroll
   for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
   float wxf[5], wxb[5];
@@ -298,95 +313,88 @@ __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_i
       for (int c = 0; c < CS; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
     }
   }
-#pragma unroll
-  for (int c = 0; c < CS; ++c) dst[c * dstride] = acc[c];
 }
 
-// ---- staging: rows ys-2 .. ys+n+1, columns x0-4 .. x0+63; softmax and image scale on the way in; positions outside
-// the image get the sentinel colour (and p = 0) ----
-template <int C>
-struct PsItem {
-  float4 vi[3];
-  float4 vv[C];
-};
+// ---- staging ----
+__device__ __forceinline__ unsigned ps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int C, int CS, bool SOFTMAX>
-__device__ __forceinline__ void ps_stage_store(const PsParams& Q, const PsItem<C>& it, unsigned outside, float* s_img,
-                                               float* s_p, int so) {
-  const float sc = Q.img_scale;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float4 o = make_float4(it.vi[c].x * sc, it.vi[c].y * sc, it.vi[c].z * sc, it.vi[c].w * sc);
-    if (c == 0 && outside) {  // bit e: element e lies outside the image
-      if (outside & 1) o.x = PS_SENTINEL;
-      if (outside & 2) o.y = PS_SENTINEL;
-      if (outside & 4) o.z = PS_SENTINEL;
-      if (outside & 8) o.w = PS_SENTINEL;
-    }
-    *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = o;
-  }
-  float v[C][4];
-#pragma unroll
-  for (int c = 0; c < C; ++c) v[c][0] = it.vv[c].x, v[c][1] = it.vv[c].y, v[c][2] = it.vv[c].z, v[c][3] = it.vv[c].w;
-  if (CS != C) {  // p0 = 1 / (1 + e^(v1 - v0))
-#pragma unroll
-    for (int e = 0; e < 4; ++e) v[0][e] = rcp_approx(1.f + ex2_approx((v[1][e] - v[0][e]) * LOG2E));
-  } else if (SOFTMAX) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float m = v[0][e];
-#pragma unroll
-      for (int c = 1; c < C; ++c) m = fmaxf(m, v[c][e]);
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        v[c][e] = ex2_approx((v[c][e] - m) * LOG2E);
-        s += v[c][e];
-      }
-      const float inv = rcp_approx(s);
-#pragma unroll
-      for (int c = 0; c < C; ++c) v[c][e] *= inv;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < CS; ++c)
-    *reinterpret_cast<float4*>(s_p + c * PS_PLANE + so) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
-}
-
+// Rows [r0, r1) of the tile, element by element, raw values (0 outside the image): the layout a TMA load leaves.
 template <int C>
-__device__ __forceinline__ void ps_item_outside(PsItem<C>& it) {
-#pragma unroll
-  for (int c = 0; c < 3; ++c) it.vi[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int c = 0; c < C; ++c) it.vv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-// any W / alignment: element-wise loads
-template <int C>
-__device__ __noinline__ void ps_stage_load_slow(const PsParams& Q, PsItem<C>& it, unsigned& outside, const float* img,
-                                                const float* val, int x0, int ys, int item) {
+__device__ __noinline__ void ps_rows_load_slow(const PsParams& Q, const PsBlk& K, float* s_img, float* s_val, int r0,
+                                               int r1, int lane) {
   const int H = Q.p.H, W = Q.p.W;
   const size_t plane = (size_t)H * W;
-  const int t = item / PS_Q, q = item - t * PS_Q;
-  const int y = ys - 2 + t;
-  const int xb = x0 - 4 + 4 * q;
-  float vi[3][4], vv[C][4];
-  outside = 0;
-#pragma unroll 1
-  for (int e = 0; e < 4; ++e) {
-    const int x = xb + e;
+  const float* img = Q.p.images + (size_t)K.b * 3 * plane;
+  const float* val = Q.p.values + (size_t)K.b * C * plane;
+  for (int i = r0 * PS_PITCH + lane; i < r1 * PS_PITCH; i += 32) {
+    const int t = i / PS_PITCH, cs = i - t * PS_PITCH;
+    const int y = K.ys - 2 + t, x = K.x0 - 4 + cs;
     const bool in = y >= 0 && y < H && x >= 0 && x < W;
     const size_t o = in ? (size_t)y * W + x : 0;
-    if (!in) outside |= 1u << e;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) vi[c][e] = in ? __ldg(img + c * plane + o) : 0.f;
+    for (int c = 0; c < 3; ++c) s_img[c * PS_PLANE + i] = in ? __ldg(img + c * plane + o) : 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) vv[c][e] = in ? __ldg(val + c * plane + o) : 0.f;
+    for (int c = 0; c < C; ++c) s_val[c * PS_PLANE + i] = in ? __ldg(val + c * plane + o) : 0.f;
   }
+}
+
+// Rows [r0, r1) of the tile, in place: image * sqrt(-kc) (sentinel outside the image), values -> probabilities.
+template <int C, int CS, bool SOFTMAX>
+__device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk& K, float* s_img, float* s_val, int r0,
+                                                  int r1, int lane) {
+  const int H = Q.p.H, W = Q.p.W;
+  const float sc = Q.img_scale;
+#pragma unroll 1
+  for (int it = r0 * PS_Q + lane; it < r1 * PS_Q; it += 32) {
+    const int t = it / PS_Q, q = it - t * PS_Q;
+    const int y = K.ys - 2 + t, xb = K.x0 - 4 + 4 * q;
+    const bool row_in = y >= 0 && y < H;
+    const int so = it * 4;  // PS_PITCH == 4 * PS_Q
+    float4 v[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) it.vi[c] = make_float4(vi[c][0], vi[c][1], vi[c][2], vi[c][3]);
+    for (int c = 0; c < 3; ++c) v[c] = *reinterpret_cast<const float4*>(s_img + c * PS_PLANE + so);
+    float4 u[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) it.vv[c] = make_float4(vv[c][0], vv[c][1], vv[c][2], vv[c][3]);
+    for (int c = 0; c < C; ++c) u[c] = *reinterpret_cast<const float4*>(s_val + c * PS_PLANE + so);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = make_float4(v[c].x * sc, v[c].y * sc, v[c].z * sc, v[c].w * sc);
+    if (!row_in || xb < 0 || xb + 3 >= W) {  // some element lies outside the image
+      if (!row_in || xb + 0 < 0 || xb + 0 >= W) v[0].x = PS_SENTINEL;
+      if (!row_in || xb + 1 < 0 || xb + 1 >= W) v[0].y = PS_SENTINEL;
+      if (!row_in || xb + 2 < 0 || xb + 2 >= W) v[0].z = PS_SENTINEL;
+      if (!row_in || xb + 3 < 0 || xb + 3 >= W) v[0].w = PS_SENTINEL;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = v[c];
+    float w[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c][0] = u[c].x, w[c][1] = u[c].y, w[c][2] = u[c].z, w[c][3] = u[c].w;
+    if (CS != C) {  // p0 = 1 / (1 + e^(v1 - v0))
+#pragma unroll
+      for (int e = 0; e < 4; ++e) w[0][e] = rcp_approx(1.f + ex2_approx((w[1][e] - w[0][e]) * LOG2E));
+    } else if (SOFTMAX) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float m = w[0][e];
+#pragma unroll
+        for (int c = 1; c < C; ++c) m = fmaxf(m, w[c][e]);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          w[c][e] = ex2_approx((w[c][e] - m) * LOG2E);
+          s += w[c][e];
+        }
+        const float inv = rcp_approx(s);
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c][e] *= inv;
+      }
+    }
+    if (CS != C || SOFTMAX) {
+#pragma unroll
+      for (int c = 0; c < CS; ++c)
+        *reinterpret_cast<float4*>(s_val + c * PS_PLANE + so) = make_float4(w[c][0], w[c][1], w[c][2], w[c][3]);
+    }
+  }
 }
 
 template <int CS>
@@ -399,22 +407,22 @@ __device__ __forceinline__ void ps_zero(float (&X)[8][CS]) {
 
 template <int C, bool SOFTMAX>
 struct PsCfg {
-  static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // stored channels
-  static constexpr int CTAS = CS == 1 ? 4 : 3;            // resident CTAs per SM (shared memory and registers)
-  static constexpr size_t smem_floats = (size_t)(3 + CS) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 +
-                                        6 * (size_t)CS * PS_CAP + 6 * 10;
+  static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // accumulated channels
+  static constexpr int CTAS = CS == 1 ? 4 : 3;            // resident CTAs per SM (registers)
+  static constexpr size_t smem_floats =
+      (size_t)(3 + C) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 10;
 };
 
 #ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_ctas.py): per-CTA timestamps of the phase boundaries
 __device__ unsigned long long ps_trace_buf[8192 * 8];
-#define PS_TR(slot)                                                                   \
-  do {                                                                                \
+#define PS_TR(slot)                                                                        \
+  do {                                                                                     \
     const unsigned cta__ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
-    if (threadIdx.x == 0 && cta__ < 8192) {                                           \
-      unsigned long long t__;                                                         \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                         \
-      ps_trace_buf[cta__ * 8 + (slot)] = t__;                                         \
-    }                                                                                 \
+    if (threadIdx.x == 0 && cta__ < 8192) {                                                \
+      unsigned long long t__;                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                              \
+      ps_trace_buf[cta__ * 8 + (slot)] = t__;                                              \
+    }                                                                                      \
   } while (0)
 #else
 #define PS_TR(slot)
@@ -423,24 +431,25 @@ __device__ unsigned long long ps_trace_buf[8192 * 8];
 // One CTA = one block: rows [ys, ys + n) of one 60-column tile of one image, n <= PS_CAP.
 template <int C, bool SOFTMAX>
 __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
-    pairwise_sym_kernel(const __grid_constant__ PsParams Q) {
+    pairwise_sym_kernel(const __grid_constant__ PsParams Q, const __grid_constant__ CUtensorMap tm_img,
+                        const __grid_constant__ CUtensorMap tm_val) {
   constexpr int CS = PsCfg<C, SOFTMAX>::CS;
-  extern __shared__ __align__(16) float ps_smem[];
-  float* s_img = ps_smem;                                   // [3][PS_ROWS][PS_PITCH], pre-scaled
-  float* s_p = s_img + 3 * PS_PLANE;                        // [CS][PS_ROWS][PS_PITCH]
-  float* s_head = s_p + CS * PS_PLANE;                      // [7][2][CS][64]: first two rows of segments 1..7, own part
-  float* s_carry = s_head + (PS_SEGS - 1) * 2 * CS * 64;    // [7][2][CS][64]: the same rows, upper neighbour's part
-  float* s_xfix = s_carry + (PS_SEGS - 1) * 2 * CS * 64;    // [6][CS][PS_CAP]: weight correction of the band columns
-  float* s_wx = s_xfix + 6 * CS * PS_CAP;                   // [6][2][5]: column weights of the 6 band slots
+  extern __shared__ __align__(128) float ps_smem[];
+  float* s_img = ps_smem;                                 // [3][PS_ROWS][PS_PITCH]: raw, then pre-scaled
+  float* s_p = s_img + 3 * PS_PLANE;                      // [C][PS_ROWS][PS_PITCH]: raw values, then probabilities
+  float* s_head = s_p + C * PS_PLANE;                     // [7][2][CS][64]: first two rows of segments 1..7, own part
+  float* s_carry = s_head + (PS_SEGS - 1) * 2 * CS * 64;  // [7][2][CS][64]: the same rows, upper neighbour's part
+  float* s_gband = s_carry + (PS_SEGS - 1) * 2 * CS * 64; // [6][CS][PS_CAP]: G of the band-column pixels
+  float* s_wx = s_gband + 6 * CS * PS_CAP;                // [6][2][5]: column weights of the 6 band slots
+  __shared__ __align__(8) unsigned long long s_bar;
   __shared__ float s_red[PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
-  __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int seg = warp * 2 + (lane >> 4), strip = lane & 15;
   const int H = Q.p.H, W = Q.p.W;
-  const size_t plane = (size_t)H * W;
   const float ksu = Q.p.ks_unit;
+  const int S = Q.S;
   PS_TR(0);
 
   PsBlk K;
@@ -451,6 +460,33 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   K.nc = K.n + 2;
   const int xe = min(K.x0 + PS_TW, W);  // owned pixels [x0, xe) x [ys, ys + n)
   K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
+  const int rows = K.nc + 2;  // staged rows in use: ys-2 .. ys+n+1
+
+  // ---- tile load: one TMA box per plane (all 8S+2 rows of the launch's block shape), completion on s_bar ----
+  if (Q.use_tma && tid == 0) {
+    // The first wave's loads all queue on HBM at once; issued together they would all complete together (after the
+    // whole wave's bytes have moved) with the SMs idle meanwhile.  CTAs are dispatched breadth first, so the k-th
+    // CTA of an SM holds back k quarter-wave transfer times: the quarters complete in turn, the early ones march
+    // under the later ones' traffic, and the SM's CTAs stay out of phase from then on.
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (cta >= WSDL_NUM_SMS && cta < (unsigned)WSDL_NUM_SMS * PsCfg<C, SOFTMAX>::CTAS && Q.stagger_ns > 0)
+      __nanosleep((cta / WSDL_NUM_SMS) * Q.stagger_ns);
+    const unsigned bar = ps_smem_u32(&s_bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bytes = (unsigned)((3 + C) * (PS_SEGS * S + 2) * PS_PITCH * sizeof(float));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+    for (int c = 0; c < 3 + C; ++c) {
+      const CUtensorMap* tm = c < 3 ? &tm_img : &tm_val;
+      const int pl = c < 3 ? K.b * 3 + c : K.b * C + (c - 3);
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              ps_smem_u32(s_img + c * PS_PLANE)),
+          "l"(tm), "r"(K.x0 - 4), "r"(K.ys - 2), "r"(pl), "r"(bar)
+          : "memory");
+    }
+  }
   K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
   int okmask = 0;  // which of this thread's 4 columns are owned pixels of the image
 #pragma unroll
@@ -459,78 +495,38 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
   }
   float lsum = 0.f;
-
-  // ---- stage ----
-  {
-    const float* img = Q.p.images + (size_t)K.b * 3 * plane;
-    const float* val = Q.p.values + (size_t)K.b * C * plane;
-    const int items = (K.n + 4) * PS_Q;
-    if (Q.vec4_ok) {
-      // float4 groups are aligned to 4 columns, so each is entirely inside or outside the image
-      int t = tid / PS_Q, q = tid - t * PS_Q;  // item = t * PS_Q + q, advanced incrementally below
-#pragma unroll 1
-      for (int it = tid; it < items; it += 3 * PS_THREADS) {  // three items in flight per thread
-        PsItem<C> u[3];
-        int so[3];
-        unsigned out[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int item = it + k * PS_THREADS;
-          const int xb = K.x0 - 4 + 4 * q, y = K.ys - 2 + t;
-          so[k] = (item < items) ? item * 4 : -1;
-          const bool in = (item < items) && xb >= 0 && xb < W && y >= 0 && y < H;
-          out[k] = in ? 0u : 15u;
-          if (in) {
-            const size_t o = (size_t)y * W + xb;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) u[k].vi[c] = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
-#pragma unroll
-            for (int c = 0; c < C; ++c) u[k].vv[c] = __ldg(reinterpret_cast<const float4*>(val + c * plane + o));
-          } else {
-            ps_item_outside<C>(u[k]);
-          }
-          t += PS_THREADS / PS_Q, q += PS_THREADS % PS_Q;  // next item of this thread: + PS_THREADS
-          if (q >= PS_Q) q -= PS_Q, ++t;
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (so[k] >= 0) ps_stage_store<C, CS, SOFTMAX>(Q, u[k], out[k], s_img, s_p, so[k]);
-      }
-    } else {
-#pragma unroll 1
-      for (int it = tid; it < items; it += PS_THREADS) {
-        PsItem<C> u;
-        unsigned out;
-        ps_stage_load_slow<C>(Q, u, out, img, val, K.x0, K.ys, it);
-        ps_stage_store<C, CS, SOFTMAX>(Q, u, out, s_img, s_p, it * 4);
-      }
-    }
-    if (K.xband && tid < 60) {  // column weights of the band slots: Wx(x -> x + j - 2), Wx(x + j - 2 -> x)
-      const int slot = tid / 10, rem = tid - slot * 10, j = rem % 5;
-      const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
-      float w = 0.f;
-      if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, Q.g1, Q.g4) : ps_w1d(xb, x, W, Q.g1, Q.g4);
-      s_wx[tid] = w;
-    }
+  if (K.xband && tid >= 64 && tid < 124) {  // column weights of the band slots: Wx(x -> x + j - 2), Wx(x + j - 2 -> x)
+    const int e = tid - 64, slot = e / 10, rem = e - slot * 10, j = rem % 5;
+    const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
+    float w = 0.f;
+    if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, Q.g1, Q.g4) : ps_w1d(xb, x, W, Q.g1, Q.g4);
+    s_wx[e] = w;
   }
-  __syncthreads();
-  PS_TR(1);
+  __syncthreads();  // s_bar is initialised
 
-  if (K.xband) {  // weight correction of the band pixels this block owns (columns 0..2 and W-3..W-1)
-    const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
-    const int ncb = nlo + nhi;
-    for (int i = tid; i < ncb * K.n; i += PS_THREADS) {  // column fastest
-      const int ty = i / ncb, k = i - ty * ncb;
-      const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo);
-      const int slot = ps_band_slot(x, W);
-      ps_xfix_item<CS>(Q, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, K.ys + ty, x, s_xfix + slot * CS * PS_CAP + ty, PS_CAP);
+  // ---- each warp: its own rows (the centre rows of its two segments; warp 3 also the 2 look-ahead rows) ----
+  {
+    const int r0 = min(2 * warp * S, rows), r1 = warp == 3 ? rows : min(2 * (warp + 1) * S, rows);
+    const int re = min(r0 + 2, r1);  // the two rows the warp above looks ahead into
+    if (Q.use_tma) {
+      asm volatile(
+          "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(
+              ps_smem_u32(&s_bar))
+          : "memory");
+    } else {
+      ps_rows_load_slow<C>(Q, K, s_img, s_p, r0, r1, lane);
+      __syncwarp();
     }
-    __syncthreads();
+    PS_TR(1);
+    ps_rows_transform<C, CS, SOFTMAX>(Q, K, s_img, s_p, r0, re, lane);
+    if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");  // pairs with the bar.sync of warp - 1
+    ps_rows_transform<C, CS, SOFTMAX>(Q, K, s_img, s_p, re, r1, lane);
+    __syncwarp();
+    if (warp < 3) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
   }
   PS_TR(2);
 
   // ---- march ----
-  const int S = max(2, (K.nc + PS_SEGS - 1) / PS_SEGS);
   const int t0 = seg * S, t1 = min(t0 + S, K.nc);
   if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
     float A[8][CS], Bq[8][CS], Cq[8][CS];
@@ -556,7 +552,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       ps_exchange<CS>(A, own, strip);
       if (act) {
         if (s >= 2) {
-          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_xfix, lsum);
+          ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_gband, lsum);
         } else if (seg > 0) {
 #pragma unroll
           for (int c = 0; c < CS; ++c)
@@ -605,13 +601,40 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
           const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
           pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
         }
-        ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_xfix, lsum);
+        ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, G, pc, s_gband, lsum);
       }
     }
   }
 
-  // ---- one loss partial per CTA; the last CTA adds them per image in a fixed order, in double ----
+  // ---- band columns (and corners): G + weight correction -> final gradient of these pixels (stored again) ----
+  if (K.xband) {
+    __syncthreads();  // s_gband is complete; the first stores of these pixels are ordered before the ones below
+    const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
+    const int ncb = nlo + nhi;
+    const size_t plane = (size_t)H * W;
+    for (int i = tid; i < ncb * K.n; i += PS_THREADS) {  // column fastest
+      const int ty = i / ncb, k = i - ty * ncb;
+      const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
+      const int slot = ps_band_slot(x, W);
+      float acc[CS], pz[CS], o[C];
+      ps_xfix_item<CS>(Q, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, acc, pz);
+      lsum += ps_pixel_grad<C, CS, SOFTMAX>(K.scale2, pz, acc, o);  // the loss is linear in G: add the correction's share
+      if (Q.p.grad_values) {
+#pragma unroll
+        for (int c = 0; c < CS; ++c) acc[c] += s_gband[(slot * CS + c) * PS_CAP + ty];
+        ps_pixel_grad<C, CS, SOFTMAX>(K.scale2, pz, acc, o);
+        float* go = Q.p.grad_values + (size_t)K.b * C * plane + (size_t)y * W + x;
+#pragma unroll
+        for (int c = 0; c < C; ++c) go[c * plane] = o[c];
+      }
+    }
+  }
+
+  // ---- one loss partial per CTA (fire and forget); the last CTA of the grid waits for all of them and adds them
+  // per image in a fixed order, in double.  Every other CTA was dispatched before it and none waits for it. ----
   const int kpi = Q.nb * Q.n_x;  // CTAs (= partials) per image
+  const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
+  const bool finisher = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
   {
     const float w = warp_sum(lsum);
     if (lane == 0) s_red[warp] = w;
@@ -621,11 +644,8 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #pragma unroll
       for (int i = 0; i < PS_THREADS / 32; ++i) t += s_red[i];
       __stcg(Q.p.partial + (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x, 2.f * t);
-      __threadfence();
-      const unsigned n = atomicAdd(Q.p.ticket, 1u);
-      s_last = (n == gridDim.x * gridDim.y * gridDim.z - 1u);
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
     }
-    __syncthreads();
   }
   PS_TR(4);
 #ifdef WSDL_PS_TRACE
@@ -638,8 +658,15 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     }
   }
 #endif
-  if (!s_last) return;
-  __threadfence();
+  if (!finisher) return;
+  if (tid == 0) {
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
+      if (seen < n_ctas) __nanosleep(200);
+    } while (seen < n_ctas);
+  }
+  __syncthreads();
   double wtot = 0.0;
   for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {
     double acc = 0.0;
@@ -689,12 +716,38 @@ size_t ps_workspace_floats(int B, int H, int W) {
   return (size_t)B * n_x * ps_row_blocks(B, H, W);
 }
 
+typedef CUresult (*PsEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PsEncodeFn ps_encoder() {  // cuTensorMapEncodeTiled through the runtime: no link-time dependency on libcuda
+  static const PsEncodeFn fn = []() -> PsEncodeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (PsEncodeFn)p;
+  }();
+  return fn;
+}
+
+// (W, H, planes) f32 tensor, box = 68 columns x `rows` rows x 1 plane, zero fill outside
+static bool ps_encode(CUtensorMap* tm, const float* base, int W, int H, long long planes, int rows) {
+  const PsEncodeFn enc = ps_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)PS_PITCH, (cuuint32_t)rows, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int C, bool SOFTMAX>
-static int ps_launch_t(PsParams& Q, cudaStream_t s) {
+static int ps_launch_t(PsParams& Q, const CUtensorMap& tm_img, const CUtensorMap& tm_val, cudaStream_t s) {
   constexpr size_t smem = PsCfg<C, SOFTMAX>::smem_floats * sizeof(float);
-  Q.n_x = (Q.p.W + PS_TW - 1) / PS_TW;
-  Q.nb = ps_row_blocks(Q.p.B, Q.p.H, Q.p.W);
-  if (Q.nb > 65535 || Q.n_x > 65535 || Q.p.B > 65535) return 1;
   static bool attr_set = false;  // idempotent; a race only repeats the call
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -702,7 +755,7 @@ static int ps_launch_t(PsParams& Q, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem, s>>>(Q);
+  pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem, s>>>(Q, tm_img, tm_val);
   WSDL_LAUNCH_CHECK();
   return 0;
 }
@@ -711,13 +764,31 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   if (P.pad != 2 || P.C < 1 || P.C > 2 || P.H < 6 || P.W < 6) return 1;
   PsParams Q;
   Q.p = P;
-  Q.vec4_ok = ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0);
+  Q.n_x = (P.W + PS_TW - 1) / PS_TW;
+  Q.nb = ps_row_blocks(P.B, P.H, P.W);
+  if (Q.nb > 65535 || Q.n_x > 65535 || P.B > 65535) return 1;
+  const int n_max = (P.H + Q.nb - 1) / Q.nb;
+  Q.S = (n_max + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n_max + 2 + PS_SEGS - 1) / PS_SEGS;
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
   Q.l32 = log2f(1.5f), Q.l1g = log2f(1.f + Q.g4);
-  if (P.C == 2) return P.inner_softmax ? ps_launch_t<2, true>(Q, s) : ps_launch_t<2, false>(Q, s);
-  return P.inner_softmax ? ps_launch_t<1, true>(Q, s) : ps_launch_t<1, false>(Q, s);
+  {  // one quarter wave of tiles at ~6 TB/s; only when the launch fills the machine
+    static const int stagger_env = []() { const char* e = getenv("WSDL_PS_STAGGER_NS"); return e ? atoi(e) : -1; }();
+    const double tile_bytes = (double)(3 + P.C) * (PS_SEGS * Q.S + 2) * PS_PITCH * 4.0;
+    const long long ctas = (long long)Q.nb * Q.n_x * P.B;
+    Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 6000.0) : 0u;
+    if (stagger_env >= 0) Q.stagger_ns = (unsigned)stagger_env;
+  }
+  CUtensorMap tm_img, tm_val;
+  memset(&tm_img, 0, sizeof(tm_img)), memset(&tm_val, 0, sizeof(tm_val));
+  static const int no_tma = []() { const char* e = getenv("WSDL_PAIRWISE_NO_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
+  Q.use_tma = !no_tma && ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0) &&
+              ps_encode(&tm_img, P.images, P.W, P.H, 3LL * P.B, PS_SEGS * Q.S + 2) &&
+              ps_encode(&tm_val, P.values, P.W, P.H, (long long)P.C * P.B, PS_SEGS * Q.S + 2);
+  if (P.C == 2)
+    return P.inner_softmax ? ps_launch_t<2, true>(Q, tm_img, tm_val, s) : ps_launch_t<2, false>(Q, tm_img, tm_val, s);
+  return P.inner_softmax ? ps_launch_t<1, true>(Q, tm_img, tm_val, s) : ps_launch_t<1, false>(Q, tm_img, tm_val, s);
 }
 
 }  // namespace wsdl
