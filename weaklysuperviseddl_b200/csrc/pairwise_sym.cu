@@ -269,7 +269,11 @@ __device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
 
 // xfix(a) for one band pixel a = (zy, zx): sum over its in-image window partners b of
 // (true pair weight - weight applied by the march) / 2 * kc(a,b) (p(a) - p(b)).  Reads the staged tile; s_wx holds
-// Wx(zx -> zx + j - 2) and Wx(zx + j - 2 -> zx), j = 0..4, for the band slot of zx.
+// Wx(zx -> zx + j - 2) and Wx(zx + j - 2 -> zx), j = 0..4, for the band slot of zx.  The difference vanishes unless
+// the COLUMN weights of the pair differ from the interior gamma^dx^2 (the march's row multiplicity is exactly
+// (Wy + Wy') / (2 gamma^dy^2)), which happens for at most two partner columns of a band pixel; those two columns are
+// evaluated for all five rows without branches (weight 0 where there is nothing to add), so the loads and the
+// exponentials of the ten candidates overlap.
 template <int CS>
 __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_img, const float* s_p, const float* s_wx,
                                             int ys, int x0, int zy, int zx, float (&acc)[CS], float (&pz)[CS]) {
@@ -279,9 +283,16 @@ __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_i
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
 #pragma unroll
   for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
-  float wxf[5], wxb[5];
+  // the (at most two) partner columns whose weights are not the interior ones
+  int jsp[2] = {-1, -1};
 #pragma unroll
-  for (int j = 0; j < 5; ++j) wxf[j] = s_wx[j], wxb[j] = s_wx[5 + j];
+  for (int j = 0; j < 5; ++j) {
+    const float f = s_wx[j], b = s_wx[5 + j], g = ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
+    if (f != 0.f && (f != g || b != g)) {
+      if (jsp[0] < 0) jsp[0] = j;
+      else jsp[1] = j;
+    }
+  }
   // row weights: forward, backward, and what the march applies (2 gamma^dy^2 times its row multiplicity)
   float wyf[5], wyb[5], wym[5];
   if (zy >= 5 && zy <= H - 6) {  // every partner row is clear of the row bands
@@ -298,14 +309,13 @@ __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_i
     }
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
+  for (int u = 0; u < 2; ++u) {
+    const int j = jsp[u] < 0 ? 2 : jsp[u];  // no such column: the pixel's own (weight 0 below)
+    const float live = jsp[u] < 0 ? 0.f : 0.5f;
+    const float wxf = s_wx[j], wxb = s_wx[5 + j], gx = ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      if (i == 2 && j == 2) continue;
-      const float wmj = wym[i] * ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
-      const float diff = 0.5f * (fmaf(wyf[i], wxf[j], wyb[i] * wxb[j]) - wmj);
-      // partner outside the image (k is 0 in the march too) / the weight the march applies is the true one
-      if (wxf[j] == 0.f || wyf[i] == 0.f || fabsf(diff) <= 1e-6f * wmj) continue;
+    for (int i = 0; i < 5; ++i) {
+      const float diff = live * (fmaf(wyf[i], wxf, wyb[i] * wxb) - wym[i] * gx);  // 0 for rows outside the image
       const int sn = so + (i - 2) * PS_PITCH + (j - 2);
       const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
       const float k = diff * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0)));
@@ -344,7 +354,7 @@ __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk
                                                   int r1, int lane) {
   const int H = Q.p.H, W = Q.p.W;
   const float sc = Q.img_scale;
-#pragma unroll 1
+#pragma unroll 2
   for (int it = r0 * PS_Q + lane; it < r1 * PS_Q; it += 32) {
     const int t = it / PS_Q, q = it - t * PS_Q;
     const int y = K.ys - 2 + t, xb = K.x0 - 4 + 4 * q;
@@ -413,15 +423,15 @@ struct PsCfg {
       (size_t)(3 + C) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 10;
 };
 
-#ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_ctas.py): per-CTA timestamps of the phase boundaries
-__device__ unsigned long long ps_trace_buf[8192 * 8];
+#ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_ctas.py): per-warp timestamps of the phase boundaries
+__device__ unsigned long long ps_trace_buf[4096 * 4 * 16];
 #define PS_TR(slot)                                                                        \
   do {                                                                                     \
     const unsigned cta__ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
-    if (threadIdx.x == 0 && cta__ < 8192) {                                                \
+    if ((threadIdx.x & 31) == 0 && cta__ < 4096) {                                         \
       unsigned long long t__;                                                              \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                              \
-      ps_trace_buf[cta__ * 8 + (slot)] = t__;                                              \
+      ps_trace_buf[(cta__ * 4 + (threadIdx.x >> 5)) * 16 + (slot)] = t__;                  \
     }                                                                                      \
   } while (0)
 #else
@@ -455,8 +465,11 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   PsBlk K;
   K.b = blockIdx.z;
   K.x0 = blockIdx.y * PS_TW;
-  K.ys = (int)(((long long)blockIdx.x * H) / Q.nb);
-  K.n = (int)(((long long)(blockIdx.x + 1) * H) / Q.nb) - K.ys;
+  {  // balanced split of the H rows over the nb row blocks: the first H % nb blocks have one row more
+    const int base = H / Q.nb, extra = H - base * Q.nb, i = blockIdx.x;
+    K.ys = i * base + min(i, extra);
+    K.n = base + (i < extra ? 1 : 0);
+  }
   K.nc = K.n + 2;
   const int xe = min(K.x0 + PS_TW, W);  // owned pixels [x0, xe) x [ys, ys + n)
   K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
@@ -518,17 +531,27 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       __syncwarp();
     }
     PS_TR(1);
+#ifndef WSDL_X_NOTRANSFORM
     ps_rows_transform<C, CS, SOFTMAX>(Q, K, s_img, s_p, r0, re, lane);
+#endif
     if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");  // pairs with the bar.sync of warp - 1
+    PS_TR(2);
+#ifndef WSDL_X_NOTRANSFORM
     ps_rows_transform<C, CS, SOFTMAX>(Q, K, s_img, s_p, re, r1, lane);
+#endif
     __syncwarp();
+    PS_TR(3);
     if (warp < 3) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
   }
-  PS_TR(2);
+  PS_TR(4);
 
   // ---- march ----
   const int t0 = seg * S, t1 = min(t0 + S, K.nc);
+#ifdef WSDL_X_NOMARCH
+  if (false) {
+#else
   if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
+#endif
     float A[8][CS], Bq[8][CS], Cq[8][CS];
     ps_zero<CS>(A), ps_zero<CS>(Bq), ps_zero<CS>(Cq);
     // one copy of the step in the instruction stream (the body is ~11 KB); the accumulator rows rotate by moves
@@ -564,6 +587,9 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       for (int w = 0; w < 8; ++w)
 #pragma unroll
         for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
+#ifdef WSDL_PS_TRACE
+      if (s < 4) PS_TR(5 + s);
+#endif
     }
     {  // rows t0+S, t0+S+1 belong to the next segment: hand over what this one contributed to them
       float oy[4][CS], oz[4][CS];
@@ -582,11 +608,16 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       }
     }
   }
+  PS_TR(9);
   __syncthreads();
-  PS_TR(3);
+  PS_TR(10);
 
   // ---- the first two rows of segments 1..7: own part + the upper neighbour's carry ----
+#ifdef WSDL_X_NOTAIL
+  if (false) {
+#else
   if (seg > 0) {
+#endif
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
       const int t = t0 + i;
@@ -606,8 +637,13 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     }
   }
 
+  PS_TR(11);
   // ---- band columns (and corners): G + weight correction -> final gradient of these pixels (stored again) ----
+#ifdef WSDL_X_NOTAIL
+  if (false) {
+#else
   if (K.xband) {
+#endif
     __syncthreads();  // s_gband is complete; the first stores of these pixels are ordered before the ones below
     const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
     const int ncb = nlo + nhi;
@@ -630,6 +666,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     }
   }
 
+  PS_TR(12);
   // ---- one loss partial per CTA (fire and forget); the last CTA of the grid waits for all of them and adds them
   // per image in a fixed order, in double.  Every other CTA was dispatched before it and none waits for it. ----
   const int kpi = Q.nb * Q.n_x;  // CTAs (= partials) per image
@@ -647,14 +684,14 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
     }
   }
-  PS_TR(4);
+  PS_TR(13);
 #ifdef WSDL_PS_TRACE
   {
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if (tid == 0 && cta < 8192) {
+    if (lane == 0 && cta < 4096) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      ps_trace_buf[cta * 8 + 7] = smid;
+      ps_trace_buf[(cta * 4 + warp) * 16 + 15] = smid;
     }
   }
 #endif
@@ -795,6 +832,6 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
 
 #ifdef WSDL_PS_TRACE
 extern "C" int wsdl_ps_trace_read(unsigned long long* host, int n) {
-  return (int)cudaMemcpyFromSymbol(host, wsdl::ps_trace_buf, (size_t)n * 8 * sizeof(unsigned long long));
+  return (int)cudaMemcpyFromSymbol(host, wsdl::ps_trace_buf, (size_t)n * 64 * sizeof(unsigned long long));
 }
 #endif
