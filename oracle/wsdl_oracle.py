@@ -3,7 +3,7 @@
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
 `--impl reference` legs may import this file, and only as the *checker* or the
 *timed CPU baseline*; the product package (`weaklysuperviseddl_b200/`) never
-does.  Parity status: PINNED -- `tests/test_oracle_pins_reference.py` runs every
+does.  Parity status: PINNED -- `tests/test_oracle.py` runs every
 function below against the real reference functions loaded from /root/reference
 (in the authoring container) and against the fixtures in `tests/golden/` that
 `oracle/make_golden.py` produced from the real reference (those travel to the
