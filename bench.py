@@ -28,6 +28,7 @@ LCAM = dict(S=512, layers=((1024, 32, 32), (2048, 32, 32)), chunk=128, thresh=0.
 N_SETS = 8  # rotated input sets: 8 x 45 MB > 126 MB L2
 BYTES_PER_PIX = 28  # 20 B read (2 logits + 3 rgb) + 8 B gradient written, C=2
 L2_MB = 126
+NCU_TRAFFIC_BYTES = 32_220_000  # dram read 32.18 MB + write 0.04 MB per launch (ncu --set full, round 1)
 
 
 def peaks():
@@ -299,9 +300,26 @@ def bench_pairwise(args, lib, dev, rank, world):
     value = world * pix_per_step * args.steps / (ms * 1e-3) / 1e9
     ms_per_step = ms / args.steps
     peak, peak_src = peaks()
-    # dominant kernel: pairwise_fwd_bwd_kernel<2,2>, two launches per step and nothing else but two 4-byte memsets
+    # dominant kernel: pairwise_sym_kernel<2,*> (csrc/pairwise_sym.cu), two launches per step (cut: <2,true>,
+    # boundary: <2,false>) and nothing else but two 8-byte memsets of the loss ticket
     launch_ms = ms_per_step / 2.0
     achieved = BYTES_PER_PIX * B * H * W / (launch_ms * 1e-3) / 1e9
+    per_kernel = {}
+    for name, which in (("cut", 0), ("boundary", 1)):  # each launch alone, CUDA events on the launching stream
+        def only(n, which=which):
+            for i in range(n):
+                logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
+                if which == 0:
+                    rc = lib.wsdl_pairwise_fwd_bwd(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
+                                                   PAIR["sigma_cut"], 0.0, 1, 1, 0, None, loss_cut.data_ptr(),
+                                                   g_cut.data_ptr(), ws.data_ptr(), nws, sp())
+                else:
+                    rc = lib.wsdl_pairwise_fwd_bwd(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
+                                                   PAIR["sigma_bnd"], PAIR["sigma_space"], 0, 0, 1, None,
+                                                   loss_bnd.data_ptr(), g_bnd.data_ptr(), ws.data_ptr(), nws, sp())
+                _native_check(rc)
+        t_ms, _ = _timed(only, 20, 200, dev, world, None)
+        per_kernel[name] = t_ms / 200
     res = {
         "metric": "cut+boundary loss fwd+bwd throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -316,10 +334,13 @@ def bench_pairwise(args, lib, dev, rank, world):
             "sharding": "batch per rank, no data-path collective",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "pairwise_fwd_bwd_kernel<2,2>",
+                     "traffic": NCU_TRAFFIC_BYTES, "kernel": "pairwise_sym_kernel<2,true|false>",
                      "algorithmic_bytes_per_launch": BYTES_PER_PIX * B * H * W, "launch_ms": launch_ms,
-                     "peak_source": peak_src,
-                     "note": "launch duration = timed step / 2 launches (CUDA events on the launching stream)"},
+                     "peak_source": peak_src, "per_kernel_ms_direct_launch": per_kernel,
+                     "note": "launch duration = timed step / 2 launches (CUDA events on the launching stream, inside "
+                             "the graph); traffic = dram__bytes_read+write per launch from profiles/r01_c_ncu_full_sym.txt "
+                             "(the 12.8 MB gradient is still dirty in L2 when the kernel ends); the kernel is bound by "
+                             "FP32/MUFU issue, not HBM (DESIGN.md 4.2)"},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
     }

@@ -54,7 +54,13 @@ constexpr int PS_PITCH = 68;                   // smem row: image x0-4 .. x0+63 
 constexpr int PS_Q = PS_PITCH / 4;             // float4 per staged row
 constexpr int PS_SEGS = 8;                     // row segments per block, one per half warp
 constexpr int PS_THREADS = 16 * PS_SEGS;       // 128
-constexpr int PS_SMAX = 4;                     // rows per segment
+#ifndef WSDL_PS_SMAX
+#define WSDL_PS_SMAX 4
+#endif
+#ifndef WSDL_PS_CTAS
+#define WSDL_PS_CTAS 4
+#endif
+constexpr int PS_SMAX = WSDL_PS_SMAX;           // rows per segment
 constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 32 centre rows per block: 2 warm-up + 30 owned
 constexpr int PS_ROWS = PS_CENTERS + 2;        // + 2 look-ahead rows
 constexpr int PS_CAP = PS_CENTERS - 2;         // owned rows per block
@@ -418,7 +424,7 @@ __device__ __forceinline__ void ps_zero(float (&X)[8][CS]) {
 template <int C, bool SOFTMAX>
 struct PsCfg {
   static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // accumulated channels
-  static constexpr int CTAS = CS == 1 ? 4 : 3;            // resident CTAs per SM (registers)
+  static constexpr int CTAS = CS == 1 ? WSDL_PS_CTAS : WSDL_PS_CTAS - 1;  // resident CTAs per SM (registers)
   static constexpr size_t smem_floats =
       (size_t)(3 + C) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 10;
 };
@@ -789,6 +795,9 @@ static int ps_launch_t(PsParams& Q, const CUtensorMap& tm_img, const CUtensorMap
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
