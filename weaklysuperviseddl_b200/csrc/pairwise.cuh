@@ -34,4 +34,8 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 int ps_launch(const PwParams& P, cudaStream_t s);
 size_t ps_workspace_floats(int B, int H, int W);
 
+// Persistent warp-specialised version of the same kernel (pairwise_pipe.cu); same return convention.
+int pp_launch(const PwParams& P, cudaStream_t s);
+size_t pp_workspace_floats(int B, int H, int W);
+
 }  // namespace wsdl

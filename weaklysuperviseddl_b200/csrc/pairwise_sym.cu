@@ -801,7 +801,9 @@ static int ps_launch_t(PsParams& Q, const CUtensorMap& tm_img, const CUtensorMap
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem, s>>>(Q, tm_img, tm_val);
+  static const size_t pad = []() { const char* e = getenv("WSDL_PS_SMEM_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : 0; }();
+  if (pad) cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
+  pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem + pad, s>>>(Q, tm_img, tm_val);
   WSDL_LAUNCH_CHECK();
   return 0;
 }
