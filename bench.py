@@ -247,6 +247,7 @@ def make_pairwise_state(lib, dev, seed):
         sets.append((logits, torch.softmax(logits, dim=1), img, torch.empty_like(logits), torch.empty_like(logits)))
     nws = lib.wsdl_pairwise_workspace_bytes(B, H, W)
     ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    _native_check(lib.wsdl_pairwise_workspace_init(ws.data_ptr(), nws, torch.cuda.current_stream(dev).cuda_stream))
     loss_cut = torch.empty(1, device=dev)
     loss_bnd = torch.empty(B, device=dev)
     return sets, ws, nws, loss_cut, loss_bnd
@@ -261,10 +262,10 @@ def bench_pairwise(args, lib, dev, rank, world):
 
     def one_step(i):
         logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
-        rc = lib.wsdl_pairwise_fwd_bwd(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_cut"],
+        rc = lib.wsdl_pairwise_fwd_bwd_prepared(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_cut"],
                                        0.0, 1, 1, 0, None, loss_cut.data_ptr(), g_cut.data_ptr(), ws.data_ptr(), nws, sp())
         _native_check(rc)
-        rc = lib.wsdl_pairwise_fwd_bwd(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_bnd"],
+        rc = lib.wsdl_pairwise_fwd_bwd_prepared(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_bnd"],
                                        PAIR["sigma_space"], 0, 0, 1, None, loss_bnd.data_ptr(), g_bnd.data_ptr(),
                                        ws.data_ptr(), nws, sp())
         _native_check(rc)
@@ -301,7 +302,7 @@ def bench_pairwise(args, lib, dev, rank, world):
     ms_per_step = ms / args.steps
     peak, peak_src = peaks()
     # dominant kernel: pairwise_sym_kernel<2,*> (csrc/pairwise_sym.cu), two launches per step (cut: <2,true>,
-    # boundary: <2,false>) and nothing else but two 8-byte memsets of the loss ticket
+    # boundary: <2,false>) and nothing else (prepared workspace: no per-call memset)
     launch_ms = ms_per_step / 2.0
     achieved = BYTES_PER_PIX * B * H * W / (launch_ms * 1e-3) / 1e9
     per_kernel = {}
@@ -310,11 +311,11 @@ def bench_pairwise(args, lib, dev, rank, world):
             for i in range(n):
                 logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
                 if which == 0:
-                    rc = lib.wsdl_pairwise_fwd_bwd(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
+                    rc = lib.wsdl_pairwise_fwd_bwd_prepared(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
                                                    PAIR["sigma_cut"], 0.0, 1, 1, 0, None, loss_cut.data_ptr(),
                                                    g_cut.data_ptr(), ws.data_ptr(), nws, sp())
                 else:
-                    rc = lib.wsdl_pairwise_fwd_bwd(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
+                    rc = lib.wsdl_pairwise_fwd_bwd_prepared(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
                                                    PAIR["sigma_bnd"], PAIR["sigma_space"], 0, 0, 1, None,
                                                    loss_bnd.data_ptr(), g_bnd.data_ptr(), ws.data_ptr(), nws, sp())
                 _native_check(rc)

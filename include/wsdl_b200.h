@@ -109,6 +109,18 @@ int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C
                           int per_image_loss, const float* grad_out, float* loss_out, float* grad_values,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same call for a PREPARED workspace: one that wsdl_pairwise_workspace_init() has initialised once (it zeroes the
+ * 512-byte control block) and that has since only been used by complete pairwise calls ordered on one stream.
+ * Every pairwise kernel leaves the control block initialised again, so the per-call 8-byte memset of
+ * wsdl_pairwise_fwd_bwd (one extra node per call in a CUDA graph) is not needed.  A workspace must not be shared by
+ * calls that may run concurrently. */
+int wsdl_pairwise_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
+int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int B, int C, int H, int W, int window,
+                                   float sigma_color, float sigma_space, int inner_softmax, int divide_by_c,
+                                   int per_image_loss, const float* grad_out, float* loss_out, float* grad_values,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* compute_affinities / compute_affinities_single (AlternatingDirectionCutLoss.py:612-637,
  * AlternatingDirectionBoundaryLoss.py:46-70): images (B,3,H,W) -> out (K,B,H,W) with
  * K = window*window-1, offset order dy outer / dx inner, centre skipped; out[k] is the

@@ -25,7 +25,7 @@ for name, args in (("cut", (logits, img, 5, 0.05, None, True, True, False)), ("b
     t0 = a[a > 0].min()
     T = np.where(a > 0, (a - t0) / 1000.0, np.nan)
     print(f"== {name}: {len(a)} CTAs, span {np.nanmax(T):.1f} us")
-    mn = ["ready", "marched-loop", "band", "handed"]; hn = ["landed", "converted", "marched seen", "tail done"]
+    mn = ["ready", "marched-loop", "band", "handed"]; hn = ["landed", "converted", "-", "-"]
     for j in range(5):
         if np.isnan(T[:, 0, j, 0]).all():
             break

@@ -217,3 +217,32 @@ def test_config2_full_size_properties(WF):
     L, g = O.pairwise_closed_form(probs[b].cpu().numpy(), img[b].cpu().numpy(), 0.1, 5.0, 5, False, False)
     assert_loss_close(lb[b], L)
     assert_grad_close(gb[b], g)
+
+
+def test_prepared_workspace_is_self_cleaning(WF):
+    """wsdl_pairwise_fwd_bwd_prepared on one workspace, launch after launch (different kernels in between), must
+    equal wsdl_pairwise_fwd_bwd (which zeroes the ticket itself) bit for bit."""
+    from weaklysuperviseddl_b200 import _native
+
+    lib = _native.lib()
+    gen = torch.Generator().manual_seed(77)
+    shapes = [(2, 2, 64, 64, 5), (1, 3, 33, 31, 5), (2, 2, 19, 23, 3), (2, 2, 64, 64, 5), (1, 2, 224, 224, 5)]
+    nmax = max(lib.wsdl_pairwise_workspace_bytes(B, H, W_) for (B, C, H, W_, win) in shapes)
+    ws = torch.empty(nmax, dtype=torch.uint8, device="cuda").fill_(0xAB)  # garbage until initialised
+    sp = torch.cuda.current_stream().cuda_stream
+    assert lib.wsdl_pairwise_workspace_init(ws.data_ptr(), nmax, sp) == 0
+    for (B, C, H, W_, win) in shapes * 2:
+        vals = torch.randn(B, C, H, W_, generator=gen).cuda()
+        img = smooth_images(gen, B, H, W_).cuda()
+        out = []
+        for prepared in (True, False):
+            loss = torch.empty(1, device="cuda")
+            grad = torch.empty_like(vals)
+            w = ws if prepared else torch.empty(nmax, dtype=torch.uint8, device="cuda").fill_(0xCD)
+            fn = lib.wsdl_pairwise_fwd_bwd_prepared if prepared else lib.wsdl_pairwise_fwd_bwd
+            rc = fn(vals.data_ptr(), img.data_ptr(), B, C, H, W_, win, 0.05, 0.0, 1, 1, 0, None, loss.data_ptr(),
+                    grad.data_ptr(), w.data_ptr(), nmax, sp)
+            assert rc == 0
+            out.append((loss, grad))
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    torch.cuda.synchronize()

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(PW_THREADS) pairwise_fwd_bwd_kernel(const __gr
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (tid == 0) *P.ticket = 0u;  // every CTA has checked in: leave the ticket ready for the next launch
   pw_final_reduce(P, tiles);
 }
 
@@ -532,6 +533,7 @@ __global__ void __launch_bounds__(PW_THREADS, (C <= 2 ? 3 : 2)) pairwise_fast_ke
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (tid == 0) *P.ticket = 0u;  // every CTA has checked in: leave the ticket ready for the next launch
   pw_final_reduce(P, tiles);
 }
 
@@ -622,10 +624,10 @@ extern "C" size_t wsdl_pairwise_workspace_bytes(int B, int H, int W) {
   return 512 + pw_align(floats * sizeof(float));
 }
 
-extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C, int H, int W,
-                                     int window, float sigma_color, float sigma_space, int inner_softmax,
-                                     int divide_by_c, int per_image_loss, const float* grad_out, float* loss_out,
-                                     float* grad_values, void* workspace, size_t workspace_bytes, void* stream) {
+static int pairwise_fwd_bwd_impl(const float* values, const float* images, int B, int C, int H, int W, int window,
+                                 float sigma_color, float sigma_space, int inner_softmax, int divide_by_c,
+                                 int per_image_loss, const float* grad_out, float* loss_out, float* grad_values,
+                                 void* workspace, size_t workspace_bytes, void* stream, bool prepared) {
   if (!values || !images || !loss_out || !workspace) return WSDL_E_NULL;
   if (B < 1 || H < 1 || W < 1 || C < 1 || C > WSDL_MAX_CLASSES || B > 65535) return WSDL_E_SHAPE;
   if (window < 1 || (window & 1) == 0 || window / 2 > PW_MAXPAD) return WSDL_E_SHAPE;
@@ -662,8 +664,10 @@ extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, i
   const double K = (double)window * window - 1.0;
   const double N = (per_image_loss ? 1.0 : (double)B) * (double)H * (double)W;
   P.kappa = 1.0 / (K * N * (divide_by_c ? (double)C : 1.0));
-  cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
-  if (e != cudaSuccess) return (int)e;
+  if (!prepared) {  // every kernel leaves the ticket at 0 again: a prepared workspace needs no per-call memset
+    cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (pad == 2 && H > 2 * PF_PAD && W > 2 * PF_PAD) {
     static const int no_sym = []() { const char* e = getenv("WSDL_PAIRWISE_NO_SYM"); return (e && e[0] == '1') ? 1 : 0; }();
     if (!no_sym) {  // pair-symmetric kernels: the hot configurations (window 5, C <= 2)
@@ -687,6 +691,29 @@ extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, i
   }
   if (pad == 2 && C == 2) return pw_launch<2, 2>(P, s);
   return pw_launch<0, 0>(P, s);
+}
+
+extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C, int H, int W,
+                                     int window, float sigma_color, float sigma_space, int inner_softmax,
+                                     int divide_by_c, int per_image_loss, const float* grad_out, float* loss_out,
+                                     float* grad_values, void* workspace, size_t workspace_bytes, void* stream) {
+  return pairwise_fwd_bwd_impl(values, images, B, C, H, W, window, sigma_color, sigma_space, inner_softmax, divide_by_c,
+                               per_image_loss, grad_out, loss_out, grad_values, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int wsdl_pairwise_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace) return WSDL_E_NULL;
+  if (workspace_bytes < 512) return WSDL_E_WORKSPACE;
+  return (int)cudaMemsetAsync(workspace, 0, 512, (cudaStream_t)stream);
+}
+
+extern "C" int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int B, int C, int H, int W,
+                                              int window, float sigma_color, float sigma_space, int inner_softmax,
+                                              int divide_by_c, int per_image_loss, const float* grad_out,
+                                              float* loss_out, float* grad_values, void* workspace,
+                                              size_t workspace_bytes, void* stream) {
+  return pairwise_fwd_bwd_impl(values, images, B, C, H, W, window, sigma_color, sigma_space, inner_softmax, divide_by_c,
+                               per_image_loss, grad_out, loss_out, grad_values, workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int wsdl_affinities(const float* images, int B, int H, int W, int window, float sigma_color,

@@ -29,10 +29,12 @@ namespace pp {
 constexpr int PP_TW = 60;     // owned columns per tile
 constexpr int PP_PITCH = 68;  // smem row: image x0-4 .. x0+63 (2 pad + 2 halo | 60 | 2 halo + 2 pad)
 constexpr int PP_Q = PP_PITCH / 4;
-constexpr int PP_SEGS = 8;    // row segments per tile, one per half warp of the M group
-constexpr int PP_GROUP = 128; // threads per role
-constexpr int PP_THREADS = 2 * PP_GROUP;
+constexpr int PP_SEGS = 16;   // row segments per tile (two rows each), one per half warp of the M group
+constexpr int PP_M_THREADS = 256;  // marching warps 0-7
+constexpr int PP_H_THREADS = 128;  // loading / converting warps 8-11
+constexpr int PP_THREADS = PP_M_THREADS + PP_H_THREADS;
 constexpr int PP_CTAS_PER_SM = 2;
+constexpr int PP_M_REGS = 96, PP_H_REGS = 48;  // setmaxnreg: 256 * 96 + 128 * 48 = 384 * 80 (the launch allocation)
 constexpr float PP_SENTINEL = 1e15f;  // staged colour (channel 0) of positions outside the image: 2^-(1e30) = 0
 
 struct PpParams {
@@ -385,14 +387,13 @@ __device__ __forceinline__ void pp_zero(float (&X)[8][CS]) {
 template <int C, bool SOFTMAX>
 struct PpCfg {
   static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // accumulated channels
-  static constexpr int SMAX = CS == 1 ? 4 : 3;            // rows per segment (shared memory: two buffers, 2 CTAs/SM)
-  static constexpr int ROWS = PP_SEGS * SMAX + 2;         // staged rows: 2 warm-up + owned + 2 look-ahead
-  static constexpr int CAP = PP_SEGS * SMAX - 2;          // owned rows per tile
+  static constexpr int ROWS = PP_SEGS * 2 + 2;            // staged rows: 2 warm-up + owned + 2 look-ahead
+  static constexpr int CAP = PP_SEGS * 2 - 2;             // owned rows per tile
   static constexpr int PLANE = (ROWS * PP_PITCH + 31) / 32 * 32;  // floats; planes start 128-byte aligned (TMA)
-  static constexpr int HEAD = (PP_SEGS - 1) * 2 * CS * 64;        // first two rows of segments 1..7
+  static constexpr int BUF = (3 + C) * PLANE;                     // one tile buffer: image planes | value planes
+  static constexpr int CARRY = (PP_SEGS - 1) * 2 * CS * 64;       // what a segment adds to the two rows of the next
   static constexpr int GB = (6 * CS * CAP + 31) / 32 * 32;        // G of the band-column pixels
-  static constexpr int BUF = (3 + C) * PLANE + 2 * HEAD + GB;     // planes | head G | head p | band G
-  static constexpr size_t smem_bytes = (2 * (size_t)BUF + 64) * sizeof(float);
+  static constexpr size_t smem_bytes = (2 * (size_t)BUF + CARRY + GB + 64) * sizeof(float);
 };
 
 __device__ __forceinline__ void pp_bar_wait(unsigned long long* bar, unsigned parity) {
@@ -405,7 +406,8 @@ __device__ __forceinline__ void pp_bar_wait(unsigned long long* bar, unsigned pa
 __device__ __forceinline__ void pp_bar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pp_smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void pp_group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(PP_GROUP) : "memory"); }
+__device__ __forceinline__ void pp_sync_m() { asm volatile("bar.sync 1, %0;" ::"n"(PP_M_THREADS) : "memory"); }
+__device__ __forceinline__ void pp_sync_h() { asm volatile("bar.sync 2, %0;" ::"n"(PP_H_THREADS) : "memory"); }
 
 __device__ __forceinline__ PpBlk pp_tile(const PpParams& Q, int tile) {
   PpBlk K;
@@ -438,13 +440,13 @@ __device__ __forceinline__ void pp_masks(const PpParams& Q, const PpBlk& K, int 
 
 #ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_pipe.py): timestamps per CTA, role, tile, phase
 __device__ unsigned long long pp_trace_buf[512 * 2 * 8 * 4];
-#define PP_TR(role_, j_, slot_)                                                              \
-  do {                                                                                       \
-    if ((threadIdx.x & 127) == 0 && blockIdx.x < 512 && (j_) < 8) {                          \
-      unsigned long long t__;                                                                \
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                \
-      pp_trace_buf[((blockIdx.x * 2 + (role_)) * 8 + (j_)) * 4 + (slot_)] = t__;             \
-    }                                                                                        \
+#define PP_TR(role_, j_, slot_)                                                                  \
+  do {                                                                                           \
+    if ((threadIdx.x == 0 || threadIdx.x == PP_M_THREADS) && blockIdx.x < 512 && (j_) < 8) {     \
+      unsigned long long t__;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                    \
+      pp_trace_buf[((blockIdx.x * 2 + (role_)) * 8 + (j_)) * 4 + (slot_)] = t__;                 \
+    }                                                                                            \
   } while (0)
 #else
 #define PP_TR(role_, j_, slot_)
@@ -457,24 +459,25 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
   using Cfg = PpCfg<C, SOFTMAX>;
   constexpr int CS = Cfg::CS, PL = Cfg::PLANE, CAP = Cfg::CAP;
   extern __shared__ __align__(128) float pp_smem[];
-  float* s_wx = pp_smem + 2 * Cfg::BUF;  // [6][2][5]: column weights of the 6 band slots
-  __shared__ __align__(8) unsigned long long s_full[2], s_ready[2], s_marched[2], s_taildone[2];
-  __shared__ float s_red[2][2][PP_GROUP / 32];  // [role][tile parity][warp]
-  __shared__ double s_dred[PP_GROUP / 32];
+  float* s_carry = pp_smem + 2 * Cfg::BUF;  // [15][2][CS][64]
+  float* s_gband = s_carry + Cfg::CARRY;    // [6][CS][CAP]
+  float* s_wx = s_gband + Cfg::GB;          // [6][2][5]: column weights of the 6 band slots
+  __shared__ __align__(8) unsigned long long s_full[2], s_ready[2], s_marched[2];
+  __shared__ float s_red[2][PP_M_THREADS / 32];  // [tile parity][warp]
+  __shared__ double s_dred[PP_M_THREADS / 32];
 
-  const int tid = threadIdx.x, role = tid >> 7, gt = tid & (PP_GROUP - 1), lane = tid & 31, gw = gt >> 5;
-  const int H = Q.p.H, W = Q.p.W, S = Q.S;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int H = Q.p.H, W = Q.p.W;
   const int G = gridDim.x;
   const int n_my = (Q.n_tiles - (int)blockIdx.x + G - 1) / G;  // tiles blockIdx.x, blockIdx.x + G, ...
-  const int kpi2 = 2 * Q.nb * Q.n_x;                           // loss partials per image (M and H of every tile)
+  const int kpi = Q.nb * Q.n_x;                                // tiles (= loss partials) per image
 
   if (tid == 0) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pp_smem_u32(&s_full[b])));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(&s_ready[b])), "n"(PP_GROUP / 32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(&s_ready[b])), "n"(PP_H_THREADS / 32));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pp_smem_u32(&s_marched[b])));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pp_smem_u32(&s_taildone[b])), "n"(PP_GROUP / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -487,15 +490,17 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
   }
   __syncthreads();  // the only CTA-wide barrier: from here on the two roles run on their own
 
-  if (role == 1) {
-    // =============================== H: load, convert, tail ===============================
+  if (tid >= PP_M_THREADS) {
+    // =============================== H: load and convert ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PP_H_REGS));
+    const int gt = tid - PP_M_THREADS;
     auto issue = [&](int j) {  // leader only: TMA load of this CTA's j-th tile into buffer j & 1
       const int b = j & 1;
       const PpBlk K = pp_tile(Q, (int)blockIdx.x + j * G);
       float* planes = pp_smem + b * Cfg::BUF;
       const unsigned bar = pp_smem_u32(&s_full[b]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the planes were last written by threads
-      const unsigned bytes = (unsigned)((3 + C) * (PP_SEGS * S + 2) * PP_PITCH * sizeof(float));
+      const unsigned bytes = (unsigned)((3 + C) * Cfg::ROWS * PP_PITCH * sizeof(float));
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 #pragma unroll
       for (int c = 0; c < 3 + C; ++c) {
@@ -508,49 +513,6 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
             : "memory");
       }
     };
-    float lsum = 0.f;
-    auto tail = [&](int jj) {  // first two rows of segments 1..7 of tile jj, from the head arrays
-      const int b = jj & 1, tile = (int)blockIdx.x + jj * G;
-      const PpBlk K = pp_tile(Q, tile);
-      const float* s_head = pp_smem + b * Cfg::BUF + (3 + C) * PL;
-      const float* s_headp = s_head + Cfg::HEAD;
-      pp_bar_wait(&s_marched[b], (jj >> 1) & 1);
-      PP_TR(1, jj, 2);
-      if (Q.use_tma && gt == 0 && jj + 2 < n_my) issue(jj + 2);  // the planes of buffer b are free
-      lsum = 0.f;
-      for (int i = gt; i < (PP_SEGS - 1) * 2 * 16; i += PP_GROUP) {
-        const int hr = i >> 4, strip = i & 15;  // head row (seg - 1) * 2 + r
-        const int seg = (hr >> 1) + 1, t = seg * S + (hr & 1);
-        if (t < min(seg * S + S, K.nc)) {
-          int okmask, bandmask;
-          pp_masks(Q, K, strip, okmask, bandmask);
-          float Gv[4][CS], pc[4][CS];
-#pragma unroll
-          for (int c = 0; c < CS; ++c) {
-            const float4 g = *reinterpret_cast<const float4*>(s_head + (hr * CS + c) * 64 + 4 * strip);
-            const float4 p = *reinterpret_cast<const float4*>(s_headp + (hr * CS + c) * 64 + 4 * strip);
-            Gv[0][c] = g.x, Gv[1][c] = g.y, Gv[2][c] = g.z, Gv[3][c] = g.w;
-            pc[0][c] = p.x, pc[1][c] = p.y, pc[2][c] = p.z, pc[3][c] = p.w;
-          }
-          pp_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, bandmask, Gv, pc, lsum);
-        }
-      }
-      const float w = warp_sum(lsum);
-      if (lane == 0) {
-        s_red[1][jj & 1][gw] = w;
-        pp_bar_arrive(&s_taildone[b]);  // this warp no longer reads the head arrays of buffer b
-      }
-      pp_group_sync(2);
-      if (gt == 0) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < PP_GROUP / 32; ++i) t += s_red[1][jj & 1][i];
-        const int img = tile / (Q.nb * Q.n_x), within = tile - img * (Q.nb * Q.n_x);
-        __stcg(Q.p.partial + (size_t)img * kpi2 + 2 * within + 1, 2.f * t);
-      }
-      PP_TR(1, jj, 3);
-    };
-
     if (Q.use_tma && gt == 0) {
       issue(0);
       if (n_my > 1) issue(1);
@@ -561,58 +523,28 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
       float* s_img = pp_smem + b * Cfg::BUF;
       float* s_p = s_img + 3 * PL;
       const int rows = K.nc + 2;
+      if (j >= 2) {  // M has finished with the tile that was in this buffer
+        pp_bar_wait(&s_marched[b], ((j - 2) >> 1) & 1);
+        if (Q.use_tma && gt == 0) issue(j);
+      }
       if (Q.use_tma) {
         pp_bar_wait(&s_full[b], (j >> 1) & 1);
       } else {
-        pp_tile_load_slow<C, PL>(Q, K, s_img, s_p, rows, gt, PP_GROUP);
-        pp_group_sync(2);
+        pp_tile_load_slow<C, PL>(Q, K, s_img, s_p, rows, gt, PP_H_THREADS);
+        pp_sync_h();
       }
       PP_TR(1, j, 0);
-      pp_tile_transform<C, CS, SOFTMAX, PL>(Q, K, s_img, s_p, rows, gt, PP_GROUP);
+      pp_tile_transform<C, CS, SOFTMAX, PL>(Q, K, s_img, s_p, rows, gt, PP_H_THREADS);
       __syncwarp();
       if (lane == 0) pp_bar_arrive(&s_ready[b]);
       PP_TR(1, j, 1);
-      if (j >= 1) tail(j - 1);
-    }
-    tail(n_my - 1);
-
-    // ---- ticket: both roles of every CTA check in; the H warps of the last CTA add the partials ----
-    if (gt == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
-    if ((int)blockIdx.x != G - 1) return;
-    if (gt == 0) {
-      unsigned seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
-        if (seen < 2u * G) __nanosleep(200);
-      } while (seen < 2u * G);
-    }
-    pp_group_sync(2);
-    double wtot = 0.0;
-    for (int b = gw; b < Q.p.B; b += PP_GROUP / 32) {
-      double acc = 0.0;
-      for (int i = lane; i < kpi2; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)b * kpi2 + i);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (Q.p.per_image) {
-        if (lane == 0) Q.p.loss_out[b] = (float)(acc * Q.p.kappa);
-      } else {
-        wtot += acc;
-      }
-    }
-    if (!Q.p.per_image) {
-      if (lane == 0) s_dred[gw] = wtot;
-      pp_group_sync(2);
-      if (gt == 0) {
-        double t = 0.0;
-#pragma unroll
-        for (int i = 0; i < PP_GROUP / 32; ++i) t += s_dred[i];
-        Q.p.loss_out[0] = (float)(t * Q.p.kappa);
-      }
     }
     return;
   }
 
   // =============================== M: march ===============================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PP_M_REGS));
+  const int gw = tid >> 5;
   const int seg = gw * 2 + (lane >> 4), strip = lane & 15;
   const float ksu = Q.p.ks_unit;
   for (int j = 0; j < n_my; ++j) {
@@ -620,31 +552,27 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
     const PpBlk K = pp_tile(Q, tile);
     float* s_img = pp_smem + b * Cfg::BUF;
     float* s_p = s_img + 3 * PL;
-    float* s_head = s_img + (3 + C) * PL;
-    float* s_headp = s_head + Cfg::HEAD;
-    float* s_gband = s_headp + Cfg::HEAD;
     int okmask, bandmask;
     pp_masks(Q, K, strip, okmask, bandmask);
     float lsum = 0.f;
-    if (j >= 2) pp_bar_wait(&s_taildone[b], ((j - 2) >> 1) & 1);  // the head arrays of this buffer are free
     pp_bar_wait(&s_ready[b], (j >> 1) & 1);
     PP_TR(0, j, 0);
 
-    const int t0 = seg * S, t1 = min(t0 + S, K.nc);
-    float oy[4][CS], oz[4][CS];  // what this segment contributes to the first two rows of the next one
+    // two centre rows per segment: t0, t0 + 1.  Their G stays in registers until the segment above has handed over
+    // what it adds to them.
+    const int t0 = seg * 2;
+    float g0[4][CS], g1[4][CS], p0[4][CS], p1[4][CS];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int c = 0; c < CS; ++c) oy[q][c] = 0.f, oz[q][c] = 0.f;
-    if (gw * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
+      for (int c = 0; c < CS; ++c) g0[q][c] = 0.f, g1[q][c] = 0.f, p0[q][c] = 0.f, p1[q][c] = 0.f;
+    if (gw * 4 < K.nc) {  // warp-uniform: at least one of its two segments has rows
       float A[8][CS], Bq[8][CS], Cq[8][CS];
       pp_zero<CS>(A), pp_zero<CS>(Bq), pp_zero<CS>(Cq);
-#pragma unroll 1
-      for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
         const int t = t0 + s;
-        const bool act = t < t1;
-        float pc[4][CS], own[4][CS];
-        if (act) {
+        if (t < K.nc) {
           // exponent offsets of this centre row: spatial term + multiplicity of the row pairs at the top / bottom border
           const int y = K.ys - 2 + t;
           const float l0 = (y == 1 || y == H - 2) ? Q.l1g : 0.f;
@@ -654,76 +582,74 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
           ks.a1 = ksu + l0, ks.a4 = 4.f * ksu + l0;
           ks.b0 = ksu + l1, ks.b1 = 2.f * ksu + l1, ks.b4 = 5.f * ksu + l1;
           ks.c0 = 4.f * ksu + l2, ks.c1 = 5.f * ksu + l2, ks.c4 = 8.f * ksu + l2;
-          pp_step<CS, PL>(A, Bq, Cq, pc, s_img, s_p, t * PP_PITCH + 4 * strip, ks);
+          if (s == 0) pp_step<CS, PL>(A, Bq, Cq, p0, s_img, s_p, t * PP_PITCH + 4 * strip, ks);
+          else pp_step<CS, PL>(Bq, Cq, A, p1, s_img, s_p, t * PP_PITCH + 4 * strip, ks);
         }
-        pp_exchange<CS>(A, own, strip);
-        if (act) {
-          if (s >= 2) {
-            if (bandmask) {  // the band pass finishes these pixels from their G
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if ((bandmask >> q) & 1) {
-                  const int slot = pp_band_slot(K.x0 - 2 + 4 * strip + q, W);
-#pragma unroll
-                  for (int c = 0; c < CS; ++c) s_gband[(slot * CS + c) * CAP + (t - 2)] = own[q][c];
-                }
-            }
-            pp_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, bandmask, own, pc, lsum);
-          } else if (seg > 0) {
-#pragma unroll
-            for (int c = 0; c < CS; ++c) {
-              *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * CS + c) * 64 + 4 * strip) =
-                  make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
-              *reinterpret_cast<float4*>(s_headp + (((seg - 1) * 2 + s) * CS + c) * 64 + 4 * strip) =
-                  make_float4(pc[0][c], pc[1][c], pc[2][c], pc[3][c]);
-            }
-          }
+        if (s == 0) {
+          pp_exchange<CS>(A, g0, strip);
+          pp_zero<CS>(A);  // becomes the accumulator of row t0 + 3
+        } else {
+          pp_exchange<CS>(Bq, g1, strip);
         }
-#pragma unroll
-        for (int w = 0; w < 8; ++w)
-#pragma unroll
-          for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
       }
-      pp_exchange<CS>(A, oy, strip);
-      pp_exchange<CS>(Bq, oz, strip);
+      // rows t0 + 2 (Cq) and t0 + 3 (A) belong to the next segment: hand over what this one contributed
+      float oy[4][CS], oz[4][CS];
+      pp_exchange<CS>(Cq, oy, strip);
+      pp_exchange<CS>(A, oz, strip);
+      if (seg < PP_SEGS - 1) {
+#pragma unroll
+        for (int c = 0; c < CS; ++c) {
+          if (t0 + 2 < K.nc)
+            *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip) =
+                make_float4(oy[0][c], oy[1][c], oy[2][c], oy[3][c]);
+          if (t0 + 3 < K.nc)
+            *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip) =
+                make_float4(oz[0][c], oz[1][c], oz[2][c], oz[3][c]);
+        }
+      }
     }
     PP_TR(0, j, 1);
-    pp_group_sync(1);  // every head row holds its own segment's part
-    if (seg < PP_SEGS - 1) {  // rows t0+S, t0+S+1 belong to the next segment: add what this one contributed
+    pp_sync_m();  // the carries are in shared memory
+    if (seg > 0) {
 #pragma unroll
-      for (int c = 0; c < CS; ++c) {
-        if (t0 + S < K.nc) {
-          float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip);
-          float4 v = *h;
-          v.x += oy[0][c], v.y += oy[1][c], v.z += oy[2][c], v.w += oy[3][c];
-          *h = v;
-        }
-        if (t0 + S + 1 < K.nc) {
-          float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip);
-          float4 v = *h;
-          v.x += oz[0][c], v.y += oz[1][c], v.z += oz[2][c], v.w += oz[3][c];
-          *h = v;
+      for (int r = 0; r < 2; ++r) {
+        const int t = t0 + r;
+        if (t < K.nc) {
+          float(&g)[4][CS] = r == 0 ? g0 : g1;
+          const float(&pc)[4][CS] = r == 0 ? p0 : p1;
+#pragma unroll
+          for (int c = 0; c < CS; ++c) {
+            const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + r) * CS + c) * 64 + 4 * strip);
+            g[0][c] += k.x, g[1][c] += k.y, g[2][c] += k.z, g[3][c] += k.w;
+          }
+          if (bandmask) {  // the band pass finishes these pixels from their G
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if ((bandmask >> q) & 1) {
+                const int slot = pp_band_slot(K.x0 - 2 + 4 * strip + q, W);
+#pragma unroll
+                for (int c = 0; c < CS; ++c) s_gband[(slot * CS + c) * CAP + (t - 2)] = g[q][c];
+              }
+          }
+          pp_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, bandmask, g, pc, lsum);
         }
       }
     }
     if (K.xband) {
       // ---- band columns (and corners): G + weight correction -> the gradient of these pixels ----
-      pp_group_sync(1);  // heads and band G are complete
+      pp_sync_m();  // band G is complete
       const int xe = min(K.x0 + PP_TW, W);
       const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
       const int ncb = nlo + nhi;
       const size_t plane = (size_t)H * W;
-      for (int i = gt; i < ncb * K.n; i += PP_GROUP) {  // column fastest
+      for (int i = tid; i < ncb * K.n; i += PP_M_THREADS) {  // column fastest
         const int ty = i / ncb, k = i - ty * ncb;
         const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
         const int slot = pp_band_slot(x, W);
         float acc[CS], pz[CS], o[C];
         pp_xfix_item<CS, PL>(Q, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, acc, pz);
-        const int t = ty + 2, sg = t / S, sr = t - sg * S;
 #pragma unroll
-        for (int c = 0; c < CS; ++c)
-          acc[c] += (sg > 0 && sr < 2) ? s_head[(((sg - 1) * 2 + sr) * CS + c) * 64 + (x - K.x0 + 2)]
-                                       : s_gband[(slot * CS + c) * CAP + ty];
+        for (int c = 0; c < CS; ++c) acc[c] += s_gband[(slot * CS + c) * CAP + ty];
         lsum += pp_pixel_grad<C, CS, SOFTMAX>(K.scale2, pz, acc, o);
         if (Q.p.grad_values) {
           float* go = Q.p.grad_values + (size_t)K.b * C * plane + (size_t)y * W + x;
@@ -734,19 +660,53 @@ __global__ void __launch_bounds__(PP_THREADS, PP_CTAS_PER_SM)
     }
     PP_TR(0, j, 2);
     const float w = warp_sum(lsum);
-    if (lane == 0) s_red[0][j & 1][gw] = w;
-    pp_group_sync(1);  // nobody reads the planes any more; heads are final
-    if (gt == 0) {
+    if (lane == 0) s_red[j & 1][gw] = w;
+    pp_sync_m();  // nobody reads the planes, the carries or the band G of this tile any more
+    if (tid == 0) {
       float t = 0.f;
 #pragma unroll
-      for (int i = 0; i < PP_GROUP / 32; ++i) t += s_red[0][j & 1][i];
-      const int img = tile / (Q.nb * Q.n_x), within = tile - img * (Q.nb * Q.n_x);
-      __stcg(Q.p.partial + (size_t)img * kpi2 + 2 * within, 2.f * t);
+      for (int i = 0; i < PP_M_THREADS / 32; ++i) t += s_red[j & 1][i];
+      const int img = tile / kpi, within = tile - img * kpi;
+      __stcg(Q.p.partial + (size_t)img * kpi + within, 2.f * t);
       pp_bar_arrive(&s_marched[b]);
     }
     PP_TR(0, j, 3);
   }
-  if (gt == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
+
+  // ---- ticket: every CTA checks in; the M warps of the last CTA add the partials per image, in double ----
+  if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
+  if ((int)blockIdx.x != G - 1) return;
+  if (tid == 0) {
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
+      if (seen < (unsigned)G) __nanosleep(200);
+    } while (seen < (unsigned)G);
+    *Q.p.ticket = 0u;  // every CTA has checked in: leave the ticket ready for the next launch
+  }
+  pp_sync_m();
+  double wtot = 0.0;
+  for (int b = gw; b < Q.p.B; b += PP_M_THREADS / 32) {
+    double acc = 0.0;
+    for (int i = lane; i < kpi; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)b * kpi + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (Q.p.per_image) {
+      if (lane == 0) Q.p.loss_out[b] = (float)(acc * Q.p.kappa);
+    } else {
+      wtot += acc;
+    }
+  }
+  if (!Q.p.per_image) {
+    if (lane == 0) s_dred[gw] = wtot;
+    pp_sync_m();
+    if (tid == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < PP_M_THREADS / 32; ++i) t += s_dred[i];
+      Q.p.loss_out[0] = (float)(t * Q.p.kappa);
+    }
+  }
 }
 
 // Row blocks per column tile: at most `cap` rows each; among the next few candidates the count with the lowest
@@ -760,7 +720,7 @@ static int pp_row_blocks(int B, int H, int W, int cap) {
   for (int nb = nb_min; nb <= nb_min + 12; ++nb) {
     const int n = (H + nb - 1) / nb;  // rows of the largest block
     if (n < 6 && nb > nb_min) break;
-    const int S = (n + 2 + PP_SEGS - 1) / PP_SEGS < 2 ? 2 : (n + 2 + PP_SEGS - 1) / PP_SEGS;
+    const int S = 2;  // two rows per segment, always
     const double per_cta = (double)B * n_x * nb / slots;
     const double rounds = per_cta < 1.0 ? 1.0 : (double)(long long)(per_cta + 0.999999);
     const double cost = (S + 1.0) * rounds + 1.5;  // + the exposed load and conversion of the first tile
@@ -769,7 +729,7 @@ static int pp_row_blocks(int B, int H, int W, int cap) {
   return best;
 }
 
-static int pp_cap(int C, int inner_softmax) { return (C == 2 && inner_softmax) || C == 1 ? PP_SEGS * 4 - 2 : PP_SEGS * 3 - 2; }
+static int pp_cap(int, int) { return PP_SEGS * 2 - 2; }
 
 typedef CUresult (*PpEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -824,8 +784,7 @@ static int pp_launch_t(PpParams& Q, const CUtensorMap& tm_img, const CUtensorMap
 
 size_t pp_workspace_floats(int B, int H, int W) {
   const int n_x = (W + pp::PP_TW - 1) / pp::PP_TW;
-  const int a = pp::pp_row_blocks(B, H, W, pp::PP_SEGS * 4 - 2), b = pp::pp_row_blocks(B, H, W, pp::PP_SEGS * 3 - 2);
-  return 2 * (size_t)B * n_x * (a > b ? a : b);
+  return (size_t)B * n_x * pp::pp_row_blocks(B, H, W, pp::PP_SEGS * 2 - 2);
 }
 
 // returns 1 when the shape is not this kernel's (the caller then takes another one), 0 on success
@@ -839,8 +798,7 @@ int pp_launch(const PwParams& P, cudaStream_t s) {
   const long long n_tiles = (long long)Q.nb * Q.n_x * P.B;
   if (n_tiles > 0x3fffffffLL) return 1;
   Q.n_tiles = (int)n_tiles;
-  const int n_max = (P.H + Q.nb - 1) / Q.nb;
-  Q.S = (n_max + 2 + PP_SEGS - 1) / PP_SEGS < 2 ? 2 : (n_max + 2 + PP_SEGS - 1) / PP_SEGS;
+  Q.S = 2;
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
@@ -849,8 +807,8 @@ int pp_launch(const PwParams& P, cudaStream_t s) {
   memset(&tm_img, 0, sizeof(tm_img)), memset(&tm_val, 0, sizeof(tm_val));
   static const int no_tma = []() { const char* e = getenv("WSDL_PAIRWISE_NO_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
   Q.use_tma = !no_tma && ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0) &&
-              pp_encode(&tm_img, P.images, P.W, P.H, 3LL * P.B, PP_SEGS * Q.S + 2) &&
-              pp_encode(&tm_val, P.values, P.W, P.H, (long long)P.C * P.B, PP_SEGS * Q.S + 2);
+              pp_encode(&tm_img, P.images, P.W, P.H, 3LL * P.B, PP_SEGS * 2 + 2) &&
+              pp_encode(&tm_val, P.values, P.W, P.H, (long long)P.C * P.B, PP_SEGS * 2 + 2);
   if (P.C == 2)
     return P.inner_softmax ? pp_launch_t<2, true>(Q, tm_img, tm_val, s) : pp_launch_t<2, false>(Q, tm_img, tm_val, s);
   return P.inner_softmax ? pp_launch_t<1, true>(Q, tm_img, tm_val, s) : pp_launch_t<1, false>(Q, tm_img, tm_val, s);

@@ -708,6 +708,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
       if (seen < n_ctas) __nanosleep(200);
     } while (seen < n_ctas);
+    *Q.p.ticket = 0u;  // every CTA has checked in: leave the ticket ready for the next launch
   }
   __syncthreads();
   double wtot = 0.0;

@@ -118,6 +118,24 @@ def threshold_mask(cam: torch.Tensor, thresh: float, near_band: float = NEAR_BAN
     return mask, near
 
 
+_PAIR_WS = {}  # (device index, stream, bytes) -> prepared workspace (wsdl_pairwise_workspace_init, then self-cleaning)
+
+
+def _pairwise_workspace(lib, dev, nbytes: int) -> torch.Tensor:
+    """One prepared workspace per device, stream and size: calls on one stream are ordered, so they can share it;
+    it is initialised once and every kernel leaves it initialised (no per-call memset, no per-call allocation)."""
+    stream = _stream_ptr(dev)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, nbytes)
+    ws = _PAIR_WS.get(key)
+    if ws is None:
+        if len(_PAIR_WS) > 64:
+            _PAIR_WS.clear()
+        ws = torch.empty(max(nbytes, 512), dtype=torch.uint8, device=dev)
+        _native.check(lib.wsdl_pairwise_workspace_init(ws.data_ptr(), ws.numel(), stream), "wsdl_pairwise_workspace_init")
+        _PAIR_WS[key] = ws
+    return ws
+
+
 def _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softmax, divide_by_c, per_image, want_grad,
                   grad_out=None):
     B, C, H, W = values.shape
@@ -125,10 +143,10 @@ def _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softma
     lib = _native.lib()
     with torch.cuda.device(dev):
         nbytes = lib.wsdl_pairwise_workspace_bytes(B, H, W)
-        workspace = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        workspace = _pairwise_workspace(lib, dev, nbytes)
         loss = torch.empty(B if per_image else 1, dtype=torch.float32, device=dev)
         grad = torch.empty_like(values) if want_grad else None
-        rc = lib.wsdl_pairwise_fwd_bwd(
+        rc = lib.wsdl_pairwise_fwd_bwd_prepared(
             values.data_ptr(), images.data_ptr(), B, C, H, W, int(window), float(sigma_color),
             float(sigma_space) if sigma_space is not None else 0.0,
             int(inner_softmax), int(divide_by_c), int(per_image),
@@ -136,7 +154,7 @@ def _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softma
             loss.data_ptr(), grad.data_ptr() if grad is not None else None,
             workspace.data_ptr(), nbytes, _stream_ptr(dev),
         )
-    _native.check(rc, "wsdl_pairwise_fwd_bwd")
+    _native.check(rc, "wsdl_pairwise_fwd_bwd_prepared")
     return loss, grad
 
 
