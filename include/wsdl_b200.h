@@ -128,6 +128,20 @@ int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int
 int wsdl_affinities(const float* images, int B, int H, int W, int window, float sigma_color, float sigma_space,
                     float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Either side of the path.
+ * wsdl_labels_from_masks: masks (B,H,W) u8 {0,1} -> training labels (B,S,S) i64 {0,1}; what the reference gets from
+ * save_image (PsuedoMasks.py:67-69) -> PNG -> convert('L') + NEAREST resize + int64 (SegmentationDataset.py:21,26,35)
+ * -> clamp(max=1) (SegmentationModel.py:100), without the PNG round trip.
+ * wsdl_iou_acc_counts: counts[b] += {|pred>0 & true>0|, |pred>0 | true>0|, |pred == true|} over the n elements of
+ * image b (compute_iou_and_acc, ExtraUtilities.py:4-21); elem: 0 u8, 1 i32, 2 i64, 3 f32; counts (B,3) u64, zeroed by
+ * the caller.
+ * ------------------------------------------------------------------------------------- */
+int wsdl_labels_from_masks(const uint8_t* mask, int B, int H, int W, int out_size, long long* labels, void* stream);
+
+int wsdl_iou_acc_counts(const void* pred, const void* truth, int B, size_t n, int elem, unsigned long long* counts,
+                        void* stream);
+
 /* Scale of a saved gradient by a device scalar (autograd backward of the fused launch, whose
  * gradient was computed for an upstream gradient of 1): dst[i] = src[i] * scale[per ? i / per : 0].
  * dst may alias src. */

@@ -89,3 +89,50 @@ def refine_pseudo_mask(model, image, mask, lambda_boundary=0.1, threshold=0.5, l
     X_final = F.softmax(X, dim=1)
     pseudo_mask_refined = (X_final[0, 1] > threshold).float()
     return pseudo_mask_refined
+
+
+def refine_pseudo_masks_batched(model, images, masks, lambda_boundary=0.1, threshold=0.5, lr=1e-2, num_steps=20,
+                                sigma_color=0.1, window_size=5, return_state=False):
+    """`refine_pseudo_mask` (reference AlternatingDirectionCutLoss.py:709-767) for a whole batch at once, with
+    nothing on the host inside the step loop.
+
+    images (B,3,H,W), masks (B,H,W) holding {0,255}.  Every image keeps its own problem exactly as in the
+    reference -- its own KL term (batchmean over a batch of one), its own cut loss (the inner softmax of
+    LocalNormalizedCutLoss included, :745 -> :78) and its own dynamic weight lambda * KL / (cut + 1e-6) (:748) --
+    but the weight stays on the device: it is handed to the fused cut-loss launch as the per-image upstream gradient,
+    so the two `.item()` syncs per step and image of the reference disappear.  Adam on X with torch's defaults,
+    written out element-wise (identical for every image since Adam is element-wise).  Returns (B,H,W) float {0,1}."""
+    device = next(model.parameters()).device
+    images = images.to(device).float()
+    model.eval()
+    with torch.no_grad():
+        S = F.softmax(model(images)['out'], dim=1)
+    B = images.shape[0]
+    m = (masks.to(device) == 255).long()
+    X = F.one_hot(m, num_classes=2).permute(0, 3, 1, 2).float().contiguous()
+    exp_avg = torch.zeros_like(X)
+    exp_avg_sq = torch.zeros_like(X)
+    beta1, beta2, eps = 0.9, 0.999, 1e-8
+    lam = torch.full((B,), float(lambda_boundary), device=device)
+    for step in range(1, num_steps + 1):
+        Xn = F.softmax(X, dim=1)
+        # KL(S || Xn), reduction 'batchmean' with a batch of one: the sum over the image
+        logq = (Xn + 1e-8).log()
+        kl = (torch.xlogy(S, S) - S * logq).flatten(1).sum(1)                       # (B,)
+        # cut loss of every image and its gradient w.r.t. Xn: one fused launch for the whole batch
+        loss_b, g_b = WF.pairwise_loss_and_grad(Xn, images, window_size, sigma_color, None, True, True, True)
+        w = lam * kl / (loss_b + 1e-6)                                               # (B,), stays on the device
+        # d total / d Xn = -S / (Xn + 1e-8) + w * d cut / d Xn ; then through the outer softmax
+        gXn = -S / (Xn + 1e-8) + w.view(B, 1, 1, 1) * g_b
+        gX = Xn * (gXn - (gXn * Xn).sum(dim=1, keepdim=True))
+        # Adam (torch defaults: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad)
+        exp_avg.mul_(beta1).add_(gX, alpha=1 - beta1)
+        exp_avg_sq.mul_(beta2).addcmul_(gX, gX, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        denom = (exp_avg_sq.sqrt() / (bc2 ** 0.5)).add_(eps)
+        X.addcdiv_(exp_avg, denom, value=-lr / bc1)
+    Xf = F.softmax(X, dim=1)
+    refined = (Xf[:, 1] > threshold).float()
+    if return_state:
+        return refined, X, Xf
+    return refined

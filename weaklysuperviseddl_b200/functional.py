@@ -255,3 +255,46 @@ def keep_largest(mask: torch.Tensor, return_area: bool = False):
     _native.check(rc, "wsdl_keep_largest")
     out = out[0] if single else out
     return (out, area) if return_area else out
+
+
+_ELEM_CODE = {torch.uint8: 0, torch.bool: 0, torch.int32: 1, torch.int64: 2, torch.float32: 3}
+
+
+def iou_acc_counts(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
+    """ExtraUtilities.py:4-21 as one pass: (B,...) or (...) masks of one dtype -> (B,3) int64 device tensor
+    {intersection, union, equal} per image.  No host synchronisation."""
+    _require_cuda(pred, "pred_mask")
+    _require_cuda(true, "true_mask")
+    if pred.shape != true.shape:
+        raise ValueError(f"mask shapes differ: {tuple(pred.shape)} vs {tuple(true.shape)}")
+    if pred.dtype != true.dtype:
+        common = torch.promote_types(pred.dtype, true.dtype)
+        pred, true = pred.to(common), true.to(common)
+    if pred.dtype not in _ELEM_CODE:
+        pred, true = pred.float(), true.float()
+    p, t = pred.contiguous(), true.contiguous()
+    B = p.shape[0] if p.dim() >= 3 else 1
+    n = p.numel() // B
+    counts = torch.zeros((B, 3), dtype=torch.int64, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = _native.lib().wsdl_iou_acc_counts(p.data_ptr(), t.data_ptr(), B, n, _ELEM_CODE[p.dtype], counts.data_ptr(),
+                                               _stream_ptr(p.device))
+    _native.check(rc, "wsdl_iou_acc_counts")
+    return counts
+
+
+def labels_from_masks(masks: torch.Tensor, size: int = 256) -> torch.Tensor:
+    """Pseudo-masks (B,H,W) u8 {0,1} -> training labels (B,size,size) int64 {0,1}: the reference's PNG round trip
+    (PsuedoMasks.py:67-69 -> SegmentationDataset.py:21,26,35 -> SegmentationModel.py:100) without the files."""
+    _require_cuda(masks, "masks")
+    m = masks.unsqueeze(0) if masks.dim() == 2 else masks
+    if m.dim() != 3:
+        raise ValueError("masks must be (H,W) or (B,H,W)")
+    m = (m != 0).to(torch.uint8) if m.dtype != torch.uint8 else m
+    m = m.contiguous()
+    B, H, W = m.shape
+    out = torch.empty((B, size, size), dtype=torch.int64, device=m.device)
+    with torch.cuda.device(m.device):
+        rc = _native.lib().wsdl_labels_from_masks(m.data_ptr(), B, H, W, int(size), out.data_ptr(), _stream_ptr(m.device))
+    _native.check(rc, "wsdl_labels_from_masks")
+    return out[0] if masks.dim() == 2 else out
