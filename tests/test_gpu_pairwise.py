@@ -112,6 +112,8 @@ CASES = [
     (1, 2, 100, 120, 5, 0.1, 5.0, True, False, True),     # softmax + spatial term, two full tiles
     (1, 2, 90, 122, 5, 0.1, 5.0, False, False, True),     # 2-column last tile: its left halo centres feed tile 1
     (3, 2, 39, 44, 5, 0.05, None, True, True, False),     # several images per CTA range, rows split mid-image
+    (1, 2, 256, 256, 5, 0.1, None, True, True, False),    # the reference's own call (refine_pseudo_mask, CutLoss.py:745)
+    (1, 2, 300, 520, 5, 0.1, 5.0, False, False, True),    # tall/wide: many row blocks and column tiles, boundary form
 ]
 
 

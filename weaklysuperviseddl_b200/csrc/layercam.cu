@@ -15,7 +15,7 @@
 //     normalises the low-resolution map in place: c -= min; c /= (max(c) + 1e-8) with true
 //     IEEE division, exactly the reference's arithmetic (LayerCAM.py:62-67).
 //
-//  B  layercam_upsample_fuse  each thread owns one output column and walks down rows; the
+//  B  layercam_upsample_fuse  each thread owns four adjacent output columns and walks down rows; the
 //     horizontally interpolated values of the two low-resolution rows are kept in registers
 //     and reused for every output row of the same cell, in torch's rounding order
 //     (ATen/native/UpSample.h: horizontal first, then vertical).  Layers are averaged,
@@ -324,11 +324,13 @@ __device__ __forceinline__ float lerp2(float l0, float a, float l1, float b) {
   return __fadd_rn(__fmul_rn(l0, a), __fmul_rn(l1, b));  // no FMA contraction: matches the eager op order
 }
 
+constexpr int UP_COLS = 4;  // output columns per thread: one 32-bit mask store (128-bit CAM store) per row
+
 template <int NL>  // number of layers, 1..4: taps and row caches live in registers
 __global__ void __launch_bounds__(UP_THREADS) layercam_upsample_fuse(const __grid_constant__ UpParams P) {
   __shared__ Tap s_ytap[NL][UP_ROWS];
   const int tid = threadIdx.x;
-  const int x = blockIdx.x * UP_THREADS + tid;
+  const int x0 = (blockIdx.x * UP_THREADS + tid) * UP_COLS;
   const int y_begin = blockIdx.y * UP_ROWS;
   const int b = blockIdx.z;
   const int rows = min(UP_ROWS, P.out_h - y_begin);
@@ -338,55 +340,82 @@ __global__ void __launch_bounds__(UP_THREADS) layercam_upsample_fuse(const __gri
     if (rr < rows) s_ytap[l][rr] = make_tap(P.L[l].scale_y, y_begin + rr, P.L[l].h);
   }
   __syncthreads();
-  const bool in_x = x < P.out_w;
-  const int xc = in_x ? x : P.out_w - 1;
+  if (x0 >= P.out_w) return;
+  const int ncol = min(UP_COLS, P.out_w - x0);
+  const bool vec = (ncol == UP_COLS) && ((P.out_w & 3) == 0);  // aligned 4-column group
 
-  Tap xt[NL];
+  Tap xt[NL][UP_COLS];
   const float* base[NL];
   int cur0[NL], cur1[NL];
-  float h0[NL], h1[NL];
+  float h0[NL][UP_COLS], h1[NL][UP_COLS];
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
-    xt[l] = make_tap(P.L[l].scale_x, xc, P.L[l].w);
+#pragma unroll
+    for (int c = 0; c < UP_COLS; ++c) {
+      xt[l][c] = make_tap(P.L[l].scale_x, min(x0 + c, P.out_w - 1), P.L[l].w);
+      h0[l][c] = h1[l][c] = 0.f;
+    }
     base[l] = P.L[l].low + (size_t)b * P.L[l].h * P.L[l].w;
     cur0[l] = cur1[l] = -1;
-    h0[l] = h1[l] = 0.f;
   }
 
   unsigned near = 0;
-  const size_t out_base = ((size_t)b * P.out_h + y_begin) * P.out_w + xc;
+  const size_t out_base = ((size_t)b * P.out_h + y_begin) * P.out_w + x0;
   for (int rr = 0; rr < rows; ++rr) {
-    float s = 0.f;
+    float s[UP_COLS];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
       const Tap yt = s_ytap[l][rr];
-      if (yt.i0 != cur0[l] || yt.i1 != cur1[l]) {  // warp-uniform
+      if (yt.i0 != cur0[l] || yt.i1 != cur1[l]) {  // CTA-uniform
         const int w = P.L[l].w;
         if (yt.i0 == cur1[l]) {
-          h0[l] = h1[l];
+#pragma unroll
+          for (int c = 0; c < UP_COLS; ++c) h0[l][c] = h1[l][c];
         } else {
           const float* r0 = base[l] + (size_t)yt.i0 * w;
-          h0[l] = lerp2(xt[l].l0, __ldg(r0 + xt[l].i0), xt[l].l1, __ldg(r0 + xt[l].i1));
+#pragma unroll
+          for (int c = 0; c < UP_COLS; ++c)
+            h0[l][c] = lerp2(xt[l][c].l0, __ldg(r0 + xt[l][c].i0), xt[l][c].l1, __ldg(r0 + xt[l][c].i1));
         }
         if (yt.i1 == yt.i0) {
-          h1[l] = h0[l];
+#pragma unroll
+          for (int c = 0; c < UP_COLS; ++c) h1[l][c] = h0[l][c];
         } else {
           const float* r1 = base[l] + (size_t)yt.i1 * w;
-          h1[l] = lerp2(xt[l].l0, __ldg(r1 + xt[l].i0), xt[l].l1, __ldg(r1 + xt[l].i1));
+#pragma unroll
+          for (int c = 0; c < UP_COLS; ++c)
+            h1[l][c] = lerp2(xt[l][c].l0, __ldg(r1 + xt[l][c].i0), xt[l][c].l1, __ldg(r1 + xt[l][c].i1));
         }
         cur0[l] = yt.i0;
         cur1[l] = yt.i1;
       }
-      const float v = lerp2(yt.l0, h0[l], yt.l1, h1[l]);
-      s = (l == 0) ? v : s + v;  // python sum(): 0 + cam_0 + cam_1 ... (LayerCAM.py:74)
+#pragma unroll
+      for (int c = 0; c < UP_COLS; ++c) {
+        const float v = lerp2(yt.l0, h0[l][c], yt.l1, h1[l][c]);
+        s[c] = (l == 0) ? v : s[c] + v;  // python sum(): 0 + cam_0 + cam_1 ... (LayerCAM.py:74)
+      }
     }
-    float cam = (P.inv_layers != 0.f) ? s * P.inv_layers : __fdiv_rn(s, P.n_layers_f);
-    if (P.alpha_mode == 0) cam = pow_like_torch(fmaxf(cam, 0.f), P.alpha);  // LayerCAM.py:76
-    if (in_x) {
-      const size_t o = out_base + (size_t)rr * P.out_w;
-      if (P.cam_out) P.cam_out[o] = cam;
-      if (P.mask_out) P.mask_out[o] = (cam >= P.thresh && cam > 0.f) ? 1 : 0;  // PsuedoMasks.py:60-62
-      near += (fabsf(cam - P.thresh) < P.band) ? 1u : 0u;
+    float cam[UP_COLS];
+    unsigned bits = 0;
+#pragma unroll
+    for (int c = 0; c < UP_COLS; ++c) {
+      float v = (P.inv_layers != 0.f) ? s[c] * P.inv_layers : __fdiv_rn(s[c], P.n_layers_f);
+      if (P.alpha_mode == 0) v = pow_like_torch(fmaxf(v, 0.f), P.alpha);  // LayerCAM.py:76
+      cam[c] = v;
+      if (v >= P.thresh && v > 0.f) bits |= 1u << (8 * c);  // PsuedoMasks.py:60-62
+      if (c < ncol) near += (fabsf(v - P.thresh) < P.band) ? 1u : 0u;
+    }
+    const size_t o = out_base + (size_t)rr * P.out_w;
+    if (vec) {
+      if (P.cam_out) *reinterpret_cast<float4*>(P.cam_out + o) = make_float4(cam[0], cam[1], cam[2], cam[3]);
+      if (P.mask_out) *reinterpret_cast<unsigned*>(P.mask_out + o) = bits;
+    } else {
+#pragma unroll
+      for (int c = 0; c < UP_COLS; ++c)
+        if (c < ncol) {
+          if (P.cam_out) P.cam_out[o + c] = cam[c];
+          if (P.mask_out) P.mask_out[o + c] = (uint8_t)((bits >> (8 * c)) & 1u);
+        }
     }
   }
   if (P.near_count) {
@@ -625,11 +654,12 @@ extern "C" int wsdl_layercam_fused(const void* const* act, const void* const* gr
   U.near_count = near_count;
   dim3 grid((out_w + UP_THREADS - 1) / UP_THREADS, (out_h + UP_ROWS - 1) / UP_ROWS, B);
   if (grid.y > 65535) return WSDL_E_SHAPE;
+  dim3 grid4((out_w + UP_THREADS * UP_COLS - 1) / (UP_THREADS * UP_COLS), grid.y, B);  // 4 columns per thread
   switch (n_layers) {
-    case 1: layercam_upsample_fuse<1><<<grid, UP_THREADS, 0, s>>>(U); break;
-    case 2: layercam_upsample_fuse<2><<<grid, UP_THREADS, 0, s>>>(U); break;
-    case 3: layercam_upsample_fuse<3><<<grid, UP_THREADS, 0, s>>>(U); break;
-    case 4: layercam_upsample_fuse<4><<<grid, UP_THREADS, 0, s>>>(U); break;
+    case 1: layercam_upsample_fuse<1><<<grid4, UP_THREADS, 0, s>>>(U); break;
+    case 2: layercam_upsample_fuse<2><<<grid4, UP_THREADS, 0, s>>>(U); break;
+    case 3: layercam_upsample_fuse<3><<<grid4, UP_THREADS, 0, s>>>(U); break;
+    case 4: layercam_upsample_fuse<4><<<grid4, UP_THREADS, 0, s>>>(U); break;
     default: layercam_upsample_fuse_generic<<<grid, UP_THREADS, 0, s>>>(U); break;
   }
   WSDL_LAUNCH_CHECK();
