@@ -361,6 +361,10 @@ __global__ void __launch_bounds__(UP_THREADS) layercam_upsample_fuse(const __gri
 
   unsigned near = 0;
   const size_t out_base = ((size_t)b * P.out_h + y_begin) * P.out_w + x0;
+  // launch-uniform choices, hoisted out of the pixel loop
+  const bool mean_by_mul = P.inv_layers != 0.f;
+  const int shape = P.alpha_mode != 0 ? 0 : (P.alpha == 1.0f ? 1 : 2);  // 0: as is, 1: clamp only, 2: clamp + pow
+  const bool count_near = P.near_count != nullptr;
   for (int rr = 0; rr < rows; ++rr) {
     float s[UP_COLS];
 #pragma unroll
@@ -399,11 +403,12 @@ __global__ void __launch_bounds__(UP_THREADS) layercam_upsample_fuse(const __gri
     unsigned bits = 0;
 #pragma unroll
     for (int c = 0; c < UP_COLS; ++c) {
-      float v = (P.inv_layers != 0.f) ? s[c] * P.inv_layers : __fdiv_rn(s[c], P.n_layers_f);
-      if (P.alpha_mode == 0) v = pow_like_torch(fmaxf(v, 0.f), P.alpha);  // LayerCAM.py:76
+      float v = mean_by_mul ? s[c] * P.inv_layers : __fdiv_rn(s[c], P.n_layers_f);
+      if (shape == 1) v = fmaxf(v, 0.f);                              // clamp(0) ** 1
+      else if (shape == 2) v = pow_like_torch(fmaxf(v, 0.f), P.alpha);  // LayerCAM.py:76
       cam[c] = v;
       if (v >= P.thresh && v > 0.f) bits |= 1u << (8 * c);  // PsuedoMasks.py:60-62
-      if (c < ncol) near += (fabsf(v - P.thresh) < P.band) ? 1u : 0u;
+      if (count_near && c < ncol) near += (fabsf(v - P.thresh) < P.band) ? 1u : 0u;
     }
     const size_t o = out_base + (size_t)rr * P.out_w;
     if (vec) {
