@@ -104,6 +104,15 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_pairwise_sample(sample_B, reps, threads):
     """The reference's CPU path for configs[1] (oracle port: same ATen op sequence as
@@ -157,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------ B200 arm
@@ -176,6 +185,11 @@ def main():
         args.steps = 30 if args.impl == "reference" else 4000
     if args.warmup is None:
         args.warmup = 3 if args.impl == "reference" else 200
+    # ONE JSON line on stdout: anything a library prints there (NCCL's version banner, ...) goes to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -201,7 +215,7 @@ def main():
     else:
         res = bench_pairwise(args, lib, dev, rank, world)
     if rank == 0:
-        print(json.dumps(res), flush=True)
+        _emit(res)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
