@@ -537,6 +537,26 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       __syncwarp();
     }
     PS_TR(1);
+    if (Q.use_tma && tid == 0) {
+      // This CTA's tile has landed: pull the tile of the CTA that will take over an SM slot one wave from now into
+      // L2, so that its load is an L2 hit instead of a second trip to HBM behind everybody else's.
+      const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      const unsigned nxt = cta + (unsigned)WSDL_NUM_SMS * PsCfg<C, SOFTMAX>::CTAS;
+      if (nxt < gridDim.x * gridDim.y * gridDim.z) {
+        const unsigned rb = nxt % gridDim.x, rest = nxt / gridDim.x;
+        const unsigned tx = rest % gridDim.y, nb_img = rest / gridDim.y;
+        const int base = H / Q.nb, extra = H - base * Q.nb;
+        const int ys2 = (int)rb * base + min((int)rb, extra);
+#pragma unroll
+        for (int c = 0; c < 3 + C; ++c) {
+          const CUtensorMap* tm = c < 3 ? &tm_img : &tm_val;
+          const int pl = c < 3 ? (int)nb_img * 3 + c : (int)nb_img * C + (c - 3);
+          asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm),
+                       "r"((int)tx * PS_TW - 4), "r"(ys2 - 2), "r"(pl)
+                       : "memory");
+        }
+      }
+    }
 #ifndef WSDL_X_NOTRANSFORM
     ps_rows_transform<C, CS, SOFTMAX>(Q, K, s_img, s_p, r0, re, lane);
 #endif
