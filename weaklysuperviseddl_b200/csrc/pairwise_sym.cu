@@ -528,9 +528,12 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     const int r0 = min(2 * warp * S, rows), r1 = warp == 3 ? rows : min(2 * (warp + 1) * S, rows);
     const int re = min(r0 + 2, r1);  // the two rows the warp above looks ahead into
     if (Q.use_tma) {
+      // try_wait suspends the warp in hardware (up to the hint) instead of spinning: waiting warps must not take
+      // issue slots from the CTAs that are marching on the same SM
       asm volatile(
-          "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(
-              ps_smem_u32(&s_bar))
+          "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0, %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(
+              ps_smem_u32(&s_bar)),
+          "r"(20000u)
           : "memory");
     } else {
       ps_rows_load_slow<C>(Q, K, s_img, s_p, r0, r1, lane);
