@@ -471,11 +471,9 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   PsBlk K;
   K.b = blockIdx.z;
   K.x0 = blockIdx.y * PS_TW;
-  {  // balanced split of the H rows over the nb row blocks: the first H % nb blocks have one row more
-    const int base = H / Q.nb, extra = H - base * Q.nb, i = blockIdx.x;
-    K.ys = i * base + min(i, extra);
-    K.n = base + (i < extra ? 1 : 0);
-  }
+  // full blocks of 8 S - 2 rows (every segment row is used), the remainder in the last block of the column
+  K.ys = blockIdx.x * (PS_SEGS * S - 2);
+  K.n = min(PS_SEGS * S - 2, H - K.ys);
   K.nc = K.n + 2;
   const int xe = min(K.x0 + PS_TW, W);  // owned pixels [x0, xe) x [ys, ys + n)
   K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
@@ -548,8 +546,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       if (nxt < gridDim.x * gridDim.y * gridDim.z) {
         const unsigned rb = nxt % gridDim.x, rest = nxt / gridDim.x;
         const unsigned tx = rest % gridDim.y, nb_img = rest / gridDim.y;
-        const int base = H / Q.nb, extra = H - base * Q.nb;
-        const int ys2 = (int)rb * base + min((int)rb, extra);
+        const int ys2 = (int)rb * (PS_SEGS * S - 2);
 #pragma unroll
         for (int c = 0; c < 3 + C; ++c) {
           const CUtensorMap* tm = c < 3 ? &tm_img : &tm_val;
@@ -841,6 +838,7 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   if (Q.nb > 65535 || Q.n_x > 65535 || P.B > 65535) return 1;
   const int n_max = (P.H + Q.nb - 1) / Q.nb;
   Q.S = (n_max + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n_max + 2 + PS_SEGS - 1) / PS_SEGS;
+  Q.nb = (P.H + PS_SEGS * Q.S - 3) / (PS_SEGS * Q.S - 2);  // blocks of 8 S - 2 rows: never more than the model chose
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
