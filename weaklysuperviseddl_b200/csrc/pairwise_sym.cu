@@ -374,11 +374,16 @@ __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk
     for (int c = 0; c < C; ++c) u[c] = *reinterpret_cast<const float4*>(s_val + c * PS_PLANE + so);
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = make_float4(v[c].x * sc, v[c].y * sc, v[c].z * sc, v[c].w * sc);
-    if (!row_in || xb < 0 || xb + 3 >= W) {  // some element lies outside the image
-      if (!row_in || xb + 0 < 0 || xb + 0 >= W) v[0].x = PS_SENTINEL;
-      if (!row_in || xb + 1 < 0 || xb + 1 >= W) v[0].y = PS_SENTINEL;
-      if (!row_in || xb + 2 < 0 || xb + 2 >= W) v[0].z = PS_SENTINEL;
-      if (!row_in || xb + 3 < 0 || xb + 3 >= W) v[0].w = PS_SENTINEL;
+    if (!row_in || xb < 0 || xb + 3 >= W) {  // some element lies outside the image (rare: border tiles only)
+      const bool all_out = !row_in || xb + 3 < 0 || xb >= W;
+      if (all_out) {
+        v[0] = make_float4(PS_SENTINEL, PS_SENTINEL, PS_SENTINEL, PS_SENTINEL);
+      } else {  // a group straddling the border: widths that are not a multiple of 4
+        if (xb + 0 < 0 || xb + 0 >= W) v[0].x = PS_SENTINEL;
+        if (xb + 1 < 0 || xb + 1 >= W) v[0].y = PS_SENTINEL;
+        if (xb + 2 < 0 || xb + 2 >= W) v[0].z = PS_SENTINEL;
+        if (xb + 3 < 0 || xb + 3 >= W) v[0].w = PS_SENTINEL;
+      }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = v[c];
@@ -731,17 +736,37 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     *Q.p.ticket = 0u;  // every CTA has checked in: leave the ticket ready for the next launch
   }
   __syncthreads();
+  // The tile is no longer needed: stage the partials of a group of images in its shared memory with independent
+  // loads (one L2 round trip instead of one per image), then add them per image in a fixed order.
   double wtot = 0.0;
-  for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {
-    double acc = 0.0;
-    for (int i = lane; i < kpi; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)b * kpi + i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (Q.p.per_image) {
-      if (lane == 0) Q.p.loss_out[b] = (float)(acc * Q.p.kappa);
-    } else {
-      wtot += acc;
+  float* s_part = ps_smem;
+  constexpr int STAGE = 3 * PS_PLANE;  // floats available
+  const int ipc = kpi <= STAGE ? STAGE / kpi : 0;  // images per staged group (0: partials of one image do not fit)
+  for (int b0 = 0; b0 < Q.p.B; b0 += (ipc ? ipc : 1)) {
+    const int nb_img = ipc ? min(ipc, Q.p.B - b0) : 1;
+    if (ipc) {
+      const int n = nb_img * kpi;
+      const float* src = Q.p.partial + (size_t)b0 * kpi;
+#pragma unroll 8
+      for (int i = tid; i < n; i += PS_THREADS) s_part[i] = ld_cg_f32(src + i);
+      __syncthreads();
     }
+    for (int b = warp; b < nb_img; b += PS_THREADS / 32) {
+      double acc = 0.0;
+      if (ipc) {
+        for (int i = lane; i < kpi; i += 32) acc += (double)s_part[b * kpi + i];
+      } else {
+        for (int i = lane; i < kpi; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)(b0 + b) * kpi + i);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (Q.p.per_image) {
+        if (lane == 0) Q.p.loss_out[b0 + b] = (float)(acc * Q.p.kappa);
+      } else {
+        wtot += acc;
+      }
+    }
+    if (ipc) __syncthreads();  // the next group overwrites the stage
   }
   if (!Q.p.per_image) {
     if (lane == 0) s_dred[warp] = wtot;
