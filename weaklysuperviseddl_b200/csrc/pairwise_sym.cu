@@ -18,8 +18,8 @@
 // contributions it makes to rows t+1, t+2 live in three rotating accumulator rows in registers, the ones it makes
 // to the 2 columns either side of its strip go to the neighbouring lanes by warp shuffle when a row completes.
 // 16 strips (a half warp) span the 64 staged columns of a tile (60 owned + 2 halo each side), 8 segments span the
-// block's rows; the first two rows of a segment are completed by the two rows its upper neighbour carries over,
-// through shared memory.  A CTA is one block: up to 30 rows of one 60-column tile of one image (grid = row blocks x
+// block's rows; the first two rows of a segment are completed by what its upper neighbour adds to them, through
+// shared memory after the march.  A CTA is one block: up to 30 rows of one 60-column tile of one image (grid = row blocks x
 // column tiles x images, a few CTAs per SM slot so that the loads of one overlap the march of the others); it
 // pays 2 warm-up rows instead of a halo in y.
 //
@@ -429,9 +429,9 @@ __device__ __forceinline__ void ps_zero(float (&X)[8][CS]) {
 template <int C, bool SOFTMAX>
 struct PsCfg {
   static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // accumulated channels
-  static constexpr int CTAS = CS == 1 ? WSDL_PS_CTAS : WSDL_PS_CTAS - 1;  // resident CTAs per SM (registers)
+  static constexpr int CTAS = WSDL_PS_CTAS;               // resident CTAs per SM (<= 128 registers per thread)
   static constexpr size_t smem_floats =
-      (size_t)(3 + C) * PS_PLANE + 2 * (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 10;
+      (size_t)(3 + C) * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 10;
 };
 
 #ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_ctas.py): per-warp timestamps of the phase boundaries
@@ -458,9 +458,8 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   extern __shared__ __align__(128) float ps_smem[];
   float* s_img = ps_smem;                                 // [3][PS_ROWS][PS_PITCH]: raw, then pre-scaled
   float* s_p = s_img + 3 * PS_PLANE;                      // [C][PS_ROWS][PS_PITCH]: raw values, then probabilities
-  float* s_head = s_p + C * PS_PLANE;                     // [7][2][CS][64]: first two rows of segments 1..7, own part
-  float* s_carry = s_head + (PS_SEGS - 1) * 2 * CS * 64;  // [7][2][CS][64]: the same rows, upper neighbour's part
-  float* s_gband = s_carry + (PS_SEGS - 1) * 2 * CS * 64; // [6][CS][PS_CAP]: G of the band-column pixels
+  float* s_head = s_p + C * PS_PLANE;                     // [7][2][CS][64]: G of the first two rows of segments 1..7
+  float* s_gband = s_head + (PS_SEGS - 1) * 2 * CS * 64;  // [6][CS][PS_CAP]: G of the band-column pixels
   float* s_wx = s_gband + 6 * CS * PS_CAP;                // [6][2][5]: column weights of the 6 band slots
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ float s_red[PS_THREADS / 32];
@@ -578,6 +577,11 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 
   // ---- march ----
   const int t0 = seg * S, t1 = min(t0 + S, K.nc);
+  float oy[4][CS], oz[4][CS];  // what this segment adds to the first two rows of the next one
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < CS; ++c) oy[q][c] = 0.f, oz[q][c] = 0.f;
 #ifdef WSDL_X_NOMARCH
   if (false) {
 #else
@@ -622,28 +626,33 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       if (s < 4) PS_TR(5 + s);
 #endif
     }
-    {  // rows t0+S, t0+S+1 belong to the next segment: hand over what this one contributed to them
-      float oy[4][CS], oz[4][CS];
-      ps_exchange<CS>(A, oy, strip);
-      ps_exchange<CS>(Bq, oz, strip);
-      if (seg < PS_SEGS - 1) {
+    // rows t0+S, t0+S+1 belong to the next segment: what this one contributed to them is added after the barrier
+    ps_exchange<CS>(A, oy, strip);
+    ps_exchange<CS>(Bq, oz, strip);
+  }
+  PS_TR(9);
+  __syncthreads();  // every head row holds its own segment's part
+  if (seg < PS_SEGS - 1) {  // exactly one thread adds to each element: the strip of the segment above
 #pragma unroll
-        for (int c = 0; c < CS; ++c) {
-          if (t0 + S < K.nc)
-            *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip) =
-                make_float4(oy[0][c], oy[1][c], oy[2][c], oy[3][c]);
-          if (t0 + S + 1 < K.nc)
-            *reinterpret_cast<float4*>(s_carry + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip) =
-                make_float4(oz[0][c], oz[1][c], oz[2][c], oz[3][c]);
-        }
+    for (int c = 0; c < CS; ++c) {
+      if (t0 + S < K.nc) {
+        float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 0) * CS + c) * 64 + 4 * strip);
+        float4 v = *h;
+        v.x += oy[0][c], v.y += oy[1][c], v.z += oy[2][c], v.w += oy[3][c];
+        *h = v;
+      }
+      if (t0 + S + 1 < K.nc) {
+        float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 1) * CS + c) * 64 + 4 * strip);
+        float4 v = *h;
+        v.x += oz[0][c], v.y += oz[1][c], v.z += oz[2][c], v.w += oz[3][c];
+        *h = v;
       }
     }
   }
-  PS_TR(9);
   __syncthreads();
   PS_TR(10);
 
-  // ---- the first two rows of segments 1..7: own part + the upper neighbour's carry ----
+  // ---- the first two rows of segments 1..7, now complete ----
 #ifdef WSDL_X_NOTAIL
   if (false) {
 #else
@@ -657,8 +666,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #pragma unroll
         for (int c = 0; c < CS; ++c) {
           const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
-          const float4 k = *reinterpret_cast<const float4*>(s_carry + (((seg - 1) * 2 + i) * CS + c) * 64 + 4 * strip);
-          G[0][c] = h.x + k.x, G[1][c] = h.y + k.y, G[2][c] = h.z + k.z, G[3][c] = h.w + k.w;
+          G[0][c] = h.x, G[1][c] = h.y, G[2][c] = h.z, G[3][c] = h.w;
           const float2 p01 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 2);
           const float2 p23 = *reinterpret_cast<const float2*>(s_p + c * PS_PLANE + t * PS_PITCH + 4 * strip + 4);
           pc[0][c] = p01.x, pc[1][c] = p01.y, pc[2][c] = p23.x, pc[3][c] = p23.y;
