@@ -1,4 +1,6 @@
+# per-warp phase trace of the default pairwise kernel (needs weaklysuperviseddl_b200/libwsdl_b200_trace.so, built
+# with WSDL_NVCC_EXTRA=-DWSDL_PS_TRACE); set TRACE=pipe for the persistent variant
 cp weaklysuperviseddl_b200/libwsdl_b200.so /tmp/keep.so
 cp weaklysuperviseddl_b200/libwsdl_b200_trace.so weaklysuperviseddl_b200/libwsdl_b200.so
-for pad in 0 20 55 120; do echo "=== smem pad $pad KB"; WSDL_PS_SMEM_PAD_KB=$pad PYTHONPATH=. python scripts/trace_ctas.py 2>&1 | grep -A30 "== cut" | grep -E "== cut|first wave|step[0-3]|march end|CTA lifetime|per-SM"; done
+if [ "$TRACE" = "pipe" ]; then WSDL_PAIRWISE_PIPE=1 PYTHONPATH=. python scripts/trace_pipe.py 2>&1 | grep -v Warn; else PYTHONPATH=. python scripts/trace_ctas.py 2>&1 | grep -v Warn; fi
 cp /tmp/keep.so weaklysuperviseddl_b200/libwsdl_b200.so
