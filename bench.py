@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--one-stream", action="store_true")
+    ap.add_argument("--stream-pairs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
@@ -274,32 +276,64 @@ def bench_pairwise(args, lib, dev, rank, world):
     sets, ws, nws, loss_cut, loss_bnd = make_pairwise_state(lib, dev, 1 + rank)
     sp = lambda: torch.cuda.current_stream(dev).cuda_stream
 
-    def one_step(i):
+    # The two launches of a step are independent (cut loss on the logits, boundary loss on the probabilities): they go
+    # to two streams, each with its own prepared workspace, so that CTAs of one kernel fill the SM slots the other
+    # leaves idle while it ramps up, waits for tiles or drains.  `--one-stream` keeps them on one stream.
+    two = not args.one_stream
+    n_pairs = max(1, args.stream_pairs) if two else 1  # consecutive steps rotate over this many stream pairs
+    lanes = []
+    for _ in range(n_pairs):
+        st = (torch.cuda.Stream(dev), torch.cuda.Stream(dev)) if two else (None, None)
+        wss = [torch.empty(nws, dtype=torch.uint8, device=dev) for _ in range(2)]
+        for w in wss:
+            _native_check(lib.wsdl_pairwise_workspace_init(w.data_ptr(), nws, torch.cuda.current_stream(dev).cuda_stream))
+        lanes.append((st, wss, torch.empty(1, device=dev), torch.empty(B, device=dev)))
+    torch.cuda.synchronize(dev)
+
+    def launch_cut(i, stream_ptr, w, out=None):
         logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
-        rc = lib.wsdl_pairwise_fwd_bwd_prepared(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_cut"],
-                                       0.0, 1, 1, 0, None, loss_cut.data_ptr(), g_cut.data_ptr(), ws.data_ptr(), nws, sp())
-        _native_check(rc)
-        rc = lib.wsdl_pairwise_fwd_bwd_prepared(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_bnd"],
-                                       PAIR["sigma_space"], 0, 0, 1, None, loss_bnd.data_ptr(), g_bnd.data_ptr(),
-                                       ws.data_ptr(), nws, sp())
-        _native_check(rc)
+        _native_check(lib.wsdl_pairwise_fwd_bwd_prepared(
+            logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_cut"], 0.0, 1, 1, 0, None,
+            (out if out is not None else loss_cut).data_ptr(), g_cut.data_ptr(), w.data_ptr(), nws, stream_ptr))
+
+    def launch_bnd(i, stream_ptr, w, out=None):
+        logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
+        _native_check(lib.wsdl_pairwise_fwd_bwd_prepared(
+            probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_bnd"], PAIR["sigma_space"], 0, 0, 1,
+            None, (out if out is not None else loss_bnd).data_ptr(), g_bnd.data_ptr(), w.data_ptr(), nws, stream_ptr))
+
+    def some_steps(idx):  # fork from the current stream, launch, join back
+        cur = torch.cuda.current_stream(dev)
+        if not two:
+            for i in idx:
+                launch_cut(i, cur.cuda_stream, ws)
+                launch_bnd(i, cur.cuda_stream, ws)
+            return
+        for (sc, sb), _, _, _ in lanes:
+            sc.wait_stream(cur)
+            sb.wait_stream(cur)
+        for i in idx:
+            (sc, sb), wss, lc, lb = lanes[i % n_pairs]
+            launch_cut(i, sc.cuda_stream, wss[0], lc)
+            launch_bnd(i, sb.cuda_stream, wss[1], lb)
+        for (sc, sb), _, _, _ in lanes:
+            cur.wait_stream(sc)
+            cur.wait_stream(sb)
 
     graph = None
     if not args.no_graph:
-        for i in range(N_SETS):
-            one_step(i)
+        some_steps(range(N_SETS))
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for i in range(N_SETS):
-                one_step(i)
+            some_steps(range(N_SETS))
 
     def run_steps(n):
         full, rem = (n // N_SETS, n % N_SETS) if graph is not None else (0, n)
         for _ in range(full):
             graph.replay()
-        for i in range(rem):
-            one_step(i)
+        if rem:
+            some_steps(range(rem))
 
     sampler = ClockSampler(dev.index) if rank == 0 else None
     ms, clocks = _timed(run_steps, args.warmup, args.steps, dev, world, sampler)
@@ -323,16 +357,7 @@ def bench_pairwise(args, lib, dev, rank, world):
     for name, which in (("cut", 0), ("boundary", 1)):  # each launch alone, CUDA events on the launching stream
         def only(n, which=which):
             for i in range(n):
-                logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
-                if which == 0:
-                    rc = lib.wsdl_pairwise_fwd_bwd_prepared(logits.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
-                                                   PAIR["sigma_cut"], 0.0, 1, 1, 0, None, loss_cut.data_ptr(),
-                                                   g_cut.data_ptr(), ws.data_ptr(), nws, sp())
-                else:
-                    rc = lib.wsdl_pairwise_fwd_bwd_prepared(probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"],
-                                                   PAIR["sigma_bnd"], PAIR["sigma_space"], 0, 0, 1, None,
-                                                   loss_bnd.data_ptr(), g_bnd.data_ptr(), ws.data_ptr(), nws, sp())
-                _native_check(rc)
+                (launch_cut if which == 0 else launch_bnd)(i, sp(), ws)
         t_ms, _ = _timed(only, 20, 200, dev, world, None)
         per_kernel[name] = t_ms / 200
     res = {
@@ -345,15 +370,19 @@ def bench_pairwise(args, lib, dev, rank, world):
             "step": "1 cut fwd+bwd launch (logits, sigma 0.05) + 1 boundary fwd+bwd launch (32 images, sigma 0.1/5); "
                     "pixels counted once per loss",
             "l2": f"rotating {N_SETS} input sets ({N_SETS * 45} MB) > {L2_MB} MB L2",
-            "launch": "CUDA graph of 8 steps" if graph is not None else "direct C-ABI calls",
+            "launch": ("CUDA graph of 8 steps" if graph is not None else "direct C-ABI calls") +
+                      (f"; the cut and the boundary launch of a step on two streams, consecutive steps on {n_pairs} stream "
+                       "pairs (independent work, own workspaces)" if two else "; one stream"),
             "sharding": "batch per rank, no data-path collective",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES, "kernel": "pairwise_sym_kernel<2,true|false>",
                      "algorithmic_bytes_per_launch": BYTES_PER_PIX * B * H * W, "launch_ms": launch_ms,
                      "peak_source": peak_src, "per_kernel_ms_direct_launch": per_kernel,
-                     "note": "launch duration = timed step / 2 launches (CUDA events on the launching stream, inside "
-                             "the graph); traffic = dram__bytes_read+write per launch from profiles/r01_c_ncu_full_sym.txt "
+                     "note": "launch duration = timed step / 2 launches (CUDA events on the stream the step is forked from "
+                             "and joined to, inside the graph; with two streams the launches of a step overlap, so this "
+                             "is the time the step spends per launch, not a kernel duration: those are in "
+                             "per_kernel_ms_direct_launch); traffic = dram__bytes_read+write per launch from profiles/r01_c_ncu_full_sym.txt "
                              "(the 12.8 MB gradient is still dirty in L2 when the kernel ends); the kernel is bound by "
                              "FP32/MUFU issue, not HBM (DESIGN.md 4.2)"},
         "gpu_launches": 2 * args.steps,
