@@ -138,10 +138,59 @@ def cpu_pairwise_sample(sample_B, reps, threads):
     return 2 * sample_B * H * W / best / 1e9, best
 
 
+def cpu_layercam_sample(n_images, reps, threads):
+    """The reference's CPU path for configs[2] after the backbone (oracle port of LayerCAM.py:52-76 + the threshold
+    idiom of PsuedoMasks.py:59-62), one image at a time as the reference does, 512x512-sized hooks."""
+    import torch
+
+    from oracle import wsdl_oracle as O
+
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(1)
+    S, layers = LCAM["S"], LCAM["layers"]
+    acts = [torch.randn(n_images, C, h, w, generator=gen).relu_() for (C, h, w) in layers]
+    grads = [torch.randn(n_images, C, h, w, generator=gen).mul_(1e-3) for (C, h, w) in layers]
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for i in range(n_images):
+            cam = O.layercam_from_hooks([a[i:i + 1] for a in acts], [g[i:i + 1] for g in grads], (S, S), alpha=LCAM["alpha"])
+            O.threshold_mask(cam[0], LCAM["thresh"])
+        best = min(best, time.perf_counter() - t0)
+    return n_images / best, best
+
+
+def run_reference_layercam(args):
+    import torch
+
+    threads = os.cpu_count() or 1
+    n_img = 4
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, t = cpu_layercam_sample(n_img, 1, threads)
+        if i >= args.warmup:
+            times.append(t)
+    value = n_img * len(times) / sum(times)
+    _emit({
+        "impl": "reference", "metric": "pseudo-masks/s", "value": value, "unit": "masks/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(times) / len(times) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[2]: LayerCAM->normalise->threshold after the backbone, 512x512, layers 3+4",
+                   "sample": f"{n_img} images per step, one at a time"},
+        "cpu_baseline": {"value": value, "unit": "masks/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_img} images per step; oracle port of LayerCAM.py:52-76 + PsuedoMasks.py:59-62 "
+                                   f"(torch {torch.__version__} CPU)"},
+        "e2e": {"value": value, "unit": "masks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "layercam":
+        return run_reference_layercam(args)
     import torch
 
     threads = os.cpu_count() or 1
@@ -566,7 +615,16 @@ def bench_layercam(args, lib, dev, rank, world):
         "config": {"workload": "configs[2]: fused LayerCAM->normalise->threshold, 512x512, image-sharded; "
                                f"{LCAM['chunk']} images per step per GPU", "l2": core["l2"]},
         "roofline": core["roofline"], "gpu_launches": 2 * steps, "extra": core,
+        **({"cpu_baseline": _layercam_cpu_baseline()} if (world == 1 and rank == 0 and not args.no_cpu_baseline) else {}),
     }
+
+
+def _layercam_cpu_baseline():
+    threads = os.cpu_count() or 1
+    v, t = cpu_layercam_sample(4, 2, threads)
+    return {"value": v, "unit": "masks/s", "cores": threads, "kind": "port",
+            "sample": f"4 images of 512x512-sized hooks, one at a time, best of 2, {t:.2f} s; oracle port of "
+                      "LayerCAM.py:52-76 + PsuedoMasks.py:59-62"}
 
 
 if __name__ == "__main__":
