@@ -845,7 +845,11 @@ static bool ps_encode(CUtensorMap* tm, const float* base, int W, int H, long lon
 template <int C, bool SOFTMAX>
 static int ps_launch_t(PsParams& Q, const CUtensorMap& tm_img, const CUtensorMap& tm_val, cudaStream_t s) {
   constexpr size_t smem = PsCfg<C, SOFTMAX>::smem_floats * sizeof(float);
-  static bool attr_set = false;  // idempotent; a race only repeats the call
+  // function attributes are per device: remember which devices have them (idempotent; a race only repeats the call)
+  static bool attr_done[64] = {};
+  int dev_id = 0;
+  if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, attr_done[0] = false;
+  bool& attr_set = attr_done[dev_id];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
