@@ -248,3 +248,30 @@ def test_prepared_workspace_is_self_cleaning(WF):
             out.append((loss, grad))
         assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     torch.cuda.synchronize()
+
+
+def test_module_under_cuda_graph_capture(W):
+    """The modules can be captured in a CUDA graph (workspace allocated inside the capture is not cached) and the
+    replay reproduces the eager result."""
+    gen = torch.Generator().manual_seed(31)
+    vals = torch.randn(2, 2, 48, 64, generator=gen).cuda()
+    img = smooth_images(gen, 2, 48, 64).cuda()
+    crit = W.LocalNormalizedCutLoss()
+    with torch.no_grad():
+        eager = crit(vals, img).clone()
+    static_in = vals.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s), torch.no_grad():
+        crit(static_in, img)  # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g), torch.no_grad():
+        out = crit(static_in, img)
+    for scale in (1.0, 0.5):
+        static_in.copy_(vals * scale)
+        g.replay()
+        with torch.no_grad():
+            ref = crit(vals * scale, img)
+        assert torch.equal(out.reshape(-1), ref.reshape(-1))
+    assert torch.equal(eager.reshape(-1), crit(vals, img).detach().reshape(-1))

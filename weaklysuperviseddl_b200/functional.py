@@ -125,6 +125,11 @@ def _pairwise_workspace(lib, dev, nbytes: int) -> torch.Tensor:
     """One prepared workspace per device, stream and size: calls on one stream are ordered, so they can share it;
     it is initialised once and every kernel leaves it initialised (no per-call memset, no per-call allocation)."""
     stream = _stream_ptr(dev)
+    if torch.cuda.is_current_stream_capturing():
+        # memory allocated while a CUDA graph is being captured belongs to the graph's pool: do not cache it
+        ws = torch.empty(max(nbytes, 512), dtype=torch.uint8, device=dev)
+        _native.check(lib.wsdl_pairwise_workspace_init(ws.data_ptr(), ws.numel(), stream), "wsdl_pairwise_workspace_init")
+        return ws
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, nbytes)
     ws = _PAIR_WS.get(key)
     if ws is None:
