@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--one-stream", action="store_true")
+    ap.add_argument("--separate", action="store_true", help="two launches per step (cut, boundary) instead of the fused one")
     ap.add_argument("--stream-pairs", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
@@ -351,8 +352,39 @@ def bench_pairwise(args, lib, dev, rank, world):
             probs.data_ptr(), img.data_ptr(), B, C, H, W, PAIR["window"], PAIR["sigma_bnd"], PAIR["sigma_space"], 0, 0, 1,
             None, (out if out is not None else loss_bnd).data_ptr(), g_bnd.data_ptr(), w.data_ptr(), nws, stream_ptr))
 
+    fused = not args.separate  # one launch computes both losses of a step (they share the probability map)
+    n_streams = 2 * n_pairs if two else 1
+    fl = []  # per stream: (stream, workspace, loss_cut, loss_bnd)
+    if fused:
+        nwd = lib.wsdl_pairwise_dual_workspace_bytes(B, H, W)
+        for k in range(n_streams):
+            w = torch.empty(nwd, dtype=torch.uint8, device=dev)
+            _native_check(lib.wsdl_pairwise_workspace_init(w.data_ptr(), nwd, torch.cuda.current_stream(dev).cuda_stream))
+            fl.append((torch.cuda.Stream(dev) if two else None, w, torch.empty(1, device=dev), torch.empty(B, device=dev)))
+        torch.cuda.synchronize(dev)
+
+    def launch_dual(i, stream_ptr, lane):
+        logits, probs, img, g_cut, g_bnd = sets[i % N_SETS]
+        _, w, lc, lb = lane
+        _native_check(lib.wsdl_pairwise_dual_fwd_bwd(
+            logits.data_ptr(), img.data_ptr(), B, H, W, PAIR["window"], PAIR["sigma_cut"], PAIR["sigma_bnd"],
+            PAIR["sigma_space"], None, None, lc.data_ptr(), lb.data_ptr(), g_cut.data_ptr(), w.data_ptr(), nwd, 1, stream_ptr))
+
     def some_steps(idx):  # fork from the current stream, launch, join back
         cur = torch.cuda.current_stream(dev)
+        if fused:
+            if not two:
+                for i in idx:
+                    launch_dual(i, cur.cuda_stream, fl[0])
+                return
+            for lane in fl:
+                lane[0].wait_stream(cur)
+            for i in idx:
+                lane = fl[i % n_streams]
+                launch_dual(i, lane[0].cuda_stream, lane)
+            for lane in fl:
+                cur.wait_stream(lane[0])
+            return
         if not two:
             for i in idx:
                 launch_cut(i, cur.cuda_stream, ws)
@@ -400,13 +432,22 @@ def bench_pairwise(args, lib, dev, rank, world):
     peak, peak_src = peaks()
     # dominant kernel: pairwise_sym_kernel<2,*> (csrc/pairwise_sym.cu), two launches per step (cut: <2,true>,
     # boundary: <2,false>) and nothing else (prepared workspace: no per-call memset)
-    launch_ms = ms_per_step / 2.0
-    achieved = BYTES_PER_PIX * B * H * W / (launch_ms * 1e-3) / 1e9
+    launches_per_step = 1 if fused else 2
+    launch_ms = ms_per_step / launches_per_step
+    # algorithmic bytes: 28 B per pixel PER LOSS; the fused launch processes 2 B H W loss-pixels
+    alg_bytes = BYTES_PER_PIX * B * H * W * (2 if fused else 1)
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     per_kernel = {}
-    for name, which in (("cut", 0), ("boundary", 1)):  # each launch alone, CUDA events on the launching stream
+    for name, which in (("cut", 0), ("boundary", 1), ("fused cut+boundary", 2)):  # each launch alone, one stream
+        if which == 2 and not fused:
+            continue
+
         def only(n, which=which):
             for i in range(n):
-                (launch_cut if which == 0 else launch_bnd)(i, sp(), ws)
+                if which == 2:
+                    launch_dual(i, sp(), fl[0])
+                else:
+                    (launch_cut if which == 0 else launch_bnd)(i, sp(), ws)
         t_ms, _ = _timed(only, 20, 200, dev, world, None)
         per_kernel[name] = t_ms / 200
     res = {
@@ -416,25 +457,30 @@ def bench_pairwise(args, lib, dev, rank, world):
         "config": {
             "workload": "configs[1]: AlternatingDirectionCutLoss + BoundaryLoss fwd/bwd, 32x2x224x224 per GPU, "
                         "smooth RGB affinities (SURVEY.md 8d)",
-            "step": "1 cut fwd+bwd launch (logits, sigma 0.05) + 1 boundary fwd+bwd launch (32 images, sigma 0.1/5); "
+            "step": ("1 fused launch: cut loss fwd+bwd on the logits (sigma 0.05) + boundary loss fwd+bwd on "
+                     "softmax(logits) (32 images, sigma 0.1/5), both loss values and d/dlogits; " if fused else
+                     "1 cut fwd+bwd launch (logits, sigma 0.05) + 1 boundary fwd+bwd launch (32 images, sigma 0.1/5); ") +
                     "pixels counted once per loss",
             "l2": f"rotating {N_SETS} input sets ({N_SETS * 45} MB) > {L2_MB} MB L2",
             "launch": ("CUDA graph of 8 steps" if graph is not None else "direct C-ABI calls") +
-                      (f"; the cut and the boundary launch of a step on two streams, consecutive steps on {n_pairs} stream "
-                       "pairs (independent work, own workspaces)" if two else "; one stream"),
+                      ((f"; consecutive steps rotate over {n_streams} streams (independent work, own workspaces)" if fused else
+                        f"; the cut and the boundary launch of a step on two streams, consecutive steps on {n_pairs} stream "
+                        "pairs (independent work, own workspaces)") if two else "; one stream"),
             "sharding": "batch per rank, no data-path collective",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES, "kernel": "pairwise_sym_kernel<2,true|false>",
-                     "algorithmic_bytes_per_launch": BYTES_PER_PIX * B * H * W, "launch_ms": launch_ms,
+                     "traffic": NCU_TRAFFIC_BYTES,
+                     "kernel": "pairwise_dual_kernel" if fused else "pairwise_sym_kernel<2,true|false>",
+                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                      "peak_source": peak_src, "per_kernel_ms_direct_launch": per_kernel,
-                     "note": "launch duration = timed step / 2 launches (CUDA events on the stream the step is forked from "
-                             "and joined to, inside the graph; with two streams the launches of a step overlap, so this "
-                             "is the time the step spends per launch, not a kernel duration: those are in "
-                             "per_kernel_ms_direct_launch); traffic = dram__bytes_read+write per launch from profiles/r01_c_ncu_full_sym.txt "
+                     "note": "launch duration = timed step / launches per step (CUDA events on the stream the steps are forked "
+                             "from and joined to, inside the graph; launches on different streams overlap, so this is the "
+                             "time the step spends per launch, not a kernel duration: those are in "
+                             "per_kernel_ms_direct_launch); algorithmic bytes = 28 B per pixel per loss x the loss-pixels "
+                             "one launch processes (the fused launch computes both losses from one read of the inputs); traffic = dram__bytes_read+write per launch from profiles/r01_c_ncu_full_sym.txt "
                              "(the 12.8 MB gradient is still dirty in L2 when the kernel ends); the kernel is bound by "
                              "FP32/MUFU issue, not HBM (DESIGN.md 4.2)"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
     e2e = e2e_pairwise(dev, world, max(3, min(50, args.steps)), max(3, min(5, args.warmup)))

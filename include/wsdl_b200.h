@@ -121,6 +121,25 @@ int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int
                                    int per_image_loss, const float* grad_out, float* loss_out, float* grad_values,
                                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Both regularisers of a two-class batch in ONE pass: LocalNormalizedCutLoss(logits, images)
+ * (AlternatingDirectionCutLoss.py:71-105; softmax inside, mean over b,h,w, / C) and, for every image b,
+ * ConstrainToBoundaryLossSingle(softmax(logits)[b], images[b]) (AlternatingDirectionBoundaryLoss.py:20-44) -- the
+ * composition of the weakly-supervised training step.  Both see the same probability map, so a pixel pair shares its
+ * colour distance and p(a) - p(b); only the affinities differ.
+ *   logits (B,2,H,W), images (B,3,H,W) f32; window must be 5 and H, W >= 6 (else WSDL_E_SHAPE: use two
+ *   wsdl_pairwise_fwd_bwd calls);
+ *   loss_cut 1 float, loss_bnd B floats;
+ *   grad_logits nullable (B,2,H,W): d(go_cut * loss_cut + sum_b go_bnd[b] * loss_bnd[b]) / d logits, softmax backward
+ *   included; grad_out_cut / grad_out_bnd nullable device pointers (1 / B floats), NULL = 1.0;
+ *   workspace >= wsdl_pairwise_dual_workspace_bytes(); prepared != 0: initialised with wsdl_pairwise_workspace_init
+ *   (self-cleaning, as for wsdl_pairwise_fwd_bwd_prepared), 0: the call zeroes the ticket itself. */
+size_t wsdl_pairwise_dual_workspace_bytes(int B, int H, int W);
+
+int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* images, int B, int H, int W, int window,
+                               float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_cut,
+                               const float* grad_out_bnd, float* loss_cut, float* loss_bnd, float* grad_logits,
+                               void* workspace, size_t workspace_bytes, int prepared, void* stream);
+
 /* compute_affinities / compute_affinities_single (AlternatingDirectionCutLoss.py:612-637,
  * AlternatingDirectionBoundaryLoss.py:46-70): images (B,3,H,W) -> out (K,B,H,W) with
  * K = window*window-1, offset order dy outer / dx inner, centre skipped; out[k] is the

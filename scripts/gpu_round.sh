@@ -9,5 +9,5 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/b
 timeout 600 python bench.py --impl reference --workload layercam --steps 5 --warmup 1 > gpurun_out/bench_ref_layercam.json 2>> gpurun_out/bench_ref.err; echo "bench ref layercam rc=$?"; cat gpurun_out/bench_ref_layercam.json
 CMD="python bench.py --steps 16 --warmup 8 --no-graph --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv $CMD > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:pairwise_sym -s 20 -c 2 -f -o gpurun_out/prof_pairwise_sym $CMD > gpurun_out/ncu_pair_full.log 2>&1; echo "ncu pair rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:pairwise_ -s 20 -c 3 -f -o gpurun_out/prof_pairwise_sym $CMD > gpurun_out/ncu_pair_full.log 2>&1; echo "ncu pair rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:layercam -s 4 -c 2 -f -o gpurun_out/prof_layercam python bench.py --workload layercam --steps 4 --warmup 3 > gpurun_out/ncu_lc_full.log 2>&1; echo "ncu layercam rc=$?"

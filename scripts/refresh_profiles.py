@@ -20,9 +20,9 @@ def run(*a):
     return subprocess.run([sys.executable, *a], capture_output=True, text=True, cwd=R).stdout
 sym = os.path.join(go, "prof_pairwise_sym.ncu-rep")
 with open(os.path.join(pr, f"{tag}_c_ncu_full_sym.txt"), "w") as f:
-    f.write("# ncu --set full --clock-control none: python bench.py --steps 16 --warmup 8 --no-graph --no-cpu-baseline, -k regex:pairwise_sym -s 20 -c 2\n")
+    f.write("# ncu --set full --clock-control none: python bench.py --steps 16 --warmup 8 --no-graph --no-cpu-baseline, -k regex:pairwise_ -s 20 -c 3\n")
     f.write(run("scripts/ncu_summary.py", sym))
-    f.write("\n# SASS opcode mix + stall samples of launch 0 (cut loss, <2,true>)\n" + run("scripts/ncu_sass.py", sym, "0"))
+    f.write("\n# SASS opcode mix + stall samples of launch 0\n" + run("scripts/ncu_sass.py", sym, "0"))
     f.write("\n# march loop only\n" + run("scripts/ncu_hot.py", sym, "12"))
 with open(os.path.join(pr, f"{tag}_c_ncu_full_layercam.txt"), "w") as f:
     f.write("# ncu --set full --clock-control none: python bench.py --workload layercam --steps 4 --warmup 3, -k regex:layercam -s 4 -c 2\n")

@@ -275,3 +275,41 @@ def test_module_under_cuda_graph_capture(W):
             ref = crit(vals * scale, img)
         assert torch.equal(out.reshape(-1), ref.reshape(-1))
     assert torch.equal(eager.reshape(-1), crit(vals, img).detach().reshape(-1))
+
+
+DUAL_CASES = [(2, 64, 64), (1, 224, 224), (2, 45, 70), (1, 6, 6), (3, 39, 44), (1, 100, 122), (2, 50, 61)]
+
+
+@pytest.mark.parametrize("case", range(len(DUAL_CASES)))
+def test_dual_launch_equals_the_two_losses(WF, case):
+    """wsdl_pairwise_dual_fwd_bwd == cut loss on the logits + boundary loss on softmax(logits), values and the
+    gradient w.r.t. the logits (with upstream gradients), against the separate launches and the fp64 oracle."""
+    B, H, W_ = DUAL_CASES[case]
+    gen = torch.Generator().manual_seed(900 + case)
+    logits = torch.randn(B, 2, H, W_, generator=gen)
+    img = smooth_images(gen, B, H, W_)
+    go_c = torch.tensor([0.7])
+    go_b = torch.rand(B, generator=gen) + 0.5
+    lc, lb, g = WF.pairwise_dual_loss_and_grad(logits.cuda(), img.cuda(), 0.05, 0.1, 5.0, 5, go_c.cuda(), go_b.cuda())
+    # fp64 oracle, image by image
+    ref_g = np.zeros((B, 2, H, W_))
+    ref_lc, ref_lb = [], []
+    for b in range(B):
+        Lc, gc = O.pairwise_closed_form(logits[b].numpy(), img[b].numpy(), 0.05, None, 5, True, True)
+        p = torch.softmax(logits[b].double(), 0).numpy()
+        Lb, gp = O.pairwise_closed_form(p, img[b].numpy(), 0.1, 5.0, 5, False, False)
+        gz = p * (gp - (p * gp).sum(0, keepdims=True))  # through the softmax
+        ref_lc.append(Lc)
+        ref_lb.append(Lb)
+        ref_g[b] = go_c.item() * gc / B + go_b[b].item() * gz
+    assert_loss_close(lc, np.mean(ref_lc), f"dual case {case} cut loss")
+    assert_loss_close(lb, np.array(ref_lb), f"dual case {case} boundary loss")
+    assert_grad_close(g, ref_g, f"dual case {case} grad")
+    # and the separate launches agree with the fused one to rounding
+    l1, _ = WF.pairwise_loss_and_grad(logits.cuda(), img.cuda(), 5, 0.05, None, True, True, False)
+    l2, _ = WF.pairwise_loss_and_grad(torch.softmax(logits.cuda(), 1), img.cuda(), 5, 0.1, 5.0, False, False, True)
+    assert abs(l1.item() - lc.item()) <= 2e-6 * abs(l1.item())
+    assert (l2 - lb).abs().max().item() <= 2e-6 * l2.abs().max().item()
+    # forward only, no upstream gradients
+    lc2, lb2, none = WF.pairwise_dual_loss_and_grad(logits.cuda(), img.cuda(), want_grad=False)
+    assert none is None and torch.equal(lc2, lc) and torch.equal(lb2, lb)

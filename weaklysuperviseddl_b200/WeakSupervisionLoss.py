@@ -53,6 +53,12 @@ class WeakSupervisionLoss(nn.Module):
             return WF.pairwise_loss(probs, img, self.window_size, self.sigma_boundary, self.sigma_space, False, False,
                                     True).mean()
 
+        if x.is_cuda and x.shape[1] == 2 and self.window_size == 5 and min(x.shape[2:]) >= 6:
+            # two classes: both regularisers see the same probability map -> ONE fused launch (wsdl_pairwise_dual_fwd_bwd)
+            pair, cut, bnd_b = WF.pairwise_dual_weighted(x, img, self.lambda_cut, self.lambda_boundary, self.sigma_cut,
+                                                         self.sigma_boundary, self.sigma_space, self.window_size)
+            total = ce + pair
+            return total, {"ce": ce.detach(), "cut": cut.detach(), "boundary": bnd_b.mean().detach()}
         if self.concurrent and x.is_cuda:
             # CTAs of one kernel fill the SM slots the other leaves idle (ramp-up, tile loads, drain): DESIGN.md 4.2
             cur = torch.cuda.current_stream(x.device)

@@ -716,6 +716,52 @@ extern "C" int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* 
                                per_image_loss, grad_out, loss_out, grad_values, workspace, workspace_bytes, stream, true);
 }
 
+extern "C" size_t wsdl_pairwise_dual_workspace_bytes(int B, int H, int W) {
+  const size_t one = wsdl_pairwise_workspace_bytes(B, H, W);
+  return one ? 2 * one : 0;
+}
+
+extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* images, int B, int H, int W, int window,
+                                          float sigma_cut, float sigma_bnd, float sigma_space,
+                                          const float* grad_out_cut, const float* grad_out_bnd, float* loss_cut,
+                                          float* loss_bnd, float* grad_logits, void* workspace, size_t workspace_bytes,
+                                          int prepared, void* stream) {
+  if (!logits || !images || !loss_cut || !loss_bnd || !workspace) return WSDL_E_NULL;
+  if (B < 1 || B > 65535 || H < 6 || W < 6 || window != 5) return WSDL_E_SHAPE;  // the pair-symmetric kernel's shapes
+  if (!(sigma_cut > 0.f) || !(sigma_bnd > 0.f)) return WSDL_E_ARG;
+  if (((uintptr_t)logits % 4) || ((uintptr_t)images % 4) || ((uintptr_t)loss_cut % 4) || ((uintptr_t)loss_bnd % 4) ||
+      (grad_logits && ((uintptr_t)grad_logits % 4)))
+    return WSDL_E_ALIGN;
+  const size_t one = wsdl_pairwise_workspace_bytes(B, H, W);
+  if (workspace_bytes < 2 * one) return WSDL_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  PwParams P;
+  P.values = logits;
+  P.images = images;
+  P.grad_out = grad_out_cut;
+  P.loss_out = loss_cut;
+  P.grad_values = grad_logits;
+  uintptr_t ws = ((uintptr_t)workspace + 255) / 256 * 256;
+  P.ticket = reinterpret_cast<unsigned*>(ws);
+  P.partial = reinterpret_cast<float*>(ws + 256);
+  float* partial_bnd = reinterpret_cast<float*>(ws + 256 + (one - 512));
+  P.B = B, P.C = 2, P.H = H, P.W = W, P.pad = 2;
+  P.tiles_x = (W + PW_TW - 1) / PW_TW;
+  P.tiles_y = (H + PW_TH - 1) / PW_TH;
+  P.inner_softmax = 1;
+  P.per_image = 0;
+  P.kc = -LOG2E / (2.f * sigma_cut * sigma_cut);
+  P.inv_2ss = 0.f;
+  P.ks_unit = 0.f;
+  P.kappa = 1.0 / (24.0 * (double)B * (double)H * (double)W * 2.0);
+  if (!prepared) {
+    cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int rc = ps_launch_dual(P, sigma_cut, sigma_bnd, sigma_space, grad_out_bnd, loss_bnd, partial_bnd, s);
+  return rc == 1 ? WSDL_E_SHAPE : rc;
+}
+
 extern "C" int wsdl_affinities(const float* images, int B, int H, int W, int window, float sigma_color,
                                float sigma_space, float* out, void* stream) {
   if (!images || !out) return WSDL_E_NULL;

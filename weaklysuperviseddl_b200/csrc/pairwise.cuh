@@ -34,6 +34,11 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 int ps_launch(const PwParams& P, cudaStream_t s);
 size_t ps_workspace_floats(int B, int H, int W);
 
+// Cut loss on the logits + boundary loss on softmax(logits) of a two-class batch in one pass (pairwise_sym.cu).
+// P describes the cut loss; returns 1 when the shape is not supported.
+int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_bnd,
+                   float* loss_bnd, float* partial_bnd, cudaStream_t s);
+
 // Persistent warp-specialised version of the same kernel (pairwise_pipe.cu); same return convention.
 int pp_launch(const PwParams& P, cudaStream_t s);
 size_t pp_workspace_floats(int B, int H, int W);

@@ -280,11 +280,12 @@ __device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
 // (Wy + Wy') / (2 gamma^dy^2)), which happens for at most two partner columns of a band pixel; those two columns are
 // evaluated for all five rows without branches (weight 0 where there is nothing to add), so the loads and the
 // exponentials of the ten candidates overlap.
+// escale: the staged image is scaled for one sigma_color; another loss on the same tile multiplies the squared
+// distance by (sigma / sigma')^2.
 template <int CS>
-__device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_img, const float* s_p, const float* s_wx,
-                                            int ys, int x0, int zy, int zx, float (&acc)[CS], float (&pz)[CS]) {
-  const int H = Q.p.H;
-  const float g1 = Q.g1, g4 = Q.g4;
+__device__ __forceinline__ void ps_xfix_item(int H, float g1, float g4, float escale, const float* s_img, const float* s_p,
+                                            const float* s_wx, int ys, int x0, int zy, int zx, float (&acc)[CS],
+                                            float (&pz)[CS]) {
   const int so = (zy - (ys - 2)) * PS_PITCH + (zx - (x0 - 4));
   const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
 #pragma unroll
@@ -324,7 +325,7 @@ __device__ __forceinline__ void ps_xfix_item(const PsParams& Q, const float* s_i
       const float diff = live * (fmaf(wyf[i], wxf, wyb[i] * wxb) - wym[i] * gx);  // 0 for rows outside the image
       const int sn = so + (i - 2) * PS_PITCH + (j - 2);
       const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
-      const float k = diff * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0)));
+      const float k = diff * ex2_approx(escale * fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0)));
 #pragma unroll
       for (int c = 0; c < CS; ++c) acc[c] = fmaf(k, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
     }
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
       const int slot = ps_band_slot(x, W);
       float acc[CS], pz[CS], o[C];
-      ps_xfix_item<CS>(Q, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, acc, pz);
+      ps_xfix_item<CS>(H, Q.g1, Q.g4, 1.f, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, acc, pz);
       lsum += ps_pixel_grad<C, CS, SOFTMAX>(K.scale2, pz, acc, o);  // the loss is linear in G: add the correction's share
       if (Q.p.grad_values) {
 #pragma unroll
@@ -785,6 +786,371 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       for (int i = 0; i < PS_THREADS / 32; ++i) t += s_dred[i];
       Q.p.loss_out[0] = (float)(t * Q.p.kappa);
     }
+  }
+}
+
+// =====================================================================================================
+// Dual kernel: the cut loss on the logits AND the boundary loss on softmax(logits) of the same two-class batch in one
+// pass (the composition of BASELINE configs[1] / config 4: LocalNormalizedCutLoss(x, I) and
+// ConstrainToBoundaryLossSingle(softmax(x)[b], I[b]) for every image b).  Both losses see the same probability map
+// (the cut loss applies its softmax inside, AlternatingDirectionCutLoss.py:78) and differ in the affinity only, so a
+// pair shares its colour differences, its squared distance and p(a) - p(b): two exponents from one FFMA chain
+// (e_b = ratio e_c + k'), two MUFU, two scatters -- 12 FP32 + 2 MUFU per pair instead of 10 + 13 + 2 in two launches,
+// and one tile load, one conversion, one emit.  Two accumulated channels (G of the cut loss, G of the boundary loss)
+// over ONE stored probability channel (p1 = 1 - p0 for both).  Output: both loss values and
+// d(go_cut L_cut + sum_b go_bnd[b] L_bnd[b]) / d logits.
+struct PsDual {
+  const float* grad_out_bnd;  // nullable, B upstream gradients of the per-image boundary losses (cut: Q.p.grad_out)
+  float* loss_bnd;            // B floats (cut: Q.p.loss_out, 1 float)
+  float* partial_bnd;         // second partial array
+  double kappa_bnd;           // 1 / (K H W)
+  float ratio;                // (sigma_cut / sigma_bnd)^2: squared distances are staged for the cut loss
+  float ksu_b;                // spatial exponent unit of the boundary loss
+  float g1b, g4b, l1g_b;      // gamma, gamma^4, log2(1 + gamma^4) of the boundary loss (cut: 1, 1, 1)
+};
+
+struct PsKsDual {  // per pair class: cut exponent offset, and boundary offset minus ratio * cut offset
+  float ca, cb, cc;  // cut: same row, one row down, two rows down (no spatial term: one value per row distance)
+  float a1, a4, b0, b1, b4, c0, c1, c4;
+};
+
+__device__ __forceinline__ void ps_pair_dual(float (&ga)[2], float (&gb)[2], const PsWin<1>& a, int ia, const PsWin<1>& b,
+                                             int ib, float kc_off, float kb_off, float ratio) {
+  const float d0 = a.i[0][ia] - b.i[0][ib], d1 = a.i[1][ia] - b.i[1][ib], d2 = a.i[2][ia] - b.i[2][ib];
+  const float ec = fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, kc_off)));
+  const float kc = ex2_approx(ec), kb = ex2_approx(fmaf(ec, ratio, kb_off));
+  const float dp = a.p[0][ia] - b.p[0][ib];
+  ga[0] = fmaf(kc, dp, ga[0]);
+  gb[0] = fmaf(-kc, dp, gb[0]);
+  ga[1] = fmaf(kb, dp, ga[1]);
+  gb[1] = fmaf(-kb, dp, gb[1]);
+}
+
+__device__ __forceinline__ void ps_step_dual(float (&X)[8][2], float (&Y)[8][2], float (&Z)[8][2], float (&pc)[4],
+                                             const float* s_img, const float* s_p, int off, const PsKsDual& ks, float ratio) {
+  PsWin<1> c;
+  ps_load<1>(c, s_img, s_p, off);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pc[j] = c.p[0][2 + j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ps_pair_dual(X[2 + j], X[3 + j], c, 2 + j, c, 3 + j, ks.ca, ks.a1, ratio);
+    ps_pair_dual(X[2 + j], X[4 + j], c, 2 + j, c, 4 + j, ks.ca, ks.a4, ratio);
+  }
+  PsWin<1> n;
+  ps_load<1>(n, s_img, s_p, off + PS_PITCH);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx)
+      ps_pair_dual(X[2 + j], Y[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks.cb, dx == 0 ? ks.b0 : (dx * dx == 1 ? ks.b1 : ks.b4),
+                   ratio);
+  ps_load<1>(n, s_img, s_p, off + 2 * PS_PITCH);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx)
+      ps_pair_dual(X[2 + j], Z[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks.cc, dx == 0 ? ks.c0 : (dx * dx == 1 ? ks.c1 : ks.c4),
+                   ratio);
+}
+
+// 4 finished pixels of centre row t: G[.][0] cut, G[.][1] boundary, one probability p0 each
+__device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, float scale_b, int t, int strip, int okmask,
+                                             const float (&G)[4][2], const float (&pc)[4], float* s_gband, float& lsum_c,
+                                             float& lsum_b) {
+  const int H = Q.p.H, W = Q.p.W;
+  const int y = K.ys - 2 + t;
+  const int xs = K.x0 - 2 + 4 * strip;
+  if (K.xband) {  // block-uniform: the band-column pass finishes these pixels from their G
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int slot = ps_band_slot(xs + j, W);
+      if (((okmask >> j) & 1) && slot >= 0) {
+        s_gband[(slot * 2 + 0) * PS_CAP + (t - 2)] = G[j][0];
+        s_gband[(slot * 2 + 1) * PS_CAP + (t - 2)] = G[j][1];
+      }
+    }
+  }
+  float out[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float p0 = pc[j], p1 = 1.f - p0;
+    out[j] = 2.f * p0 * p1 * fmaf(K.scale2, G[j][0], scale_b * G[j][1]);  // dL/dlogit0 = -dL/dlogit1
+    if ((okmask >> j) & 1) {
+      lsum_c = fmaf(p0 - p1, G[j][0], lsum_c);
+      lsum_b = fmaf(p0 - p1, G[j][1], lsum_b);
+    }
+  }
+  if (Q.p.grad_values) {
+    const size_t plane = (size_t)H * W;
+    float* go = Q.p.grad_values + (size_t)K.b * 2 * plane + (size_t)y * W + xs;
+    if (Q.vec2_ok) {
+      if (okmask & 1) {
+        *reinterpret_cast<float2*>(go) = make_float2(out[0], out[1]);
+        *reinterpret_cast<float2*>(go + plane) = make_float2(-out[0], -out[1]);
+      }
+      if (okmask & 4) {
+        *reinterpret_cast<float2*>(go + 2) = make_float2(out[2], out[3]);
+        *reinterpret_cast<float2*>(go + plane + 2) = make_float2(-out[2], -out[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if ((okmask >> j) & 1) go[j] = out[j], go[plane + j] = -out[j];
+    }
+  }
+}
+
+constexpr size_t PS_DUAL_SMEM_FLOATS =
+    (size_t)5 * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * 2 * 64 + 6 * (size_t)2 * PS_CAP + 2 * 6 * 10;
+
+__global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
+    pairwise_dual_kernel(const __grid_constant__ PsParams Q, const __grid_constant__ PsDual D,
+                         const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_val) {
+  constexpr int C = 2;
+  extern __shared__ __align__(128) float ps_smem[];
+  float* s_img = ps_smem;                                // [3][PS_ROWS][PS_PITCH]: raw, then scaled for sigma_cut
+  float* s_p = s_img + 3 * PS_PLANE;                     // [2][PS_ROWS][PS_PITCH]: logits, then p0 in plane 0
+  float* s_head = s_p + C * PS_PLANE;                    // [7][2][2][64]: G (cut, boundary) of the segment heads
+  float* s_gband = s_head + (PS_SEGS - 1) * 2 * 2 * 64;  // [6][2][PS_CAP]: G of the band-column pixels
+  float* s_wx = s_gband + 6 * 2 * PS_CAP;                // [2][6][2][5]: column weights, cut then boundary
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ float s_red[2][PS_THREADS / 32];
+  __shared__ double s_dred[PS_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seg = warp * 2 + (lane >> 4), strip = lane & 15;
+  const int H = Q.p.H, W = Q.p.W;
+  const int S = Q.S;
+
+  PsBlk K;
+  K.b = blockIdx.z;
+  K.x0 = blockIdx.y * PS_TW;
+  K.ys = blockIdx.x * (PS_SEGS * S - 2);
+  K.n = min(PS_SEGS * S - 2, H - K.ys);
+  K.nc = K.n + 2;
+  const int xe = min(K.x0 + PS_TW, W);
+  K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
+  const int rows = K.nc + 2;
+
+  if (Q.use_tma && tid == 0) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (cta >= WSDL_NUM_SMS && cta < (unsigned)WSDL_NUM_SMS * WSDL_PS_CTAS && Q.stagger_ns > 0)
+      __nanosleep((cta / WSDL_NUM_SMS) * Q.stagger_ns);
+    const unsigned bar = ps_smem_u32(&s_bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned bytes = (unsigned)(5 * (PS_SEGS * S + 2) * PS_PITCH * sizeof(float));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const CUtensorMap* tm = c < 3 ? &tm_img : &tm_val;
+      const int pl = c < 3 ? K.b * 3 + c : K.b * C + (c - 3);
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+              ps_smem_u32(s_img + c * PS_PLANE)),
+          "l"(tm), "r"(K.x0 - 4), "r"(K.ys - 2), "r"(pl), "r"(bar)
+          : "memory");
+    }
+  }
+  K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out) : 1.f);
+  const float scale_b = (float)(4.0 * D.kappa_bnd) * (D.grad_out_bnd ? __ldg(D.grad_out_bnd + K.b) : 1.f);
+  int okmask = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = 4 * strip + j;
+    if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
+  }
+  float lsum_c = 0.f, lsum_b = 0.f;
+  if (K.xband && tid < 120) {  // column weights of the band slots for gamma = 1 (cut) and gamma_b (boundary)
+    const int which = tid / 60, e = tid - which * 60, slot = e / 10, rem = e - slot * 10, j = rem % 5;
+    const float g1 = which ? D.g1b : 1.f, g4 = which ? D.g4b : 1.f;
+    const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
+    float w = 0.f;
+    if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, g1, g4) : ps_w1d(xb, x, W, g1, g4);
+    s_wx[tid] = w;
+  }
+  __syncthreads();  // s_bar is initialised
+
+  {
+    const int r0 = min(2 * warp * S, rows), r1 = warp == 3 ? rows : min(2 * (warp + 1) * S, rows);
+    const int re = min(r0 + 2, r1);
+    if (Q.use_tma) {
+      asm volatile(
+          "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0, %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(
+              ps_smem_u32(&s_bar)),
+          "r"(20000u)
+          : "memory");
+    } else {
+      ps_rows_load_slow<C>(Q, K, s_img, s_p, r0, r1, lane);
+      __syncwarp();
+    }
+    ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, r0, re, lane);
+    if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");
+    ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, re, r1, lane);
+    __syncwarp();
+    if (warp < 3) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
+  }
+
+  // ---- march ----
+  const int t0 = seg * S, t1 = min(t0 + S, K.nc);
+  float oy[4][2], oz[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) oy[q][0] = oy[q][1] = oz[q][0] = oz[q][1] = 0.f;
+  if (warp * 2 * S < K.nc) {
+    float A[8][2], Bq[8][2], Cq[8][2];
+    ps_zero<2>(A), ps_zero<2>(Bq), ps_zero<2>(Cq);
+    const float ksu = D.ksu_b, ratio = D.ratio;
+#pragma unroll 1
+    for (int s = 0; s < S; ++s) {
+      const int t = t0 + s;
+      const bool act = t < t1;
+      float pc[4], own[4][2];
+      if (act) {
+        const int y = K.ys - 2 + t;
+        const bool r1 = (y == 1 || y == H - 2);
+        const float l0c = r1 ? 1.f : 0.f, l0b = r1 ? D.l1g_b : 0.f;  // log2(1 + gamma^4): gamma = 1 for the cut loss
+        const float l1 = (y == 0 || y == H - 2) ? Q.l32 : 0.f;
+        const float l2 = (y == 0 || y == H - 3) ? Q.l32 : 0.f;
+        PsKsDual ks;
+        ks.ca = l0c, ks.cb = l1, ks.cc = l2;
+        const float ra = ratio * l0c, rb = ratio * l1, rc = ratio * l2;
+        ks.a1 = ksu + l0b - ra, ks.a4 = 4.f * ksu + l0b - ra;
+        ks.b0 = ksu + l1 - rb, ks.b1 = 2.f * ksu + l1 - rb, ks.b4 = 5.f * ksu + l1 - rb;
+        ks.c0 = 4.f * ksu + l2 - rc, ks.c1 = 5.f * ksu + l2 - rc, ks.c4 = 8.f * ksu + l2 - rc;
+        ps_step_dual(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
+      }
+      ps_exchange<2>(A, own, strip);
+      if (act) {
+        if (s >= 2) {
+          ps_emit_dual(Q, K, scale_b, t, strip, okmask, own, pc, s_gband, lsum_c, lsum_b);
+        } else if (seg > 0) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * 2 + c) * 64 + 4 * strip) =
+                make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
+        }
+      }
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
+    }
+    ps_exchange<2>(A, oy, strip);
+    ps_exchange<2>(Bq, oz, strip);
+  }
+  __syncthreads();  // every head row holds its own segment's part
+  if (seg < PS_SEGS - 1) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (t0 + S < K.nc) {
+        float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 0) * 2 + c) * 64 + 4 * strip);
+        float4 v = *h;
+        v.x += oy[0][c], v.y += oy[1][c], v.z += oy[2][c], v.w += oy[3][c];
+        *h = v;
+      }
+      if (t0 + S + 1 < K.nc) {
+        float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 1) * 2 + c) * 64 + 4 * strip);
+        float4 v = *h;
+        v.x += oz[0][c], v.y += oz[1][c], v.z += oz[2][c], v.w += oz[3][c];
+        *h = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- the first two rows of segments 1..7, now complete ----
+  if (seg > 0) {
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const int t = t0 + i;
+      if (t < t1) {
+        float G[4][2], pc[4];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * 2 + c) * 64 + 4 * strip);
+          G[0][c] = h.x, G[1][c] = h.y, G[2][c] = h.z, G[3][c] = h.w;
+        }
+        const float2 p01 = *reinterpret_cast<const float2*>(s_p + t * PS_PITCH + 4 * strip + 2);
+        const float2 p23 = *reinterpret_cast<const float2*>(s_p + t * PS_PITCH + 4 * strip + 4);
+        pc[0] = p01.x, pc[1] = p01.y, pc[2] = p23.x, pc[3] = p23.y;
+        ps_emit_dual(Q, K, scale_b, t, strip, okmask, G, pc, s_gband, lsum_c, lsum_b);
+      }
+    }
+  }
+
+  // ---- band columns (and corners) ----
+  if (K.xband) {
+    __syncthreads();
+    const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
+    const int ncb = nlo + nhi;
+    const size_t plane = (size_t)H * W;
+    for (int i = tid; i < ncb * K.n; i += PS_THREADS) {
+      const int ty = i / ncb, k = i - ty * ncb;
+      const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
+      const int slot = ps_band_slot(x, W);
+      float ac[1], ab[1], pz[1];
+      ps_xfix_item<1>(H, 1.f, 1.f, 1.f, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, ac, pz);
+      ps_xfix_item<1>(H, D.g1b, D.g4b, D.ratio, s_img, s_p, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ab, pz);
+      const float p0 = pz[0], p1 = 1.f - p0;
+      lsum_c = fmaf(p0 - p1, ac[0], lsum_c);  // the losses are linear in G: the corrections' share
+      lsum_b = fmaf(p0 - p1, ab[0], lsum_b);
+      if (Q.p.grad_values) {
+        const float gc = ac[0] + s_gband[(slot * 2 + 0) * PS_CAP + ty], gb = ab[0] + s_gband[(slot * 2 + 1) * PS_CAP + ty];
+        const float o = 2.f * p0 * p1 * fmaf(K.scale2, gc, scale_b * gb);
+        float* go = Q.p.grad_values + (size_t)K.b * 2 * plane + (size_t)y * W + x;
+        go[0] = o, go[plane] = -o;
+      }
+    }
+  }
+
+  // ---- loss partials (cut, boundary) per CTA; the last CTA of the grid finishes both ----
+  const int kpi = Q.nb * Q.n_x;
+  const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
+  const bool finisher = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
+  {
+    const float wc = warp_sum(lsum_c), wb = warp_sum(lsum_b);
+    if (lane == 0) s_red[0][warp] = wc, s_red[1][warp] = wb;
+    __syncthreads();
+    if (tid == 0) {
+      float tc = 0.f, tb = 0.f;
+#pragma unroll
+      for (int i = 0; i < PS_THREADS / 32; ++i) tc += s_red[0][i], tb += s_red[1][i];
+      const size_t idx = (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x;
+      __stcg(Q.p.partial + idx, 2.f * tc);
+      __stcg(D.partial_bnd + idx, 2.f * tb);
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
+    }
+  }
+  if (!finisher) return;
+  if (tid == 0) {
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
+      if (seen < n_ctas) __nanosleep(200);
+    } while (seen < n_ctas);
+    *Q.p.ticket = 0u;
+  }
+  __syncthreads();
+  double wtot = 0.0;
+  for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {  // image by image: cut summed over the batch, boundary per image
+    double ac = 0.0, ab = 0.0;
+    for (int i = lane; i < kpi; i += 32) {
+      ac += (double)ld_cg_f32(Q.p.partial + (size_t)b * kpi + i);
+      ab += (double)ld_cg_f32(D.partial_bnd + (size_t)b * kpi + i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(0xffffffffu, ac, o), ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    if (lane == 0) D.loss_bnd[b] = (float)(ab * D.kappa_bnd);
+    wtot += ac;
+  }
+  if (lane == 0) s_dred[warp] = wtot;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < PS_THREADS / 32; ++i) t += s_dred[i];
+    Q.p.loss_out[0] = (float)(t * Q.p.kappa);
   }
 }
 
@@ -898,7 +1264,65 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   return P.inner_softmax ? ps_launch_t<1, true>(Q, tm_img, tm_val, s) : ps_launch_t<1, false>(Q, tm_img, tm_val, s);
 }
 
+// Host side of the dual kernel.  P describes the cut loss (values = logits, C = 2, inner softmax, batch-mean loss,
+// kc for sigma_cut, no spatial term); the boundary loss comes in through the extra arguments.
+int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_bnd,
+                   float* loss_bnd, float* partial_bnd, cudaStream_t s) {
+  if (P.pad != 2 || P.C != 2 || P.H < 6 || P.W < 6 || !P.inner_softmax || P.per_image) return 1;
+  PsParams Q;
+  Q.p = P;
+  Q.n_x = (P.W + PS_TW - 1) / PS_TW;
+  Q.nb = ps_row_blocks(P.B, P.H, P.W);
+  if (Q.nb > 65535 || Q.n_x > 65535 || P.B > 65535) return 1;
+  const int n_max = (P.H + Q.nb - 1) / Q.nb;
+  Q.S = (n_max + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n_max + 2 + PS_SEGS - 1) / PS_SEGS;
+  Q.nb = (P.H + PS_SEGS * Q.S - 3) / (PS_SEGS * Q.S - 2);
+  Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
+  Q.img_scale = sqrtf(-P.kc);
+  Q.g1 = 1.f, Q.g4 = 1.f;
+  Q.l32 = log2f(1.5f), Q.l1g = 1.f;
+  {
+    static const int stagger_env = []() { const char* e = getenv("WSDL_PS_STAGGER_NS"); return e ? atoi(e) : -1; }();
+    const double tile_bytes = 5.0 * (PS_SEGS * Q.S + 2) * PS_PITCH * 4.0;
+    const long long ctas = (long long)Q.nb * Q.n_x * P.B;
+    Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 6000.0) : 0u;
+    if (stagger_env >= 0) Q.stagger_ns = (unsigned)stagger_env;
+  }
+  PsDual D;
+  D.grad_out_bnd = grad_out_bnd;
+  D.loss_bnd = loss_bnd;
+  D.partial_bnd = partial_bnd;
+  D.kappa_bnd = 1.0 / (24.0 * (double)P.H * (double)P.W);
+  D.ratio = (sigma_cut * sigma_cut) / (sigma_bnd * sigma_bnd);
+  const float inv_2ss = sigma_space > 0.f ? 1.f / (2.f * sigma_space * sigma_space) : 0.f;
+  D.ksu_b = -LOG2E * inv_2ss;
+  D.g1b = expf(-inv_2ss), D.g4b = expf(-4.f * inv_2ss);
+  D.l1g_b = log2f(1.f + D.g4b);
+  CUtensorMap tm_img, tm_val;
+  memset(&tm_img, 0, sizeof(tm_img)), memset(&tm_val, 0, sizeof(tm_val));
+  static const int no_tma = []() { const char* e = getenv("WSDL_PAIRWISE_NO_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
+  Q.use_tma = !no_tma && ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0) &&
+              ps_encode(&tm_img, P.images, P.W, P.H, 3LL * P.B, PS_SEGS * Q.S + 2) &&
+              ps_encode(&tm_val, P.values, P.W, P.H, 2LL * P.B, PS_SEGS * Q.S + 2);
+  constexpr size_t smem = PS_DUAL_SMEM_FLOATS * sizeof(float);
+  static bool attr_done[64] = {};
+  int dev_id = 0;
+  if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, attr_done[0] = false;
+  if (!attr_done[dev_id]) {
+    cudaError_t e = cudaFuncSetAttribute(pairwise_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(pairwise_dual_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    attr_done[dev_id] = true;
+  }
+  pairwise_dual_kernel<<<dim3(Q.nb, Q.n_x, P.B), PS_THREADS, smem, s>>>(Q, D, tm_img, tm_val);
+  WSDL_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace wsdl
+
 
 #ifdef WSDL_PS_TRACE
 extern "C" int wsdl_ps_trace_read(unsigned long long* host, int n) {

@@ -303,3 +303,68 @@ def labels_from_masks(masks: torch.Tensor, size: int = 256) -> torch.Tensor:
         rc = _native.lib().wsdl_labels_from_masks(m.data_ptr(), B, H, W, int(size), out.data_ptr(), _stream_ptr(m.device))
     _native.check(rc, "wsdl_labels_from_masks")
     return out[0] if masks.dim() == 2 else out
+
+
+def pairwise_dual_loss_and_grad(logits, images, sigma_cut=0.05, sigma_boundary=0.1, sigma_space=5.0, window_size=5,
+                                grad_out_cut: Optional[torch.Tensor] = None, grad_out_bnd: Optional[torch.Tensor] = None,
+                                want_grad: bool = True):
+    """One fused launch for LocalNormalizedCutLoss(logits, images) and ConstrainToBoundaryLossSingle(softmax(logits)[b],
+    images[b]) for every b (two classes, window 5).  Returns (loss_cut (1,), loss_bnd (B,), d(go_cut*cut +
+    sum_b go_bnd[b]*bnd[b])/d logits or None)."""
+    v, im = _prep_pair(logits.detach(), images)
+    B, C, H, W = v.shape
+    if C != 2:
+        raise ValueError("the fused cut + boundary launch is for two classes")
+    dev = v.device
+    lib = _native.lib()
+    with torch.cuda.device(dev):
+        nbytes = lib.wsdl_pairwise_dual_workspace_bytes(B, H, W)
+        workspace = _pairwise_workspace(lib, dev, nbytes)
+        loss_cut = torch.empty(1, dtype=torch.float32, device=dev)
+        loss_bnd = torch.empty(B, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(v) if want_grad else None
+        rc = lib.wsdl_pairwise_dual_fwd_bwd(
+            v.data_ptr(), im.data_ptr(), B, H, W, int(window_size), float(sigma_cut), float(sigma_boundary),
+            float(sigma_space) if sigma_space else 0.0,
+            grad_out_cut.data_ptr() if grad_out_cut is not None else None,
+            grad_out_bnd.data_ptr() if grad_out_bnd is not None else None,
+            loss_cut.data_ptr(), loss_bnd.data_ptr(), grad.data_ptr() if grad is not None else None,
+            workspace.data_ptr(), nbytes, 1, _stream_ptr(dev))
+    _native.check(rc, "wsdl_pairwise_dual_fwd_bwd")
+    return loss_cut, loss_bnd, grad
+
+
+class _PairwiseDual(torch.autograd.Function):
+    """lam_cut * cut(logits) + lam_bnd * mean_b boundary(softmax(logits)[b]) from one fused launch; the weights go
+    into the launch as upstream gradients, backward only scales the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, images, sigma_cut, sigma_bnd, sigma_space, window, lam_cut, lam_bnd):
+        B = logits.shape[0]
+        go_c = torch.full((1,), float(lam_cut), dtype=torch.float32, device=logits.device)
+        go_b = torch.full((B,), float(lam_bnd) / B, dtype=torch.float32, device=logits.device)
+        need = ctx.needs_input_grad[0]
+        lc, lb, g = pairwise_dual_loss_and_grad(logits, images, sigma_cut, sigma_bnd, sigma_space, window, go_c, go_b,
+                                                want_grad=need)
+        ctx.save_for_backward(g if need else torch.empty(0, device=logits.device))
+        ctx.in_dtype = logits.dtype
+        total = (float(lam_cut) * lc + float(lam_bnd) * lb.mean()).reshape(())
+        lc, lb = lc.reshape(()), lb
+        ctx.mark_non_differentiable(lc, lb)
+        return total, lc, lb
+
+    @staticmethod
+    def backward(ctx, g_total, _g_lc, _g_lb):
+        (g,) = ctx.saved_tensors
+        if g.numel() == 0:
+            return (None,) * 8
+        return (g * g_total).to(ctx.in_dtype), None, None, None, None, None, None, None
+
+
+def pairwise_dual_weighted(logits, images, lam_cut, lam_bnd, sigma_cut=0.05, sigma_boundary=0.1, sigma_space=5.0,
+                           window_size=5):
+    """Differentiable lam_cut * cut + lam_bnd * mean(boundary) for a two-class batch (one launch).
+    Returns (weighted sum, cut loss, per-image boundary losses); the last two are detached."""
+    v, im = _prep_pair(logits, images)
+    return _PairwiseDual.apply(v, im, float(sigma_cut), float(sigma_boundary), float(sigma_space) if sigma_space else 0.0,
+                               int(window_size), float(lam_cut), float(lam_bnd))
