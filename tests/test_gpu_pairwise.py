@@ -277,7 +277,8 @@ def test_module_under_cuda_graph_capture(W):
     assert torch.equal(eager.reshape(-1), crit(vals, img).detach().reshape(-1))
 
 
-DUAL_CASES = [(2, 64, 64), (1, 224, 224), (2, 45, 70), (1, 6, 6), (3, 39, 44), (1, 100, 122), (2, 50, 61)]
+DUAL_CASES = [(2, 64, 64), (1, 224, 224), (2, 45, 70), (1, 6, 6), (3, 39, 44), (1, 100, 122), (2, 50, 61), (1, 256, 256),
+              (2, 300, 520), (5, 7, 9)]
 
 
 @pytest.mark.parametrize("case", range(len(DUAL_CASES)))
