@@ -29,6 +29,9 @@ N_SETS = 8  # rotated input sets: 8 x 45 MB > 126 MB L2
 BYTES_PER_PIX = 28  # 20 B read (2 logits + 3 rgb) + 8 B gradient written, C=2
 L2_MB = 126
 NCU_TRAFFIC_BYTES = 32_220_000  # dram read 32.18 MB + write 0.04 MB per launch (ncu --set full, round 1)
+# warp instructions per launch (smsp__inst_executed.sum, profiles/r01_c_ncu_full_sym.txt): the kernels are bound by
+# instruction issue (FP32 + MUFU), not HBM -- 148 SMs x 4 schedulers x 1 instruction per clock is the second roof
+NCU_WARP_INSTR = {"fused": 20.10e6, "cut": 15.27e6, "boundary": 18.00e6}
 
 
 def peaks():
@@ -437,6 +440,9 @@ def bench_pairwise(args, lib, dev, rank, world):
     # algorithmic bytes: 28 B per pixel PER LOSS; the fused launch processes 2 B H W loss-pixels
     alg_bytes = BYTES_PER_PIX * B * H * W * (2 if fused else 1)
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965
+    instr = NCU_WARP_INSTR["fused"] if fused else 0.5 * (NCU_WARP_INSTR["cut"] + NCU_WARP_INSTR["boundary"])
+    issue_floor_ms = instr / (148 * 4 * sm_mhz * 1e6) * 1e3
     per_kernel = {}
     for name, which in (("cut", 0), ("boundary", 1), ("fused cut+boundary", 2)):  # each launch alone, one stream
         if which == 2 and not fused:
@@ -473,6 +479,9 @@ def bench_pairwise(args, lib, dev, rank, world):
                      "kernel": "pairwise_dual_kernel" if fused else "pairwise_sym_kernel<2,true|false>",
                      "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                      "peak_source": peak_src, "per_kernel_ms_direct_launch": per_kernel,
+                     "issue_roof": {"warp_instructions_per_launch": instr, "floor_ms": issue_floor_ms,
+                                    "frac": issue_floor_ms / launch_ms,
+                                    "note": "second roof: ncu warp instructions / (148 SMs x 4 schedulers x SM clock)"},
                      "note": "launch duration = timed step / launches per step (CUDA events on the stream the steps are forked "
                              "from and joined to, inside the graph; launches on different streams overlap, so this is the "
                              "time the step spends per launch, not a kernel duration: those are in "
