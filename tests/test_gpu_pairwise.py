@@ -357,3 +357,33 @@ torch.save(out, {os.path.join(td, 'pipe.pt')!r})
         lp, gp = pipe[i]
         assert (l.cpu() - lp).abs().max().item() <= 2e-6 * l.abs().max().item(), i
         assert (g.cpu() - gp).abs().max().item() <= 2e-6 * g.abs().max().item() + 1e-12, i
+
+
+def test_repeatability_stress(WF):
+    """Races (named-barrier hand-offs, carries added after the barrier, band pass, loss ticket) would show up as
+    run-to-run differences: every variant must reproduce itself bit for bit over repeated launches, also while another
+    stream keeps the GPU busy."""
+    gen = torch.Generator().manual_seed(123)
+    side = torch.cuda.Stream()
+    busy_a = torch.randn(2048, 2048, device="cuda")
+    shapes = [(4, 2, 224, 224), (2, 2, 45, 70), (3, 2, 100, 122), (1, 2, 256, 256), (6, 2, 30, 64)]
+    for (B, C, H, W_) in shapes:
+        logits = torch.randn(B, C, H, W_, generator=gen).cuda()
+        probs = torch.softmax(logits, 1)
+        img = smooth_images(gen, B, H, W_).cuda()
+        ref = None
+        for rep in range(6):
+            if rep % 2:
+                with torch.cuda.stream(side):
+                    for _ in range(4):
+                        busy_a = busy_a @ busy_a * 1e-3
+            cut = WF.pairwise_loss_and_grad(logits, img, 5, 0.05, None, True, True, False)
+            bnd = WF.pairwise_loss_and_grad(probs, img, 5, 0.1, 5.0, False, False, True)
+            dual = WF.pairwise_dual_loss_and_grad(logits, img)
+            cur = [t.clone() for t in (*cut, *bnd, *dual)]
+            if ref is None:
+                ref = cur
+            else:
+                for a, b in zip(ref, cur):
+                    assert torch.equal(a, b), (B, H, W_, rep)
+    torch.cuda.synchronize()
