@@ -1,3 +1,4 @@
+[ -f weaklysuperviseddl_b200/libwsdl_b200_trace.so ] || { echo "build it first: WSDL_NVCC_EXTRA=-DWSDL_PS_TRACE python -m weaklysuperviseddl_b200.build --force && cp weaklysuperviseddl_b200/libwsdl_b200.so weaklysuperviseddl_b200/libwsdl_b200_trace.so && python -m weaklysuperviseddl_b200.build --force"; exit 1; }
 # per-warp phase trace of the default pairwise kernel (needs weaklysuperviseddl_b200/libwsdl_b200_trace.so, built
 # with WSDL_NVCC_EXTRA=-DWSDL_PS_TRACE); set TRACE=pipe for the persistent variant
 cp weaklysuperviseddl_b200/libwsdl_b200.so /tmp/keep.so
