@@ -1161,8 +1161,10 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 // modelled time = (march steps per block + fixed cost of a block, in steps) x blocks an SM works through (a launch
 // below two blocks per SM is latency bound: more, shorter blocks keep winning there).
 static int ps_row_blocks(int B, int H, int W) {
+  static const int forced = []() { const char* e = getenv("WSDL_PS_NB"); return e ? atoi(e) : 0; }();  // tuning aid
   const int n_x = (W + PS_TW - 1) / PS_TW;
   const int nb_min = (H + PS_CAP - 1) / PS_CAP;
+  if (forced >= nb_min) return forced;
   int best = nb_min;
   double best_cost = 1e300;
   for (int nb = nb_min; nb <= nb_min + 12; ++nb) {
