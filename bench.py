@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam"])
+    ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam", "pseudomask"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--one-stream", action="store_true")
     ap.add_argument("--separate", action="store_true", help="two launches per step (cut, boundary) instead of the fused one")
@@ -267,6 +267,8 @@ def main():
 
     if args.workload == "layercam":
         res = bench_layercam(args, lib, dev, rank, world)
+    elif args.workload == "pseudomask":
+        res = bench_pseudomask(args, dev, rank, world)
     else:
         res = bench_pairwise(args, lib, dev, rank, world)
     if rank == 0:
@@ -680,6 +682,128 @@ def _layercam_cpu_baseline():
     return {"value": v, "unit": "masks/s", "cores": threads, "kind": "port",
             "sample": f"4 images of 512x512-sized hooks, one at a time, best of 2, {t:.2f} s; oracle port of "
                       "LayerCAM.py:52-76 + PsuedoMasks.py:59-62"}
+
+
+# ------------------------------------------------------------------------------------------ configs[0]
+def _hookable_resnet50(num_classes=37):
+    """The model contract of the reference's classifier (ClassificationModel.py:9-41): ResNet-50 with a dilated last
+    stage, frozen weights, hookable layer2/3/4, forward -> (logits, [f2, f3, f4]).  Random initialisation (no network)."""
+    import torch
+    import torch.nn as nn
+    import torchvision
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            r = torchvision.models.resnet50(weights=None, replace_stride_with_dilation=[False, False, True])
+            for p in r.parameters():
+                p.requires_grad = False
+            self.layer0 = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
+            self.layer1, self.layer2, self.layer3, self.layer4 = r.layer1, r.layer2, r.layer3, r.layer4
+            self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+            self.fc = nn.Linear(r.fc.in_features, num_classes)
+
+        def forward(self, x):
+            x = self.layer0(x)
+            f1 = self.layer1(x)
+            f2 = self.layer2(f1)
+            f3 = self.layer3(f2)
+            f4 = self.layer4(f3)
+            return self.fc(self.avgpool(f4).flatten(1)), [f2, f3, f4]
+
+    torch.manual_seed(0)
+    return Net().eval()
+
+
+def cpu_pseudomask_sample(n_images, threads):
+    """The reference's path for configs[0] on the host: one image at a time through the classifier (forward + backward
+    to the hooks, LayerCAM.py:35-48), LayerCAM.py:52-76, threshold (PsuedoMasks.py:59-62), keep_largest (:15-21)."""
+    import torch
+
+    from oracle import wsdl_oracle as O
+
+    torch.set_num_threads(threads)
+    net = _hookable_resnet50()
+    store = {}
+    for name in ("layer3", "layer4"):
+        layer = getattr(net, name)
+        layer.register_forward_hook(lambda m, i, o, name=name: store.__setitem__("a_" + name, o))
+        layer.register_full_backward_hook(lambda m, gi, go, name=name: store.__setitem__("g_" + name, go[0]))
+    gen = torch.Generator().manual_seed(0)
+    imgs = torch.rand(n_images, 3, 224, 224, generator=gen)
+    labels = torch.randint(0, 37, (n_images,), generator=gen)
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        x = imgs[i:i + 1].clone().requires_grad_()
+        logits, _ = net(x)
+        logits.gather(1, labels[i:i + 1].view(-1, 1)).squeeze().backward()
+        cam = O.layercam_from_hooks([store["a_layer3"], store["a_layer4"]], [store["g_layer3"], store["g_layer4"]], (224, 224))
+        O.keep_largest(O.threshold_mask(cam[0], 0.3))
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def bench_pseudomask(args, dev, rank, world):
+    """configs[0] through the drop-in classes, end to end: pinned host images -> H2D -> classifier forward + backward
+    (cuDNN) -> fused LayerCAM/normalise/upsample/threshold -> keep_largest -> D2H masks.  B = 32 images per step."""
+    import torch
+
+    from weaklysuperviseddl_b200 import functional as WF
+    from weaklysuperviseddl_b200.LayerCAM import LayerCAMGenerator
+
+    B = 32
+    net = _hookable_resnet50().to(dev)
+    gen_cam = LayerCAMGenerator(net, ["layer3", "layer4"])
+    g = torch.Generator().manual_seed(1 + rank)
+    h_imgs = torch.rand(B, 3, 224, 224, generator=g).pin_memory()
+    h_masks = torch.empty(B, 224, 224, dtype=torch.uint8).pin_memory()
+    labels = torch.randint(0, 37, (B,), generator=g).to(dev)
+    t_fused = []
+
+    def step(measure=False):
+        imgs = h_imgs.to(dev, non_blocking=True)
+        acts, grads = gen_cam._forward_backward(imgs, labels)
+        if measure:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        cam, mask, near = WF.layercam_fused(acts, grads, (224, 224), thresh=0.3, want_cam=False)
+        mask = WF.keep_largest(mask)
+        if measure:
+            e1.record()
+        h_masks.copy_(mask, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        if measure:
+            t_fused.append(e0.elapsed_time(e1))
+
+    def run_steps(n):
+        for _ in range(n):
+            step()
+
+    steps = min(args.steps, 200)
+    ms, _ = _timed(run_steps, max(3, min(args.warmup, 10)), steps, dev, world, None)
+    for _ in range(5):
+        step(measure=True)
+    value = world * B * steps / (ms * 1e-3)
+    res = {
+        "metric": "pseudo-masks/s (end to end: classifier fwd+bwd + LayerCAM -> mask + keep_largest)", "value": value,
+        "unit": "masks/s", "n_gpus": world, "steps": steps, "warmup": max(3, min(args.warmup, 10)), "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[0]: LayerCAM pseudo-mask generation, ResNet-50 (dilated layer4, random init), "
+                               "37 classes, 32x3x224x224 per step per GPU, through LayerCAMGenerator + keep_largest"},
+        "e2e": {"value": value, "unit": "masks/s", "h2d_bytes_per_step": h_imgs.numel() * 4,
+                "d2h_bytes_per_step": h_masks.numel(), "steps": steps, "ms_per_step": ms / steps,
+                "api": "LayerCAMGenerator(model, ['layer3','layer4']) hooks + fused layercam + keep_largest; pinned host buffers"},
+        "stage_share": {"fused_layercam_plus_keep_largest_ms": sum(t_fused) / len(t_fused), "step_ms": ms / steps,
+                        "note": "the rest of the step is the cuDNN classifier (out of scope by north_star) and PCIe"},
+        "gpu_launches": 4 * steps,
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, t = cpu_pseudomask_sample(2, threads)
+        res["cpu_baseline"] = {"value": v, "unit": "masks/s", "cores": threads, "kind": "port",
+                               "sample": f"2 images, one at a time, {t:.2f} s: torchvision ResNet-50 on the host cores + "
+                                         "oracle port of LayerCAM.py:52-76, PsuedoMasks.py:59-62, :15-21"}
+    return res
 
 
 if __name__ == "__main__":
