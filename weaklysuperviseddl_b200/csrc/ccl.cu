@@ -5,13 +5,23 @@
 // regionprops, max by area (first maximum = lowest label = component whose first pixel comes first
 // in raster order), `labeled == label`.  Empty masks are returned unchanged.
 //
-// Union-find with the minimum pixel index as root (so root order == skimage label order):
-//   init  -> merge with the 4 already-visited neighbours (W, NW, N, NE) -> flatten + area histogram
-//   -> per-image argmax of (area, -root) packed in one u64 atomicMax -> select.
+// Union-find with the minimum pixel index as root (so root order == skimage label order), in two levels:
+//   1. ccl_tile    one CTA labels a 32x32 tile in SHARED memory: horizontal runs are resolved with one ballot per
+//                  row (a pixel starts at the first pixel of its run), runs are joined to the row above with shared-
+//                  memory atomicMin unions (only where the left neighbour has not already made the same join), the
+//                  tile is flattened, pixels are counted per local root, and every pixel writes the GLOBAL index of
+//                  its local root; local roots also write their pixel count.
+//   2. ccl_seams   pixels on the first row / first column of a tile join the neighbours across the seam in global
+//                  memory (paths are two hops long at this point).
+//   3. ccl_gather  every local root adds its count to its global root (one atomic per local component, not per
+//                  pixel), true roots compete for the per-image (area, -root) maximum packed in one u64 atomicMax.
+//   4. ccl_select  a pixel belongs to the winner iff the root of its local root is the winning root.
 // Integer work: bit-exact against the oracle by construction.
 #include "common.cuh"
 
 namespace wsdl {
+
+constexpr int CT = 32;  // tile edge: one warp per row
 
 __device__ __forceinline__ int uf_find(const int* L, int i) {
   int p = L[i];
@@ -38,47 +48,118 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
-__global__ void ccl_init_local(const uint8_t* __restrict__ mask, int* __restrict__ L, unsigned* __restrict__ area,
-                               unsigned long long* __restrict__ best, int HW, int B) {
-  const int b = blockIdx.y;
-  const uint8_t* m = mask + (size_t)b * HW;
-  int* Lb = L + (size_t)b * HW;
-  unsigned* ab = area + (size_t)b * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    Lb[i] = m[i] ? i : -1;
-    ab[i] = 0;
+// L: -1 background, else global index (within the image) of a pixel of the same component, L[root] == root.
+// area: pixel count of the local component at its local root, 0 elsewhere.
+__global__ void __launch_bounds__(CT * CT / 4) ccl_tile(const uint8_t* __restrict__ mask, int* __restrict__ L,
+                                                         unsigned* __restrict__ area, unsigned long long* __restrict__ best,
+                                                         int H, int W) {
+  __shared__ int s_lab[CT * CT];
+  __shared__ unsigned s_cnt[CT * CT];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * CT, y0 = blockIdx.y * CT;
+  const size_t img = (size_t)b * H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps, 4 rows each
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) best[b] = 0ull;
+
+  // rows: horizontal runs by ballot; a pixel's first label is the first pixel of its run
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ly = warp * 4 + k, y = y0 + ly, x = x0 + lane;
+    const bool fg = y < H && x < W && mask[img + (size_t)y * W + x] != 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, fg);
+    const unsigned below = ~bits & ((1u << lane) - 1u);            // background pixels left of this one
+    const int start = below ? 32 - __clz(below) : 0;               // first pixel after the last of them
+    s_lab[ly * CT + lane] = fg ? ly * CT + start : -1;
+    s_cnt[ly * CT + lane] = 0u;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) best[b] = 0ull;
+  __syncthreads();
+  // join with the row above: N, else NW / NE, skipping the joins the left / right neighbour makes anyway
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ly = warp * 4 + k;
+    if (ly == 0) continue;
+    const int i = ly * CT + lane;
+    if (s_lab[i] < 0) continue;
+    const bool n = s_lab[i - CT] >= 0;
+    const bool w = lane > 0 && s_lab[i - 1] >= 0;
+    const bool nw = lane > 0 && s_lab[i - CT - 1] >= 0;
+    const bool e = lane < CT - 1 && s_lab[i + 1] >= 0;
+    const bool ne = lane < CT - 1 && s_lab[i - CT + 1] >= 0;
+    if (n) {
+      if (!(w && nw)) uf_union(s_lab, i, i - CT);  // else W has joined NW, which is in N's run
+    } else {
+      if (nw && !w) uf_union(s_lab, i, i - CT - 1);  // else W has joined its N = NW
+      if (ne && !e) uf_union(s_lab, i, i - CT + 1);  // else E joins its N = NE
+    }
+  }
+  __syncthreads();
+  // flatten, count per local root
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = (warp * 4 + k) * CT + lane;
+    if (s_lab[i] < 0) continue;
+    const int r = uf_find(s_lab, i);
+    s_lab[i] = r;  // roots keep s_lab[r] == r, so concurrent finds stay correct
+    atomicAdd(&s_cnt[r], 1u);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ly = warp * 4 + k, y = y0 + ly, x = x0 + lane;
+    if (y >= H || x >= W) continue;
+    const int i = ly * CT + lane, r = s_lab[i];
+    const size_t g = (size_t)y * W + x;
+    L[img + g] = r < 0 ? -1 : (y0 + r / CT) * W + (x0 + r % CT);
+    area[img + g] = (r == i) ? s_cnt[i] : 0u;
+  }
 }
 
-__global__ void ccl_merge(int* __restrict__ L, int H, int W) {
+// joins across the tile seams; one thread per seam pixel (first row and first column of every tile)
+__global__ void ccl_seams(int* __restrict__ L, int H, int W) {
   const int b = blockIdx.y;
-  const int HW = H * W;
-  int* Lb = L + (size_t)b * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    if (Lb[i] < 0) continue;
-    const int y = i / W, x = i - y * W;
-    if (x > 0 && Lb[i - 1] >= 0) uf_union(Lb, i, i - 1);
-    if (y > 0) {
-      if (Lb[i - W] >= 0) {
-        uf_union(Lb, i, i - W);
-      } else {  // N is background: NW and NE are not yet connected through it
-        if (x > 0 && Lb[i - W - 1] >= 0) uf_union(Lb, i, i - W - 1);
-        if (x + 1 < W && Lb[i - W + 1] >= 0) uf_union(Lb, i, i - W + 1);
+  int* Lb = L + (size_t)b * H * W;
+  const int rows = (H - 1) / CT, cols = (W - 1) / CT;  // interior seams
+  const int n_row = rows * W, n_col = cols * H;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_row + n_col; t += gridDim.x * blockDim.x) {
+    if (t < n_row) {  // pixel (y, x) in the first row of a tile: N, NW, NE are across the seam
+      const int y = (t / W + 1) * CT, x = t % W, i = y * W + x;
+      if (Lb[i] < 0) continue;
+      const bool n = Lb[i - W] >= 0;
+      const bool w = x > 0 && Lb[i - 1] >= 0, nw = x > 0 && Lb[i - W - 1] >= 0;
+      const bool e = x + 1 < W && Lb[i + 1] >= 0, ne = x + 1 < W && Lb[i - W + 1] >= 0;
+      // the left / right neighbour is in the same tile row only when it is not across a column seam; its own seam
+      // join covers ours exactly as inside a tile, whichever tile it is in
+      if (n) {
+        if (!(w && nw)) uf_union(Lb, i, i - W);
+      } else {
+        if (nw && !w) uf_union(Lb, i, i - W - 1);
+        if (ne && !e) uf_union(Lb, i, i - W + 1);
       }
+    } else {  // pixel in the first column of a tile: W, NW, SW are across the seam
+      const int u = t - n_row;
+      const int x = (u / H + 1) * CT, y = u % H, i = y * W + x;
+      if (Lb[i] < 0) continue;
+      if (Lb[i - 1] >= 0) uf_union(Lb, i, i - 1);
+      if (y > 0 && Lb[i - W - 1] >= 0) uf_union(Lb, i, i - W - 1);
+      if (y + 1 < H && Lb[i + W - 1] >= 0) uf_union(Lb, i, i + W - 1);
     }
   }
 }
 
-__global__ void ccl_flatten_area(int* __restrict__ L, unsigned* __restrict__ area, int HW) {
+// local roots hand their count to their global root; then (second launch) true roots compete for the maximum
+__global__ void ccl_gather(int* __restrict__ L, unsigned* __restrict__ area, int HW) {
   const int b = blockIdx.y;
   int* Lb = L + (size_t)b * HW;
   unsigned* ab = area + (size_t)b * HW;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    if (Lb[i] < 0) continue;
+    const unsigned a = ab[i];
+    if (a == 0u) continue;  // not a local root
     const int r = uf_find(Lb, i);
-    Lb[i] = r;  // roots keep L[r] == r, so concurrent finds stay correct
-    atomicAdd(ab + r, 1u);
+    if (r != i) {
+      atomicAdd(ab + r, a);
+      ab[i] = 0u;
+      Lb[i] = r;  // compress: pixels of this local component reach the root in two hops
+    }
   }
 }
 
@@ -89,8 +170,9 @@ __global__ void ccl_argmax(const int* __restrict__ L, const unsigned* __restrict
   const unsigned* ab = area + (size_t)b * HW;
   unsigned long long local = 0ull;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    if (Lb[i] == i) {  // a root
-      const unsigned long long key = ((unsigned long long)ab[i] << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    const unsigned a = ab[i];
+    if (a != 0u && Lb[i] == i) {  // a true root
+      const unsigned long long key = ((unsigned long long)a << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
       local = key > local ? key : local;
     }
   }
@@ -109,8 +191,10 @@ __global__ void ccl_select(const int* __restrict__ L, const unsigned long long* 
   const int root = key ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -2;
   const int* Lb = L + (size_t)b * HW;
   uint8_t* ob = out + (size_t)b * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
-    ob[i] = (Lb[i] == root) ? 1 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const int p = Lb[i];
+    ob[i] = (p >= 0 && uf_find(Lb, p) == root) ? 1 : 0;
+  }
   if (best_area && blockIdx.x == 0 && threadIdx.x == 0) best_area[b] = (unsigned)(key >> 32);
 }
 
@@ -137,13 +221,20 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   int* L = reinterpret_cast<int*>(ws);
   unsigned* area = reinterpret_cast<unsigned*>(ws + n * 4);
   cudaStream_t s = (cudaStream_t)stream;
+  const int tx = (W + CT - 1) / CT, ty = (H + CT - 1) / CT;
+  if (ty > 65535) return WSDL_E_SHAPE;
+  ccl_tile<<<dim3(tx, ty, B), CT * CT / 4, 0, s>>>(mask, L, area, best, H, W);
   int bx = (HW + 255) / 256;
   const int cap = (WSDL_NUM_SMS * 8 + B - 1) / B;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, B);
-  ccl_init_local<<<grid, 256, 0, s>>>(mask, L, area, best, HW, B);
-  ccl_merge<<<grid, 256, 0, s>>>(L, H, W);
-  ccl_flatten_area<<<grid, 256, 0, s>>>(L, area, HW);
+  const int seam_px = ((H - 1) / CT) * W + ((W - 1) / CT) * H;
+  if (seam_px > 0) {
+    int sb = (seam_px + 255) / 256;
+    if (sb > cap) sb = cap < 1 ? 1 : cap;
+    ccl_seams<<<dim3(sb, B), 256, 0, s>>>(L, H, W);
+  }
+  ccl_gather<<<grid, 256, 0, s>>>(L, area, HW);
   ccl_argmax<<<grid, 256, 0, s>>>(L, area, best, HW);
   ccl_select<<<grid, 256, 0, s>>>(L, best, out, best_area, HW);
   WSDL_LAUNCH_CHECK();
