@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--one-stream", action="store_true")
     ap.add_argument("--separate", action="store_true", help="two launches per step (cut, boundary) instead of the fused one")
     ap.add_argument("--stream-pairs", type=int, default=2)
+    ap.add_argument("--graph-steps", type=int, default=32, help="steps captured per CUDA graph (pairwise workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
@@ -407,15 +408,16 @@ def bench_pairwise(args, lib, dev, rank, world):
             cur.wait_stream(sb)
 
     graph = None
+    G_STEPS = max(1, args.graph_steps)
     if not args.no_graph:
-        some_steps(range(N_SETS))
+        some_steps(range(G_STEPS))
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            some_steps(range(N_SETS))
+            some_steps(range(G_STEPS))
 
     def run_steps(n):
-        full, rem = (n // N_SETS, n % N_SETS) if graph is not None else (0, n)
+        full, rem = (n // G_STEPS, n % G_STEPS) if graph is not None else (0, n)
         for _ in range(full):
             graph.replay()
         if rem:
@@ -470,7 +472,7 @@ def bench_pairwise(args, lib, dev, rank, world):
                      "1 cut fwd+bwd launch (logits, sigma 0.05) + 1 boundary fwd+bwd launch (32 images, sigma 0.1/5); ") +
                     "pixels counted once per loss",
             "l2": f"rotating {N_SETS} input sets ({N_SETS * 45} MB) > {L2_MB} MB L2",
-            "launch": ("CUDA graph of 8 steps" if graph is not None else "direct C-ABI calls") +
+            "launch": (f"CUDA graph of {G_STEPS} steps" if graph is not None else "direct C-ABI calls") +
                       ((f"; consecutive steps rotate over {n_streams} streams (independent work, own workspaces)" if fused else
                         f"; the cut and the boundary launch of a step on two streams, consecutive steps on {n_pairs} stream "
                         "pairs (independent work, own workspaces)") if two else "; one stream"),

@@ -54,11 +54,18 @@ constexpr int PS_PITCH = 68;                   // smem row: image x0-4 .. x0+63 
 constexpr int PS_Q = PS_PITCH / 4;             // float4 per staged row
 constexpr int PS_SEGS = 8;                     // row segments per block, one per half warp
 constexpr int PS_THREADS = 16 * PS_SEGS;       // 128
+// Tile height and residency.  3 CTAs per SM with segments of up to 5 rows (40 centre rows, 67 KB of shared memory,
+// <= 168 registers) beat 4 CTAs with 4-row segments (<= 128 registers) on configs[1]: 22.5 vs 25.5 us per fused launch
+// -- the fixed cost of a block (tile load, conversion, segment heads, loss ticket) is spread over more rows, 224 rows
+// split into 6 blocks of 38 use 93 % of the centre rows instead of 87.5 %, and the packed march needs no spills.
 #ifndef WSDL_PS_SMAX
-#define WSDL_PS_SMAX 4
+#define WSDL_PS_SMAX 5
 #endif
 #ifndef WSDL_PS_CTAS
-#define WSDL_PS_CTAS 4
+#define WSDL_PS_CTAS 3
+#endif
+#ifndef WSDL_PS_PACKED
+#define WSDL_PS_PACKED 1  // dual kernel: two-lane FP32 instructions (FADD2 / FFMA2) in the march
 #endif
 constexpr int PS_SMAX = WSDL_PS_SMAX;           // rows per segment
 constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 32 centre rows per block: 2 warm-up + 30 owned
@@ -854,6 +861,120 @@ __device__ __forceinline__ void ps_step_dual(float (&X)[8][2], float (&Y)[8][2],
                    ratio);
 }
 
+// ---- packed (f32x2) form of the dual step -------------------------------------------------------------------
+// sm_100a has two-lane FP32 instructions (FADD2 / FFMA2, with operand negation and scalar broadcast operands): the
+// same lane rate as the scalar ones but HALF the issue slots, and this kernel is bound by issue slots.  Two pairs
+// with the same offset whose centres are column neighbours are evaluated per packed instruction: 12 FADD2/FFMA2 +
+// 4 MUFU for two pairs instead of 24 + 4.  A packed operand is an (even, odd) register pair, so:
+//   * accumulator rows and staged windows are float2 "even pairs" E_k = columns (2k, 2k+1) of the 8-column window,
+//     straight from the 128-bit shared-memory loads;
+//   * even dx: centres E1, E2 against partners E_(1+dx/2), E_(2+dx/2);
+//   * odd dx between rows: the pairs are grouped by their PARTNER column (2..5 = E1, E2 of row t+1 / t+2), their
+//     centres are then the "odd pairs" O_k = columns (2k+1, 2k+2) of row t: O1, O2 for dx = -1 and O0, O1 for
+//     dx = +1.  Every partner column belongs to exactly one strip, so each pair is still evaluated once;
+//   * same row, dx = 1: centres E1, E2 against partners O1, O2.
+// Only row t is ever needed at the odd alignment: its 12 odd input pairs are built once per step, and its odd
+// accumulators XO (columns 1..6) are folded into the even ones before the row is exchanged and emitted.
+struct PsWin2 {
+  float2 e[4][4];  // [plane: I0, I1, I2, p0][even pair]
+};
+
+__device__ __forceinline__ void ps_load2(PsWin2& w, const float* s_img, const float* s_p, int off) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float* src = (c < 3 ? s_img + c * PS_PLANE : s_p) + off;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    w.e[c][0] = make_float2(a.x, a.y), w.e[c][1] = make_float2(a.z, a.w);
+    w.e[c][2] = make_float2(b.x, b.y), w.e[c][3] = make_float2(b.z, b.w);
+  }
+}
+
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+
+// two pairs: centres a (4 planes), partners b; ga/gb = (cut, boundary) accumulators of the centres / partners
+__device__ __forceinline__ void ps_pair2(float2 (&ga)[2], float2 (&gb)[2], const float2 (&a)[4], const float2 (&b)[4],
+                                         float kc_off, float kb_off, float ratio) {
+  const float2 d0 = __fadd2_rn(a[0], f2neg(b[0])), d1 = __fadd2_rn(a[1], f2neg(b[1])), d2 = __fadd2_rn(a[2], f2neg(b[2]));
+  const float2 ec =
+      __ffma2_rn(f2neg(d2), d2, __ffma2_rn(f2neg(d1), d1, __ffma2_rn(f2neg(d0), d0, make_float2(kc_off, kc_off))));
+  const float2 eb = __ffma2_rn(ec, make_float2(ratio, ratio), make_float2(kb_off, kb_off));
+  const float2 kc = make_float2(ex2_approx(ec.x), ex2_approx(ec.y));
+  const float2 kb = make_float2(ex2_approx(eb.x), ex2_approx(eb.y));
+  const float2 dp = __fadd2_rn(a[3], f2neg(b[3]));
+  ga[0] = __ffma2_rn(kc, dp, ga[0]);
+  gb[0] = __ffma2_rn(f2neg(kc), dp, gb[0]);
+  ga[1] = __ffma2_rn(kb, dp, ga[1]);
+  gb[1] = __ffma2_rn(f2neg(kb), dp, gb[1]);
+}
+
+#define PS_PL(w, k) {w.e[0][k], w.e[1][k], w.e[2][k], w.e[3][k]}
+
+// All 12 forward pairs of the columns of row t.  X, Y, Z: even-pair accumulators [pair][cut, boundary] of rows t, t+1,
+// t+2.  On return X also holds the odd-aligned contributions of this step (columns 1..6).
+__device__ __forceinline__ void ps_step_dual2(float2 (&X)[4][2], float2 (&Y)[4][2], float2 (&Z)[4][2], float (&pc)[4],
+                                              const float* s_img, const float* s_p, int off, const PsKsDual& ks, float ratio) {
+  PsWin2 c;
+  ps_load2(c, s_img, s_p, off);
+  pc[0] = c.e[3][1].x, pc[1] = c.e[3][1].y, pc[2] = c.e[3][2].x, pc[3] = c.e[3][2].y;
+  float2 co[3][4];  // odd pairs of row t: [k][plane] = columns (2k+1, 2k+2)
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) co[k][pl] = make_float2(c.e[pl][k].y, c.e[pl][k + 1].x);
+  float2 XO[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) XO[k][0] = XO[k][1] = make_float2(0.f, 0.f);
+  const float2 ce1[4] = PS_PL(c, 1), ce2[4] = PS_PL(c, 2), ce3[4] = PS_PL(c, 3);
+  // same row
+  ps_pair2(X[1], XO[1], ce1, co[1], ks.ca, ks.a1, ratio);
+  ps_pair2(X[2], XO[2], ce2, co[2], ks.ca, ks.a1, ratio);
+  ps_pair2(X[1], X[2], ce1, ce2, ks.ca, ks.a4, ratio);
+  ps_pair2(X[2], X[3], ce2, ce3, ks.ca, ks.a4, ratio);
+#pragma unroll
+  for (int r = 1; r <= 2; ++r) {
+    float2 (&Yr)[4][2] = r == 1 ? Y : Z;
+    const float kc = r == 1 ? ks.cb : ks.cc;
+    const float k0 = r == 1 ? ks.b0 : ks.c0, k1 = r == 1 ? ks.b1 : ks.c1, k4 = r == 1 ? ks.b4 : ks.c4;
+    PsWin2 n;
+    ps_load2(n, s_img, s_p, off + r * PS_PITCH);
+    const float2 n0[4] = PS_PL(n, 0), n1[4] = PS_PL(n, 1), n2[4] = PS_PL(n, 2), n3[4] = PS_PL(n, 3);
+    ps_pair2(X[1], Yr[0], ce1, n0, kc, k4, ratio);     // dx = -2
+    ps_pair2(X[2], Yr[1], ce2, n1, kc, k4, ratio);
+    ps_pair2(XO[1], Yr[1], co[1], n1, kc, k1, ratio);  // dx = -1: centres 3,4 and 5,6
+    ps_pair2(XO[2], Yr[2], co[2], n2, kc, k1, ratio);
+    ps_pair2(X[1], Yr[1], ce1, n1, kc, k0, ratio);     // dx = 0
+    ps_pair2(X[2], Yr[2], ce2, n2, kc, k0, ratio);
+    ps_pair2(XO[0], Yr[1], co[0], n1, kc, k1, ratio);  // dx = +1: centres 1,2 and 3,4
+    ps_pair2(XO[1], Yr[2], co[1], n2, kc, k1, ratio);
+    ps_pair2(X[1], Yr[2], ce1, n2, kc, k4, ratio);     // dx = +2
+    ps_pair2(X[2], Yr[3], ce2, n3, kc, k4, ratio);
+  }
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    X[0][ch].y += XO[0][ch].x;
+    X[1][ch].x += XO[0][ch].y;
+    X[1][ch].y += XO[1][ch].x;
+    X[2][ch].x += XO[1][ch].y;
+    X[2][ch].y += XO[2][ch].x;
+    X[3][ch].x += XO[2][ch].y;
+  }
+}
+
+__device__ __forceinline__ void ps_exchange2(const float2 (&X)[4][2], float (&own)[4][2], int strip) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float r0 = __shfl_down_sync(0xffffffffu, X[0][c].x, 1), r1 = __shfl_down_sync(0xffffffffu, X[0][c].y, 1);
+    float l0 = __shfl_up_sync(0xffffffffu, X[3][c].x, 1), l1 = __shfl_up_sync(0xffffffffu, X[3][c].y, 1);
+    if (strip == 15) r0 = 0.f, r1 = 0.f;
+    if (strip == 0) l0 = 0.f, l1 = 0.f;
+    own[0][c] = X[1][c].x + l0;
+    own[1][c] = X[1][c].y + l1;
+    own[2][c] = X[2][c].x + r0;
+    own[3][c] = X[2][c].y + r1;
+  }
+}
+
 // 4 finished pixels of centre row t: G[.][0] cut, G[.][1] boundary, one probability p0 each
 __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, float scale_b, int t, int strip, int okmask,
                                              const float (&G)[4][2], const float (&pc)[4], float* s_gband, float& lsum_c,
@@ -998,8 +1119,16 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 #pragma unroll
   for (int q = 0; q < 4; ++q) oy[q][0] = oy[q][1] = oz[q][0] = oz[q][1] = 0.f;
   if (warp * 2 * S < K.nc) {
+#if WSDL_PS_PACKED
+    float2 A[4][2], Bq[4][2], Cq[4][2];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) A[w][c] = Bq[w][c] = Cq[w][c] = make_float2(0.f, 0.f);
+#else
     float A[8][2], Bq[8][2], Cq[8][2];
     ps_zero<2>(A), ps_zero<2>(Bq), ps_zero<2>(Cq);
+#endif
     const float ksu = D.ksu_b, ratio = D.ratio;
     // one copy of the step in the instruction stream: unrolling by 2 / 3 (which would let the accumulator rows rotate
     // by renaming instead of moves) costs 29 -> 36 / 41 us per step -- the ~13 KB body already strains the
@@ -1021,9 +1150,15 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
         ks.a1 = ksu + l0b - ra, ks.a4 = 4.f * ksu + l0b - ra;
         ks.b0 = ksu + l1 - rb, ks.b1 = 2.f * ksu + l1 - rb, ks.b4 = 5.f * ksu + l1 - rb;
         ks.c0 = 4.f * ksu + l2 - rc, ks.c1 = 5.f * ksu + l2 - rc, ks.c4 = 8.f * ksu + l2 - rc;
+#if WSDL_PS_PACKED
+        ps_step_dual2(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
+      }
+      ps_exchange2(A, own, strip);
+#else
         ps_step_dual(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
       }
       ps_exchange<2>(A, own, strip);
+#endif
       if (act) {
         if (s >= 2) {
           ps_emit_dual(Q, K, scale_b, t, strip, okmask, own, pc, s_gband, lsum_c, lsum_b);
@@ -1034,6 +1169,15 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
                 make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
         }
       }
+#if WSDL_PS_PACKED
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = make_float2(0.f, 0.f);
+    }
+    ps_exchange2(A, oy, strip);
+    ps_exchange2(Bq, oz, strip);
+#else
 #pragma unroll
       for (int w = 0; w < 8; ++w)
 #pragma unroll
@@ -1041,6 +1185,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     }
     ps_exchange<2>(A, oy, strip);
     ps_exchange<2>(Bq, oz, strip);
+#endif
   }
   __syncthreads();  // every head row holds its own segment's part
   if (seg < PS_SEGS - 1) {
@@ -1172,7 +1317,7 @@ static int ps_row_blocks(int B, int H, int W) {
     if (n < 6 && nb > nb_min) break;
     const int S = (n + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n + 2 + PS_SEGS - 1) / PS_SEGS;
     const double per_sm = (double)B * n_x * nb / WSDL_NUM_SMS;
-    const double rounds = per_sm < 2.0 ? 2.0 : (double)(long long)(per_sm + 0.999999);
+    const double rounds = per_sm < 2.0 ? 2.0 : per_sm;  // blocks of concurrent launches fill the ragged last round
     const double cost = (S + 1.5) * rounds;
     if (cost < best_cost - 1e-9) best_cost = cost, best = nb;
   }
@@ -1251,11 +1396,12 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
   Q.l32 = log2f(1.5f), Q.l1g = log2f(1.f + Q.g4);
-  {  // one quarter wave of tiles at ~6 TB/s; only when the launch fills the machine
+  {  // a sixteenth of a wave of tiles at ~6 TB/s (a longer hold-back helps a lone launch by 2-3 % and costs launches
+     // that overlap on the device 4 %); only when the launch fills the machine
     static const int stagger_env = []() { const char* e = getenv("WSDL_PS_STAGGER_NS"); return e ? atoi(e) : -1; }();
     const double tile_bytes = (double)(3 + P.C) * (PS_SEGS * Q.S + 2) * PS_PITCH * 4.0;
     const long long ctas = (long long)Q.nb * Q.n_x * P.B;
-    Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 6000.0) : 0u;
+    Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 24000.0) : 0u;
     if (stagger_env >= 0) Q.stagger_ns = (unsigned)stagger_env;
   }
   CUtensorMap tm_img, tm_val;
@@ -1290,7 +1436,7 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
     static const int stagger_env = []() { const char* e = getenv("WSDL_PS_STAGGER_NS"); return e ? atoi(e) : -1; }();
     const double tile_bytes = 5.0 * (PS_SEGS * Q.S + 2) * PS_PITCH * 4.0;
     const long long ctas = (long long)Q.nb * Q.n_x * P.B;
-    Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 6000.0) : 0u;
+    Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 24000.0) : 0u;
     if (stagger_env >= 0) Q.stagger_ns = (unsigned)stagger_env;
   }
   PsDual D;
