@@ -28,10 +28,14 @@ LCAM = dict(S=512, layers=((1024, 32, 32), (2048, 32, 32)), chunk=128, thresh=0.
 N_SETS = 8  # rotated input sets: 8 x 45 MB > 126 MB L2
 BYTES_PER_PIX = 28  # 20 B read (2 logits + 3 rgb) + 8 B gradient written, C=2
 L2_MB = 126
-NCU_TRAFFIC_BYTES = 32_220_000  # dram read 32.18 MB + write 0.04 MB per launch (ncu --set full, round 1)
+NCU_TRAFFIC_BYTES = 32_230_000  # dram read 32.18 MB + write 0.05 MB per launch (ncu --set full, round 1)
 # warp instructions per launch (smsp__inst_executed.sum, profiles/r01_c_ncu_full_sym.txt): the kernels are bound by
 # instruction issue (FP32 + MUFU), not HBM -- 148 SMs x 4 schedulers x 1 instruction per clock is the second roof
-NCU_WARP_INSTR = {"fused": 20.10e6, "cut": 15.27e6, "boundary": 18.00e6}
+NCU_WARP_INSTR = {"fused": 15.88e6, "cut": 15.27e6, "boundary": 18.00e6}
+# third roof of the fused launch: MUFU (ex2 / rcp) warp instructions per launch from the same capture x 32 lanes against
+# the measured MUFU rate of this B200 (tests/native/pipe_probe.cu: 4.63 T lane-op/s = 16 per clock per SM)
+NCU_MUFU_WARP_INSTR = {"fused": 1.714e6}
+MUFU_LANE_OPS_PER_S = 4.63e12
 
 
 def peaks():
@@ -486,6 +490,12 @@ def bench_pairwise(args, lib, dev, rank, world):
                      "issue_roof": {"warp_instructions_per_launch": instr, "floor_ms": issue_floor_ms,
                                     "frac": issue_floor_ms / launch_ms,
                                     "note": "second roof: ncu warp instructions / (148 SMs x 4 schedulers x SM clock)"},
+                     **({"mufu_roof": {"warp_instructions_per_launch": NCU_MUFU_WARP_INSTR["fused"],
+                                       "floor_ms": NCU_MUFU_WARP_INSTR["fused"] * 32 / MUFU_LANE_OPS_PER_S * 1e3,
+                                       "frac": NCU_MUFU_WARP_INSTR["fused"] * 32 / MUFU_LANE_OPS_PER_S * 1e3 / launch_ms,
+                                       "note": "third roof: MUFU.EX2 + MUFU.RCP lane-ops / measured 4.63 T/s; the march "
+                                               "needs 768 MUFU cycles, 775 issue slots and ~680 FP32-pipe cycles per "
+                                               "warp step: the three pipes are balanced"}} if fused else {}),
                      "note": "launch duration = timed step / launches per step (CUDA events on the stream the steps are forked "
                              "from and joined to, inside the graph; launches on different streams overlap, so this is the "
                              "time the step spends per launch, not a kernel duration: those are in "

@@ -3,5 +3,5 @@
 # with WSDL_NVCC_EXTRA=-DWSDL_PS_TRACE); set TRACE=pipe for the persistent variant
 cp weaklysuperviseddl_b200/libwsdl_b200.so /tmp/keep.so
 cp weaklysuperviseddl_b200/libwsdl_b200_trace.so weaklysuperviseddl_b200/libwsdl_b200.so
-if [ "$TRACE" = "pipe" ]; then WSDL_PAIRWISE_PIPE=1 PYTHONPATH=. python scripts/trace_pipe.py 2>&1 | grep -v Warn; else PYTHONPATH=. python scripts/trace_ctas.py 2>&1 | grep -v Warn; fi
+if [ "$TRACE" = "pipe" ]; then WSDL_PAIRWISE_PIPE=1 PYTHONPATH=. python scripts/trace_pipe.py 2>&1 | grep -v Warn; else PYTHONPATH=. python scripts/trace_ctas.py $TRACE_CASES 2>&1 | grep -v Warn; fi
 cp /tmp/keep.so weaklysuperviseddl_b200/libwsdl_b200.so

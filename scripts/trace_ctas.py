@@ -13,12 +13,19 @@ lib = _native.lib()
 lib.wsdl_ps_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 N = 4096
-names = ["start", "tma landed", "early rows", "all rows", "neighbour ok", "step0", "step1", "step2", "step3", "march end",
+names = ["start", "tma landed", "early rows", "all rows", "neighbour ok", "step0", "step1", "step2", "step3", "march end (dual S=5: + step4)",
          "barrier", "heads", "band pass", "end"]
-for name, args in (("cut", (logits, img, 5, 0.05, None, True, True, False)), ("boundary", (probs, img, 5, 0.1, 5.0, False, False, True))):
+cases = [("cut", (logits, img, 5, 0.05, None, True, True, False)), ("boundary", (probs, img, 5, 0.1, 5.0, False, False, True)),
+         ("dual", None)]
+if len(sys.argv) > 1:
+    cases = [c for c in cases if c[0] in sys.argv[1:]]
+for name, args in cases:
     for _ in range(3):
         flush.zero_()
-        WF.pairwise_loss_and_grad(*args)
+        if args is None:
+            WF.pairwise_dual_loss_and_grad(logits, img)
+        else:
+            WF.pairwise_loss_and_grad(*args)
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * (N * 64))()
     lib.wsdl_ps_trace_read(buf, N)

@@ -52,8 +52,12 @@ namespace wsdl {
 constexpr int PS_TW = 60;                      // owned columns per tile
 constexpr int PS_PITCH = 68;                   // smem row: image x0-4 .. x0+63 (2 pad + 2 halo | 60 | 2 halo + 2 pad)
 constexpr int PS_Q = PS_PITCH / 4;             // float4 per staged row
-constexpr int PS_SEGS = 8;                     // row segments per block, one per half warp
-constexpr int PS_THREADS = 16 * PS_SEGS;       // 128
+#ifndef WSDL_PS_SEGS
+#define WSDL_PS_SEGS 8
+#endif
+constexpr int PS_SEGS = WSDL_PS_SEGS;          // row segments per block, one per half warp (even)
+constexpr int PS_THREADS = 16 * PS_SEGS;
+constexpr int PS_WARPS = PS_SEGS / 2;
 // Tile height and residency.  3 CTAs per SM with segments of up to 5 rows (40 centre rows, 67 KB of shared memory,
 // <= 168 registers) beat 4 CTAs with 4-row segments (<= 128 registers) on configs[1]: 22.5 vs 25.5 us per fused launch
 // -- the fixed cost of a block (tile load, conversion, segment heads, loss ticket) is spread over more rows, 224 rows
@@ -535,7 +539,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 
   // ---- each warp: its own rows (the centre rows of its two segments; warp 3 also the 2 look-ahead rows) ----
   {
-    const int r0 = min(2 * warp * S, rows), r1 = warp == 3 ? rows : min(2 * (warp + 1) * S, rows);
+    const int r0 = min(2 * warp * S, rows), r1 = warp == PS_WARPS - 1 ? rows : min(2 * (warp + 1) * S, rows);
     const int re = min(r0 + 2, r1);  // the two rows the warp above looks ahead into
     if (Q.use_tma) {
       // try_wait suspends the warp in hardware (up to the hint) instead of spinning: waiting warps must not take
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #endif
     __syncwarp();
     PS_TR(3);
-    if (warp < 3) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
+    if (warp < PS_WARPS - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
   }
   PS_TR(4);
 
@@ -987,8 +991,8 @@ __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, 
     for (int j = 0; j < 4; ++j) {
       const int slot = ps_band_slot(xs + j, W);
       if (((okmask >> j) & 1) && slot >= 0) {
-        s_gband[(slot * 2 + 0) * PS_CAP + (t - 2)] = G[j][0];
-        s_gband[(slot * 2 + 1) * PS_CAP + (t - 2)] = G[j][1];
+        s_gband[t * PS_PITCH + slot * 2 + 0] = G[j][0];
+        s_gband[t * PS_PITCH + slot * 2 + 1] = G[j][1];
       }
     }
   }
@@ -1022,8 +1026,7 @@ __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, 
   }
 }
 
-constexpr size_t PS_DUAL_SMEM_FLOATS =
-    (size_t)5 * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * 2 * 64 + 6 * (size_t)2 * PS_CAP + 2 * 6 * 10;
+constexpr size_t PS_DUAL_SMEM_FLOATS = (size_t)5 * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * 2 * 64 + 2 * 6 * 10;
 
 __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     pairwise_dual_kernel(const __grid_constant__ PsParams Q, const __grid_constant__ PsDual D,
@@ -1033,8 +1036,10 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   float* s_img = ps_smem;                                // [3][PS_ROWS][PS_PITCH]: raw, then scaled for sigma_cut
   float* s_p = s_img + 3 * PS_PLANE;                     // [2][PS_ROWS][PS_PITCH]: logits, then p0 in plane 0
   float* s_head = s_p + C * PS_PLANE;                    // [7][2][2][64]: G (cut, boundary) of the segment heads
-  float* s_gband = s_head + (PS_SEGS - 1) * 2 * 2 * 64;  // [6][2][PS_CAP]: G of the band-column pixels
-  float* s_wx = s_gband + 6 * 2 * PS_CAP;                // [2][6][2][5]: column weights, cut then boundary
+  // G of the band-column pixels, 12 floats at the start of each tile row of the SECOND logit plane: that plane is dead
+  // once a row is converted (p0 lives in plane 0), and a row's entries are written by the warp that converted it
+  float* s_gband = s_p + PS_PLANE;                       // [row t][6 slots][cut, boundary]
+  float* s_wx = s_head + (PS_SEGS - 1) * 2 * 2 * 64;     // [2][6][2][5]: column weights, cut then boundary
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ float s_red[2][PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
@@ -1053,6 +1058,15 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   const int xe = min(K.x0 + PS_TW, W);
   K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
   const int rows = K.nc + 2;
+  PS_TR(0);
+#ifdef WSDL_PS_TRACE
+  if (lane == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned c_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (c_ < 4096) ps_trace_buf[(c_ * 4 + warp) * 16 + 15] = smid;
+  }
+#endif
 
   if (Q.use_tma && tid == 0) {
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
@@ -1094,7 +1108,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   __syncthreads();  // s_bar is initialised
 
   {
-    const int r0 = min(2 * warp * S, rows), r1 = warp == 3 ? rows : min(2 * (warp + 1) * S, rows);
+    const int r0 = min(2 * warp * S, rows), r1 = warp == PS_WARPS - 1 ? rows : min(2 * (warp + 1) * S, rows);
     const int re = min(r0 + 2, r1);
     if (Q.use_tma) {
       asm volatile(
@@ -1106,12 +1120,33 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       ps_rows_load_slow<C>(Q, K, s_img, s_p, r0, r1, lane);
       __syncwarp();
     }
+    PS_TR(1);
+    if (Q.use_tma && tid == 0) {  // as in pairwise_sym_kernel: pull the tile that takes over an SM slot a wave later into L2
+      const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      const unsigned nxt = cta + (unsigned)WSDL_NUM_SMS * WSDL_PS_CTAS;
+      if (nxt < gridDim.x * gridDim.y * gridDim.z) {
+        const unsigned rb = nxt % gridDim.x, rest = nxt / gridDim.x;
+        const unsigned tx = rest % gridDim.y, nb_img = rest / gridDim.y;
+        const int ys2 = (int)rb * (PS_SEGS * S - 2);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const CUtensorMap* tm = c < 3 ? &tm_img : &tm_val;
+          const int pl = c < 3 ? (int)nb_img * 3 + c : (int)nb_img * C + (c - 3);
+          asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm),
+                       "r"((int)tx * PS_TW - 4), "r"(ys2 - 2), "r"(pl)
+                       : "memory");
+        }
+      }
+    }
     ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, r0, re, lane);
     if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");
+    PS_TR(2);
     ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, re, r1, lane);
     __syncwarp();
-    if (warp < 3) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
+    PS_TR(3);
+    if (warp < PS_WARPS - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
   }
+  PS_TR(4);
 
   // ---- march ----
   const int t0 = seg * S, t1 = min(t0 + S, K.nc);
@@ -1169,6 +1204,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
                 make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
         }
       }
+      if (s < 4) PS_TR(5 + s);
 #if WSDL_PS_PACKED
 #pragma unroll
       for (int w = 0; w < 4; ++w)
@@ -1187,7 +1223,9 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     ps_exchange<2>(Bq, oz, strip);
 #endif
   }
+  PS_TR(9);
   __syncthreads();  // every head row holds its own segment's part
+  PS_TR(10);
   if (seg < PS_SEGS - 1) {
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
@@ -1227,6 +1265,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     }
   }
 
+  PS_TR(11);
   // ---- band columns (and corners) ----
   if (K.xband) {
     __syncthreads();
@@ -1244,7 +1283,8 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       lsum_c = fmaf(p0 - p1, ac[0], lsum_c);  // the losses are linear in G: the corrections' share
       lsum_b = fmaf(p0 - p1, ab[0], lsum_b);
       if (Q.p.grad_values) {
-        const float gc = ac[0] + s_gband[(slot * 2 + 0) * PS_CAP + ty], gb = ab[0] + s_gband[(slot * 2 + 1) * PS_CAP + ty];
+        const float gc = ac[0] + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 0];
+        const float gb = ab[0] + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 1];
         const float o = 2.f * p0 * p1 * fmaf(K.scale2, gc, scale_b * gb);
         float* go = Q.p.grad_values + (size_t)K.b * 2 * plane + (size_t)y * W + x;
         go[0] = o, go[plane] = -o;
@@ -1252,6 +1292,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     }
   }
 
+  PS_TR(12);
   // ---- loss partials (cut, boundary) per CTA; the last CTA of the grid finishes both ----
   const int kpi = Q.nb * Q.n_x;
   const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
@@ -1270,6 +1311,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
     }
   }
+  PS_TR(13);
   if (!finisher) return;
   if (tid == 0) {
     unsigned seen;
