@@ -114,6 +114,9 @@ CASES = [
     (3, 2, 39, 44, 5, 0.05, None, True, True, False),     # several images per CTA range, rows split mid-image
     (1, 2, 256, 256, 5, 0.1, None, True, True, False),    # the reference's own call (refine_pseudo_mask, CutLoss.py:745)
     (1, 2, 300, 520, 5, 0.1, 5.0, False, False, True),    # tall/wide: many row blocks and column tiles, boundary form
+    (1, 2, 38, 60, 5, 0.1, 5.0, False, False, True),      # exactly one 38-row block and one 60-column tile
+    (2, 2, 40, 64, 5, 0.05, None, True, True, False),     # a 2-row last block, a 4-column last tile
+    (1, 1, 77, 60, 5, 0.1, 2.0, True, True, False),       # two full blocks + 1 row
 ]
 
 
@@ -278,7 +281,10 @@ def test_module_under_cuda_graph_capture(W):
 
 
 DUAL_CASES = [(2, 64, 64), (1, 224, 224), (2, 45, 70), (1, 6, 6), (3, 39, 44), (1, 100, 122), (2, 50, 61), (1, 256, 256),
-              (2, 300, 520), (5, 7, 9)]
+              (2, 300, 520), (5, 7, 9),
+              # row blocks of the 5-row-segment geometry (38 owned rows): exactly one block and one column tile, a 2-row
+              # last block, two full blocks + 1 row
+              (1, 38, 60), (2, 40, 64), (1, 77, 60)]
 
 
 @pytest.mark.parametrize("case", range(len(DUAL_CASES)))
