@@ -69,7 +69,7 @@ constexpr int PS_WARPS = PS_SEGS / 2;
 #define WSDL_PS_CTAS 3
 #endif
 #ifndef WSDL_PS_PACKED
-#define WSDL_PS_PACKED 1  // dual kernel: two-lane FP32 instructions (FADD2 / FFMA2) in the march
+#define WSDL_PS_PACKED 1  // two-lane FP32 instructions (FADD2 / FFMA2) in the march of every variant
 #endif
 constexpr int PS_SMAX = WSDL_PS_SMAX;           // rows per segment
 constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 32 centre rows per block: 2 warm-up + 30 owned
@@ -179,6 +179,115 @@ __device__ __forceinline__ void ps_exchange(const float (&X)[8][C], float (&own)
     own[1][c] = X[3][c] + l1;
     own[2][c] = X[4][c] + r0;
     own[3][c] = X[5][c] + r1;
+  }
+}
+
+// ---- packed (f32x2) form of the step: see the dual kernel below for the layout (even / odd column pairs) ----
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+
+template <int CS>
+struct PsWinP {
+  float2 e[3 + CS][4];  // [plane: I0, I1, I2, p...][even pair = columns (2k, 2k+1) of the 8-column window]
+};
+
+template <int CS>
+__device__ __forceinline__ void ps_loadp(PsWinP<CS>& w, const float* s_img, const float* s_p, int off) {
+#pragma unroll
+  for (int c = 0; c < 3 + CS; ++c) {
+    const float* src = (c < 3 ? s_img + c * PS_PLANE : s_p + (c - 3) * PS_PLANE) + off;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    w.e[c][0] = make_float2(a.x, a.y), w.e[c][1] = make_float2(a.z, a.w);
+    w.e[c][2] = make_float2(b.x, b.y), w.e[c][3] = make_float2(b.z, b.w);
+  }
+}
+
+// two pairs with the same offset: k = 2^(ks - |I'(a) - I'(b)|^2);  G(a) += k (p(a) - p(b));  G(b) -= k (p(a) - p(b))
+template <int CS>
+__device__ __forceinline__ void ps_pairp(float2 (&ga)[CS], float2 (&gb)[CS], const float2 (&a)[3 + CS],
+                                         const float2 (&b)[3 + CS], float ks) {
+  const float2 d0 = __fadd2_rn(a[0], f2neg(b[0])), d1 = __fadd2_rn(a[1], f2neg(b[1])), d2 = __fadd2_rn(a[2], f2neg(b[2]));
+  const float2 e = __ffma2_rn(f2neg(d2), d2, __ffma2_rn(f2neg(d1), d1, __ffma2_rn(f2neg(d0), d0, make_float2(ks, ks))));
+  const float2 k = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+#pragma unroll
+  for (int c = 0; c < CS; ++c) {
+    const float2 dp = __fadd2_rn(a[3 + c], f2neg(b[3 + c]));
+    ga[c] = __ffma2_rn(k, dp, ga[c]);
+    gb[c] = __ffma2_rn(f2neg(k), dp, gb[c]);
+  }
+}
+
+// All 12 forward pairs of the columns of row t; X, Y, Z: even-pair accumulators [pair][channel] of rows t, t+1, t+2.
+template <int CS>
+__device__ __forceinline__ void ps_stepp(float2 (&X)[4][CS], float2 (&Y)[4][CS], float2 (&Z)[4][CS], float (&pc)[4][CS],
+                                         const float* s_img, const float* s_p, int off, const PsKs& ks) {
+  PsWinP<CS> c;
+  ps_loadp<CS>(c, s_img, s_p, off);
+#pragma unroll
+  for (int cc = 0; cc < CS; ++cc)
+    pc[0][cc] = c.e[3 + cc][1].x, pc[1][cc] = c.e[3 + cc][1].y, pc[2][cc] = c.e[3 + cc][2].x, pc[3][cc] = c.e[3 + cc][2].y;
+  float2 co[3][3 + CS], ce[4][3 + CS];  // odd pairs (2k+1, 2k+2) and even pairs of row t, by plane
+#pragma unroll
+  for (int pl = 0; pl < 3 + CS; ++pl) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) co[k][pl] = make_float2(c.e[pl][k].y, c.e[pl][k + 1].x);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ce[k][pl] = c.e[pl][k];
+  }
+  float2 XO[3][CS];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int cc = 0; cc < CS; ++cc) XO[k][cc] = make_float2(0.f, 0.f);
+  ps_pairp<CS>(X[1], XO[1], ce[1], co[1], ks.a1);  // same row, dx = 1
+  ps_pairp<CS>(X[2], XO[2], ce[2], co[2], ks.a1);
+  ps_pairp<CS>(X[1], X[2], ce[1], ce[2], ks.a4);   // dx = 2
+  ps_pairp<CS>(X[2], X[3], ce[2], ce[3], ks.a4);
+#pragma unroll
+  for (int r = 1; r <= 2; ++r) {
+    float2 (&Yr)[4][CS] = r == 1 ? Y : Z;
+    const float k0 = r == 1 ? ks.b0 : ks.c0, k1 = r == 1 ? ks.b1 : ks.c1, k4 = r == 1 ? ks.b4 : ks.c4;
+    PsWinP<CS> n;
+    ps_loadp<CS>(n, s_img, s_p, off + r * PS_PITCH);
+    float2 ne[4][3 + CS];
+#pragma unroll
+    for (int pl = 0; pl < 3 + CS; ++pl)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ne[k][pl] = n.e[pl][k];
+    ps_pairp<CS>(X[1], Yr[0], ce[1], ne[0], k4);   // dx = -2
+    ps_pairp<CS>(X[2], Yr[1], ce[2], ne[1], k4);
+    ps_pairp<CS>(XO[1], Yr[1], co[1], ne[1], k1);  // dx = -1: centres 3,4 and 5,6 (grouped by partner column)
+    ps_pairp<CS>(XO[2], Yr[2], co[2], ne[2], k1);
+    ps_pairp<CS>(X[1], Yr[1], ce[1], ne[1], k0);   // dx = 0
+    ps_pairp<CS>(X[2], Yr[2], ce[2], ne[2], k0);
+    ps_pairp<CS>(XO[0], Yr[1], co[0], ne[1], k1);  // dx = +1: centres 1,2 and 3,4
+    ps_pairp<CS>(XO[1], Yr[2], co[1], ne[2], k1);
+    ps_pairp<CS>(X[1], Yr[2], ce[1], ne[2], k4);   // dx = +2
+    ps_pairp<CS>(X[2], Yr[3], ce[2], ne[3], k4);
+  }
+#pragma unroll
+  for (int ch = 0; ch < CS; ++ch) {
+    X[0][ch].y += XO[0][ch].x;
+    X[1][ch].x += XO[0][ch].y;
+    X[1][ch].y += XO[1][ch].x;
+    X[2][ch].x += XO[1][ch].y;
+    X[2][ch].y += XO[2][ch].x;
+    X[3][ch].x += XO[2][ch].y;
+  }
+}
+
+template <int CS>
+__device__ __forceinline__ void ps_exchangep(const float2 (&X)[4][CS], float (&own)[4][CS], int strip) {
+#pragma unroll
+  for (int c = 0; c < CS; ++c) {
+    float r0 = __shfl_down_sync(0xffffffffu, X[0][c].x, 1), r1 = __shfl_down_sync(0xffffffffu, X[0][c].y, 1);
+    float l0 = __shfl_up_sync(0xffffffffu, X[3][c].x, 1), l1 = __shfl_up_sync(0xffffffffu, X[3][c].y, 1);
+    if (strip == 15) r0 = 0.f, r1 = 0.f;
+    if (strip == 0) l0 = 0.f, l1 = 0.f;
+    own[0][c] = X[1][c].x + l0;
+    own[1][c] = X[1][c].y + l1;
+    own[2][c] = X[2][c].x + r0;
+    own[3][c] = X[2][c].y + r1;
   }
 }
 
@@ -599,8 +708,16 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 #else
   if (warp * 2 * S < K.nc) {  // warp-uniform: at least one of its two segments has rows
 #endif
+#if WSDL_PS_PACKED
+    float2 A[4][CS], Bq[4][CS], Cq[4][CS];
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c] = Cq[w][c] = make_float2(0.f, 0.f);
+#else
     float A[8][CS], Bq[8][CS], Cq[8][CS];
     ps_zero<CS>(A), ps_zero<CS>(Bq), ps_zero<CS>(Cq);
+#endif
     // one copy of the step in the instruction stream (the body is ~11 KB); the accumulator rows rotate by moves
 #pragma unroll 1
     for (int s = 0; s < S; ++s) {
@@ -617,9 +734,15 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
         ks.a1 = ksu + l0, ks.a4 = 4.f * ksu + l0;
         ks.b0 = ksu + l1, ks.b1 = 2.f * ksu + l1, ks.b4 = 5.f * ksu + l1;
         ks.c0 = 4.f * ksu + l2, ks.c1 = 5.f * ksu + l2, ks.c4 = 8.f * ksu + l2;
+#if WSDL_PS_PACKED
+        ps_stepp<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
+      }
+      ps_exchangep<CS>(A, own, strip);
+#else
         ps_step<CS>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks);
       }
       ps_exchange<CS>(A, own, strip);
+#endif
       if (act) {
         if (s >= 2) {
           ps_emit<C, CS, SOFTMAX>(Q, K, t, strip, okmask, own, pc, s_gband, lsum);
@@ -630,17 +753,29 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
                 make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
         }
       }
+#if WSDL_PS_PACKED
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = make_float2(0.f, 0.f);
+#else
 #pragma unroll
       for (int w = 0; w < 8; ++w)
 #pragma unroll
         for (int c = 0; c < CS; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
+#endif
 #ifdef WSDL_PS_TRACE
       if (s < 4) PS_TR(5 + s);
 #endif
     }
     // rows t0+S, t0+S+1 belong to the next segment: what this one contributed to them is added after the barrier
+#if WSDL_PS_PACKED
+    ps_exchangep<CS>(A, oy, strip);
+    ps_exchangep<CS>(Bq, oz, strip);
+#else
     ps_exchange<CS>(A, oy, strip);
     ps_exchange<CS>(Bq, oz, strip);
+#endif
   }
   PS_TR(9);
   __syncthreads();  // every head row holds its own segment's part
@@ -893,8 +1028,6 @@ __device__ __forceinline__ void ps_load2(PsWin2& w, const float* s_img, const fl
     w.e[c][2] = make_float2(b.x, b.y), w.e[c][3] = make_float2(b.z, b.w);
   }
 }
-
-__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
 
 // two pairs: centres a (4 planes), partners b; ga/gb = (cut, boundary) accumulators of the centres / partners
 __device__ __forceinline__ void ps_pair2(float2 (&ga)[2], float2 (&gb)[2], const float2 (&a)[4], const float2 (&b)[4],
