@@ -31,7 +31,7 @@ L2_MB = 126
 NCU_TRAFFIC_BYTES = 32_230_000  # dram read 32.18 MB + write 0.05 MB per launch (ncu --set full, round 1)
 # warp instructions per launch (smsp__inst_executed.sum, profiles/r01_c_ncu_full_sym.txt): the kernels are bound by
 # instruction issue (FP32 + MUFU), not HBM -- 148 SMs x 4 schedulers x 1 instruction per clock is the second roof
-NCU_WARP_INSTR = {"fused": 15.88e6, "cut": 15.27e6, "boundary": 18.00e6}
+NCU_WARP_INSTR = {"fused": 15.88e6, "cut": 12.13e6, "boundary": 14.11e6}
 # third roof of the fused launch: MUFU (ex2 / rcp) warp instructions per launch from the same capture x 32 lanes against
 # the measured MUFU rate of this B200 (tests/native/pipe_probe.cu: 4.63 T lane-op/s = 16 per clock per SM)
 NCU_MUFU_WARP_INSTR = {"fused": 1.714e6}
