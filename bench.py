@@ -232,7 +232,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam", "pseudomask"])
+    ap.add_argument("--workload", default="pairwise", choices=["pairwise", "layercam", "pseudomask", "trainstep"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--one-stream", action="store_true")
     ap.add_argument("--separate", action="store_true", help="two launches per step (cut, boundary) instead of the fused one")
@@ -274,6 +274,8 @@ def main():
         res = bench_layercam(args, lib, dev, rank, world)
     elif args.workload == "pseudomask":
         res = bench_pseudomask(args, dev, rank, world)
+    elif args.workload == "trainstep":
+        res = bench_trainstep(args, dev, rank, world)
     else:
         res = bench_pairwise(args, lib, dev, rank, world)
     if rank == 0:
@@ -815,6 +817,135 @@ def bench_pseudomask(args, dev, rank, world):
         res["cpu_baseline"] = {"value": v, "unit": "masks/s", "cores": threads, "kind": "port",
                                "sample": f"2 images, one at a time, {t:.2f} s: torchvision ResNet-50 on the host cores + "
                                          "oracle port of LayerCAM.py:52-76, PsuedoMasks.py:59-62, :15-21"}
+    return res
+
+
+def cpu_trainstep_sample(threads):
+    """One image through the same step on the host cores: DeepLabV3-R50 fp32 forward + backward and the oracle port of
+    the reference's loss composition."""
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+
+    sys.path.insert(0, ROOT)
+    from oracle import wsdl_oracle as O
+
+    torch.set_num_threads(threads)
+    net = torchvision.models.segmentation.deeplabv3_resnet50(weights=None, weights_backbone=None, num_classes=2)
+    net.train()
+    for m in net.modules():  # batch of one: batch-norm statistics need more than one value per channel
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+    gen = torch.Generator().manual_seed(0)
+    img = smooth_images(gen, 1, 224, 224, "cpu")
+    labels = (img.mean(1) > img.mean()).long()
+    t0 = time.perf_counter()
+    out = net(img)["out"]
+    p = torch.softmax(out, 1)
+    loss = (F.cross_entropy(out, labels) + 0.1 * O.cut_loss(out, img, sigma_color=0.05, window_size=5)
+            + 0.5 * O.boundary_loss(p[0], img[0], sigma_color=0.1, sigma_space=5, window_size=5))
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return 1.0 / dt, dt
+
+
+def bench_trainstep(args, dev, rank, world):
+    """BASELINE config 4: the weakly-supervised segmentation train step.  DeepLabV3-R50 (2 classes, random init, bf16
+    autocast, cuDNN: out of scope by north_star) on 32x3x224x224 per GPU; pseudo-labels made ONCE (untimed) by the fused
+    LayerCAM -> mask kernel from synthetic hooks; loss = CE + 0.1 cut + 0.5 mean boundary through WeakSupervisionLoss
+    (one fused pairwise launch); Adam; DistributedDataParallel over NCCL when world > 1.  Every step copies its images
+    and labels from pinned host memory and reads the loss back."""
+    import torch
+    import torch.distributed as dist
+    import torchvision
+
+    from weaklysuperviseddl_b200 import WeakSupervisionLoss
+    from weaklysuperviseddl_b200 import functional as WF
+
+    B, S = 32, 224
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True  # fixed shapes: let cuDNN pick its kernels once (warm-up steps)
+    fmt = torch.contiguous_format if os.environ.get("WSDL_TRAIN_NCHW") == "1" else torch.channels_last
+    net = torchvision.models.segmentation.deeplabv3_resnet50(weights=None, weights_backbone=None, num_classes=2)
+    net = net.to(dev).to(memory_format=fmt).train()
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index])
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    crit = WeakSupervisionLoss()
+    g = torch.Generator().manual_seed(11 + rank)
+    h_imgs = smooth_images(g, B, S, S, "cpu").pin_memory()
+    # pseudo-labels: synthetic layer3/layer4 hooks -> fused LayerCAM -> threshold -> keep_largest (the config-3 kernels)
+    gd = torch.Generator(device=dev).manual_seed(5 + rank)
+    acts = [torch.relu(torch.randn(B, c, 14, 14, device=dev, generator=gd)) for c in (1024, 2048)]
+    grads = [torch.randn(B, c, 14, 14, device=dev, generator=gd) * 1e-3 for c in (1024, 2048)]
+    _, mask, _ = WF.layercam_fused(acts, grads, (S, S), thresh=0.3, want_cam=False)
+    h_labels = WF.keep_largest(mask).cpu().pin_memory()  # uint8 {0,1}, the reference's on-disk mask after clamp(max=1)
+    del acts, grads
+    h_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    t_loss = []
+
+    def step(measure=False):
+        imgs = h_imgs.to(dev, non_blocking=True)  # NCHW for the pairwise kernels, channels-last copy for cuDNN
+        labels = h_labels.to(dev, non_blocking=True).long()
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(imgs.contiguous(memory_format=fmt))["out"]
+        if measure:
+            out = out.detach().requires_grad_(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        total, _ = crit(out, imgs, labels)
+        total.backward()
+        if measure:
+            e1.record()
+            torch.cuda.current_stream(dev).synchronize()
+            t_loss.append(e0.elapsed_time(e1))
+            return
+        opt.step()
+        h_loss.copy_(total.detach(), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    def run_steps(n):
+        for _ in range(n):
+            step()
+
+    steps, warmup = min(args.steps, 60), max(3, min(args.warmup, 8))
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    ms, clocks = _timed(run_steps, warmup, steps, dev, world, sampler)
+    for _ in range(6):
+        step(measure=True)
+    loss_ms = sorted(t_loss)[len(t_loss) // 2]
+    value = world * B * steps / (ms * 1e-3)
+    peak, peak_src = peaks()
+    res = {
+        "metric": "train-step images/s (weakly-supervised segmentation step: backbone + CE + cut + boundary + Adam)",
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 backbone / f32 losses",
+        "data": "synthetic",
+        "config": {"workload": "config 4: DeepLabV3-R50 (2 classes, random init) bf16 autocast, 32x3x224x224 per GPU, "
+                               "pseudo-labels from the fused LayerCAM->mask kernels, loss = CE + 0.1 cut + 0.5 mean boundary "
+                               "(WeakSupervisionLoss: one fused pairwise launch), Adam" +
+                               (", DistributedDataParallel over NCCL" if world > 1 else ""),
+                   "l2": "activations of the backbone (> 126 MB) pass through L2 between the loss launches"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h_imgs.numel() * 4 + h_labels.numel(),
+                "d2h_bytes_per_step": 4, "steps": steps, "ms_per_step": ms / steps,
+                "api": "torchvision deeplabv3_resnet50 + weaklysuperviseddl_b200.WeakSupervisionLoss; pinned host buffers"},
+        "stage_share": {"loss_fwd_bwd_ms": loss_ms, "step_ms": ms / steps, "share": loss_ms / (ms / steps),
+                        "note": "CE + fused cut/boundary launch + their autograd glue, CUDA events; the rest is the cuDNN "
+                                "backbone (out of scope by north_star), Adam, and for N > 1 the NCCL gradient all-reduce"},
+        "roofline": {"bound": "hbm", "achieved": BYTES_PER_PIX * 2 * B * S * S / (loss_ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": BYTES_PER_PIX * 2 * B * S * S / (loss_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": "pairwise_dual_kernel inside the loss (one launch per step, not overlapped with another)",
+                     "peak_source": peak_src},
+        "gpu_launches": steps,
+        "clocks": clocks,
+    }
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, t = cpu_trainstep_sample(threads)
+        res["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                               "sample": f"1 image, {t:.2f} s: torchvision DeepLabV3-R50 fp32 fwd+bwd on the host cores + "
+                                         "oracle port of the loss composition"}
     return res
 
 
