@@ -111,6 +111,27 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def _bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the end-to-end
+    leg are first-touched on the GPU's own NUMA node (8 ranks share the host's memory controllers)."""
+    if os.environ.get("WSDL_NO_NUMA_BIND") == "1":
+        return
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # affinity is an optimisation, never a requirement
+        pass
+
+
 _REAL_STDOUT = None
 
 
@@ -265,6 +286,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        _bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: host buffers land next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _native.lib()
