@@ -13,6 +13,8 @@
 //    3 C more for the two scatters.
 //  * Two classes behind a softmax (the reference's binary segmentation) satisfy p1 = 1 - p0, so G1 = -G0: only
 //    channel 0 is accumulated (CS = 1 "stored channel"), and dL/dlogit0 = -dL/dlogit1 = 4 kappa p0 p1 G0.
+//  * Two pairs with the same offset are evaluated per instruction with the two-lane FP32 forms of sm_100a (FADD2 /
+//    FFMA2: the scalar lane rate at half the issue slots); see "packed (f32x2) form" below for the register layout.
 //
 // Work mapping.  A thread owns a strip of 4 columns and marches down S consecutive rows (a "segment"); the
 // contributions it makes to rows t+1, t+2 live in three rotating accumulator rows in registers, the ones it makes
@@ -1014,21 +1016,6 @@ __device__ __forceinline__ void ps_step_dual(float (&X)[8][2], float (&Y)[8][2],
 //   * same row, dx = 1: centres E1, E2 against partners O1, O2.
 // Only row t is ever needed at the odd alignment: its 12 odd input pairs are built once per step, and its odd
 // accumulators XO (columns 1..6) are folded into the even ones before the row is exchanged and emitted.
-struct PsWin2 {
-  float2 e[4][4];  // [plane: I0, I1, I2, p0][even pair]
-};
-
-__device__ __forceinline__ void ps_load2(PsWin2& w, const float* s_img, const float* s_p, int off) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const float* src = (c < 3 ? s_img + c * PS_PLANE : s_p) + off;
-    const float4 a = *reinterpret_cast<const float4*>(src);
-    const float4 b = *reinterpret_cast<const float4*>(src + 4);
-    w.e[c][0] = make_float2(a.x, a.y), w.e[c][1] = make_float2(a.z, a.w);
-    w.e[c][2] = make_float2(b.x, b.y), w.e[c][3] = make_float2(b.z, b.w);
-  }
-}
-
 // two pairs: centres a (4 planes), partners b; ga/gb = (cut, boundary) accumulators of the centres / partners
 __device__ __forceinline__ void ps_pair2(float2 (&ga)[2], float2 (&gb)[2], const float2 (&a)[4], const float2 (&b)[4],
                                          float kc_off, float kb_off, float ratio) {
@@ -1051,8 +1038,8 @@ __device__ __forceinline__ void ps_pair2(float2 (&ga)[2], float2 (&gb)[2], const
 // t+2.  On return X also holds the odd-aligned contributions of this step (columns 1..6).
 __device__ __forceinline__ void ps_step_dual2(float2 (&X)[4][2], float2 (&Y)[4][2], float2 (&Z)[4][2], float (&pc)[4],
                                               const float* s_img, const float* s_p, int off, const PsKsDual& ks, float ratio) {
-  PsWin2 c;
-  ps_load2(c, s_img, s_p, off);
+  PsWinP<1> c;
+  ps_loadp<1>(c, s_img, s_p, off);
   pc[0] = c.e[3][1].x, pc[1] = c.e[3][1].y, pc[2] = c.e[3][2].x, pc[3] = c.e[3][2].y;
   float2 co[3][4];  // odd pairs of row t: [k][plane] = columns (2k+1, 2k+2)
 #pragma unroll
@@ -1073,8 +1060,8 @@ __device__ __forceinline__ void ps_step_dual2(float2 (&X)[4][2], float2 (&Y)[4][
     float2 (&Yr)[4][2] = r == 1 ? Y : Z;
     const float kc = r == 1 ? ks.cb : ks.cc;
     const float k0 = r == 1 ? ks.b0 : ks.c0, k1 = r == 1 ? ks.b1 : ks.c1, k4 = r == 1 ? ks.b4 : ks.c4;
-    PsWin2 n;
-    ps_load2(n, s_img, s_p, off + r * PS_PITCH);
+    PsWinP<1> n;
+    ps_loadp<1>(n, s_img, s_p, off + r * PS_PITCH);
     const float2 n0[4] = PS_PL(n, 0), n1[4] = PS_PL(n, 1), n2[4] = PS_PL(n, 2), n3[4] = PS_PL(n, 3);
     ps_pair2(X[1], Yr[0], ce1, n0, kc, k4, ratio);     // dx = -2
     ps_pair2(X[2], Yr[1], ce2, n1, kc, k4, ratio);
@@ -1095,20 +1082,6 @@ __device__ __forceinline__ void ps_step_dual2(float2 (&X)[4][2], float2 (&Y)[4][
     X[2][ch].x += XO[1][ch].y;
     X[2][ch].y += XO[2][ch].x;
     X[3][ch].x += XO[2][ch].y;
-  }
-}
-
-__device__ __forceinline__ void ps_exchange2(const float2 (&X)[4][2], float (&own)[4][2], int strip) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    float r0 = __shfl_down_sync(0xffffffffu, X[0][c].x, 1), r1 = __shfl_down_sync(0xffffffffu, X[0][c].y, 1);
-    float l0 = __shfl_up_sync(0xffffffffu, X[3][c].x, 1), l1 = __shfl_up_sync(0xffffffffu, X[3][c].y, 1);
-    if (strip == 15) r0 = 0.f, r1 = 0.f;
-    if (strip == 0) l0 = 0.f, l1 = 0.f;
-    own[0][c] = X[1][c].x + l0;
-    own[1][c] = X[1][c].y + l1;
-    own[2][c] = X[2][c].x + r0;
-    own[3][c] = X[2][c].y + r1;
   }
 }
 
@@ -1321,7 +1294,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 #if WSDL_PS_PACKED
         ps_step_dual2(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
       }
-      ps_exchange2(A, own, strip);
+      ps_exchangep<2>(A, own, strip);
 #else
         ps_step_dual(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
       }
@@ -1344,8 +1317,8 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 #pragma unroll
         for (int c = 0; c < 2; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = make_float2(0.f, 0.f);
     }
-    ps_exchange2(A, oy, strip);
-    ps_exchange2(Bq, oz, strip);
+    ps_exchangep<2>(A, oy, strip);
+    ps_exchangep<2>(Bq, oz, strip);
 #else
 #pragma unroll
       for (int w = 0; w < 8; ++w)
