@@ -147,34 +147,70 @@ __global__ void ccl_seams(int* __restrict__ L, int H, int W) {
 }
 
 // local roots hand their count to their global root; then (second launch) true roots compete for the maximum
+// The three dense passes below read the label / count arrays four pixels per thread and iteration (128-bit loads) when
+// the image size allows (VEC: H W % 4 == 0, 4-byte aligned output): with one 4-byte load per thread in flight they ran
+// at ~1.2 TB/s.
+__device__ __forceinline__ void ccl_gather_one(int* Lb, unsigned* ab, int i, unsigned a) {
+  const int r = uf_find(Lb, i);
+  if (r != i) {
+    atomicAdd(ab + r, a);
+    ab[i] = 0u;
+    Lb[i] = r;  // compress: pixels of this local component reach the root in two hops
+  }
+}
+
+template <bool VEC>
 __global__ void ccl_gather(int* __restrict__ L, unsigned* __restrict__ area, int HW) {
   const int b = blockIdx.y;
   int* Lb = L + (size_t)b * HW;
   unsigned* ab = area + (size_t)b * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const unsigned a = ab[i];
-    if (a == 0u) continue;  // not a local root
-    const int r = uf_find(Lb, i);
-    if (r != i) {
-      atomicAdd(ab + r, a);
-      ab[i] = 0u;
-      Lb[i] = r;  // compress: pixels of this local component reach the root in two hops
+  if (VEC) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(ab);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
+      // counts other threads are adding to at this moment belong to true roots, for which nothing is done here
+      const uint4 a = __ldcg(a4 + q);
+      if ((a.x | a.y | a.z | a.w) == 0u) continue;  // no local root among the four
+      if (a.x) ccl_gather_one(Lb, ab, 4 * q + 0, a.x);
+      if (a.y) ccl_gather_one(Lb, ab, 4 * q + 1, a.y);
+      if (a.z) ccl_gather_one(Lb, ab, 4 * q + 2, a.z);
+      if (a.w) ccl_gather_one(Lb, ab, 4 * q + 3, a.w);
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      const unsigned a = ab[i];
+      if (a != 0u) ccl_gather_one(Lb, ab, i, a);  // else: not a local root
     }
   }
 }
 
+__device__ __forceinline__ unsigned long long ccl_key(const int* Lb, int i, unsigned a, unsigned long long local) {
+  if (a != 0u && Lb[i] == i) {  // a true root
+    const unsigned long long key = ((unsigned long long)a << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    return key > local ? key : local;
+  }
+  return local;
+}
+
+template <bool VEC>
 __global__ void ccl_argmax(const int* __restrict__ L, const unsigned* __restrict__ area,
                            unsigned long long* __restrict__ best, int HW) {
   const int b = blockIdx.y;
   const int* Lb = L + (size_t)b * HW;
   const unsigned* ab = area + (size_t)b * HW;
   unsigned long long local = 0ull;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const unsigned a = ab[i];
-    if (a != 0u && Lb[i] == i) {  // a true root
-      const unsigned long long key = ((unsigned long long)a << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-      local = key > local ? key : local;
+  if (VEC) {
+    const uint4* a4 = reinterpret_cast<const uint4*>(ab);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
+      const uint4 a = __ldcg(a4 + q);
+      if ((a.x | a.y | a.z | a.w) == 0u) continue;
+      local = ccl_key(Lb, 4 * q + 0, a.x, local);
+      local = ccl_key(Lb, 4 * q + 1, a.y, local);
+      local = ccl_key(Lb, 4 * q + 2, a.z, local);
+      local = ccl_key(Lb, 4 * q + 3, a.w, local);
     }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+      local = ccl_key(Lb, i, ab[i], local);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -184,6 +220,7 @@ __global__ void ccl_argmax(const int* __restrict__ L, const unsigned* __restrict
   if ((threadIdx.x & 31) == 0 && local) atomicMax(best + b, local);
 }
 
+template <bool VEC>
 __global__ void ccl_select(const int* __restrict__ L, const unsigned long long* __restrict__ best,
                            uint8_t* __restrict__ out, unsigned* __restrict__ best_area, int HW) {
   const int b = blockIdx.y;
@@ -191,9 +228,25 @@ __global__ void ccl_select(const int* __restrict__ L, const unsigned long long* 
   const int root = key ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -2;
   const int* Lb = L + (size_t)b * HW;
   uint8_t* ob = out + (size_t)b * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const int p = Lb[i];
-    ob[i] = (p >= 0 && uf_find(Lb, p) == root) ? 1 : 0;
+  if (VEC) {
+    const int4* L4 = reinterpret_cast<const int4*>(Lb);
+    unsigned* o4 = reinterpret_cast<unsigned*>(ob);
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
+      const int4 p = L4[q];
+      unsigned v = 0u;
+      // neighbours mostly share their local root: one find per distinct value
+      const bool w0 = p.x >= 0 && uf_find(Lb, p.x) == root;
+      const bool w1 = p.y >= 0 && (p.y == p.x ? w0 : uf_find(Lb, p.y) == root);
+      const bool w2 = p.z >= 0 && (p.z == p.y ? w1 : uf_find(Lb, p.z) == root);
+      const bool w3 = p.w >= 0 && (p.w == p.z ? w2 : uf_find(Lb, p.w) == root);
+      v = (w0 ? 1u : 0u) | (w1 ? 0x100u : 0u) | (w2 ? 0x10000u : 0u) | (w3 ? 0x1000000u : 0u);
+      o4[q] = v;
+    }
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+      const int p = Lb[i];
+      ob[i] = (p >= 0 && uf_find(Lb, p) == root) ? 1 : 0;
+    }
   }
   if (best_area && blockIdx.x == 0 && threadIdx.x == 0) best_area[b] = (unsigned)(key >> 32);
 }
@@ -234,9 +287,18 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
     if (sb > cap) sb = cap < 1 ? 1 : cap;
     ccl_seams<<<dim3(sb, B), 256, 0, s>>>(L, H, W);
   }
-  ccl_gather<<<grid, 256, 0, s>>>(L, area, HW);
-  ccl_argmax<<<grid, 256, 0, s>>>(L, area, best, HW);
-  ccl_select<<<grid, 256, 0, s>>>(L, best, out, best_area, HW);
+  if ((HW & 3) == 0 && ((uintptr_t)out & 3) == 0) {  // four pixels per thread and iteration
+    int bv = (HW / 4 + 255) / 256;
+    if (bv > cap) bv = cap < 1 ? 1 : cap;
+    const dim3 gv(bv, B);
+    ccl_gather<true><<<gv, 256, 0, s>>>(L, area, HW);
+    ccl_argmax<true><<<gv, 256, 0, s>>>(L, area, best, HW);
+    ccl_select<true><<<gv, 256, 0, s>>>(L, best, out, best_area, HW);
+  } else {
+    ccl_gather<false><<<grid, 256, 0, s>>>(L, area, HW);
+    ccl_argmax<false><<<grid, 256, 0, s>>>(L, area, best, HW);
+    ccl_select<false><<<grid, 256, 0, s>>>(L, best, out, best_area, HW);
+  }
   WSDL_LAUNCH_CHECK();
   return 0;
 }
