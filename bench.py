@@ -541,8 +541,72 @@ def bench_pairwise(args, lib, dev, rank, world):
                                    "sample": f"8 of 32 images (8x2x224x224), best of 2, {t:.2f} s; oracle port of the "
                                              "reference ATen op sequence incl. autograd backward"}
         if world == 1 and not args.no_also:
-            res["also"] = {"layercam_512": bench_layercam_core(lib, dev, 0, 1, 30, 5)}
+            res["also"] = {"layercam_512": bench_layercam_core(lib, dev, 0, 1, 30, 5),
+                           "eager_torch_cuda": eager_torch_pairwise(dev)}
     return res
+
+
+def eager_torch_pairwise(dev):
+    """SURVEY 8d's second bar: the reference's math as plain eager PyTorch ON THE SAME GPU (the way the reference
+    itself would run there: 24 shifted copies per loss, autograd backward, the boundary loss image by image), timed on a
+    quarter of the configs[1] batch and cross-checked against the fused launch.  Written out here (not imported from
+    oracle/) -- a timing comparator, not a parity check."""
+    import torch
+    import torch.nn.functional as F
+
+    from weaklysuperviseddl_b200 import functional as WF
+
+    def pair_loss(p, img, sigma_color, sigma_space, per_channel_mean):
+        # p (B,C,H,W) probabilities, img (B,3,H,W); AlternatingDirectionCutLoss.py:71-105 / ...BoundaryLoss.py:20-70
+        pad = 2
+        H, W = p.shape[-2:]
+        pp, ip = F.pad(p, (pad,) * 4, mode="reflect"), F.pad(img, (pad,) * 4, mode="reflect")
+        total, K = 0.0, 0
+        for dy in range(-pad, pad + 1):
+            for dx in range(-pad, pad + 1):
+                if dy == 0 and dx == 0:
+                    continue
+                ps = pp[:, :, pad + dy:pad + dy + H, pad + dx:pad + dx + W]
+                isf = ip[:, :, pad + dy:pad + dy + H, pad + dx:pad + dx + W]
+                e = -((img - isf) ** 2).sum(1, keepdim=True) / (2 * sigma_color ** 2)
+                if sigma_space:
+                    e = e - (dx * dx + dy * dy) / (2 * sigma_space ** 2)
+                d2 = (p - ps) ** 2
+                total = total + (torch.exp(e) * (d2.mean(1, keepdim=True) if per_channel_mean else d2.sum(1, keepdim=True))).mean()
+                K += 1
+        return total / K
+
+    Bq = PAIR["B"] // 4
+    g = torch.Generator(device=dev).manual_seed(77)
+    logits = torch.randn(Bq, 2, PAIR["H"], PAIR["W"], device=dev, generator=g)
+    img = smooth_images(g, Bq, PAIR["H"], PAIR["W"], dev)
+
+    def step():
+        x = logits.clone().requires_grad_(True)
+        cut = pair_loss(torch.softmax(x, 1), img, PAIR["sigma_cut"], None, True)
+        probs = torch.softmax(x, 1)
+        bnd = torch.stack([pair_loss(probs[b:b + 1], img[b:b + 1], PAIR["sigma_bnd"], PAIR["sigma_space"], False)
+                           for b in range(Bq)])
+        (cut + bnd.sum()).backward()
+        return cut.detach(), bnd.detach(), x.grad
+
+    cut, bnd, grad = step()
+    lc, lb, gk = WF.pairwise_dual_loss_and_grad(logits, img, PAIR["sigma_cut"], PAIR["sigma_bnd"], PAIR["sigma_space"], 5)
+    agree = {"cut_rel": abs(cut.item() - lc.item()) / abs(cut.item()),
+             "boundary_rel": ((bnd - lb).abs().max() / bnd.abs().max()).item(),
+             "grad_rel": ((grad - gk).abs().max() / grad.abs().max()).item()}
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 3
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    return {"metric": "cut+boundary loss fwd+bwd, eager PyTorch on the same B200", "value": 2 * Bq * PAIR["H"] * PAIR["W"] / (ms * 1e-3) / 1e9,
+            "unit": "Gpix/s", "ms_per_step": ms, "sample": f"{Bq} of {PAIR['B']} images per step, {reps} steps",
+            "agreement_with_fused_launch": agree}
 
 
 def _native_check(rc):
