@@ -437,7 +437,7 @@ def bench_pairwise(args, lib, dev, rank, world):
             cur.wait_stream(sb)
 
     graph = None
-    G_STEPS = max(1, args.graph_steps)
+    G_STEPS = max(1, min(args.graph_steps, args.steps))  # a short run still replays one graph instead of launching directly
     if not args.no_graph:
         some_steps(range(G_STEPS))
         torch.cuda.synchronize(dev)
