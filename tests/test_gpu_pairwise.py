@@ -393,3 +393,44 @@ def test_repeatability_stress(WF):
                 for a, b in zip(ref, cur):
                     assert torch.equal(a, b), (B, H, W_, rep)
     torch.cuda.synchronize()
+
+
+def _eager_pair_loss(p, img, sigma_color, sigma_space, mean_over_classes):
+    """The reference's formula with plain torch ops, any device / dtype: 24 reflect-shifted copies."""
+    import torch.nn.functional as F
+
+    H, W_ = p.shape[-2:]
+    pp, ip = F.pad(p, (2,) * 4, mode="reflect"), F.pad(img, (2,) * 4, mode="reflect")
+    total = 0.0
+    for dy in range(-2, 3):
+        for dx in range(-2, 3):
+            if dy == 0 and dx == 0:
+                continue
+            ps, isf = pp[:, :, 2 + dy:2 + dy + H, 2 + dx:2 + dx + W_], ip[:, :, 2 + dy:2 + dy + H, 2 + dx:2 + dx + W_]
+            e = -((img - isf) ** 2).sum(1, keepdim=True) / (2 * sigma_color ** 2)
+            if sigma_space:
+                e = e - (dx * dx + dy * dy) / (2 * sigma_space ** 2)
+            d2 = (p - ps) ** 2
+            total = total + (torch.exp(e) * (d2.mean(1, keepdim=True) if mean_over_classes else d2.sum(1, keepdim=True))).mean()
+    return total / 24
+
+
+def test_large_image_against_eager_fp64(WF):
+    """1024 x 1024 (the largest size BASELINE names): 27 row blocks x 18 column tiles per image; fused launch and the
+    single-loss launches against an fp64 eager evaluation of the reference's formula on the GPU."""
+    gen = torch.Generator().manual_seed(21)
+    B, H, W_ = 2, 1024, 1024
+    logits = torch.randn(B, 2, H, W_, generator=gen).cuda()
+    img = smooth_images(gen, B, H, W_).cuda()
+    x = logits.double().requires_grad_(True)
+    p = torch.softmax(x, 1)
+    cut = _eager_pair_loss(p, img.double(), 0.05, None, True)
+    bnd = torch.stack([_eager_pair_loss(p[b:b + 1], img[b:b + 1].double(), 0.1, 5.0, False) for b in range(B)])
+    go_b = torch.tensor([0.5, 1.5], dtype=torch.float64, device="cuda")
+    (0.7 * cut + (go_b * bnd).sum()).backward()
+    lc, lb, g = WF.pairwise_dual_loss_and_grad(logits, img, 0.05, 0.1, 5.0, 5, torch.tensor([0.7]).cuda(), go_b.float())
+    assert abs(lc.item() - cut.item()) <= 1e-5 * abs(cut.item())
+    assert (lb.double() - bnd.detach()).abs().max().item() <= 1e-5 * bnd.abs().max().item()
+    assert (g.double() - x.grad).abs().max().item() <= 1e-5 * x.grad.abs().max().item()
+    l1, g1 = WF.pairwise_loss_and_grad(logits, img, 5, 0.05, None, True, True, False)
+    assert abs(l1.item() - cut.item()) <= 1e-5 * abs(cut.item())
