@@ -10,11 +10,13 @@
 //                  row (a pixel starts at the first pixel of its run), runs are joined to the row above with shared-
 //                  memory atomicMin unions (only where the left neighbour has not already made the same join), the
 //                  tile is flattened, pixels are counted per local root, and every pixel writes the GLOBAL index of
-//                  its local root; local roots also write their pixel count.
+//                  its local root; local roots also write their pixel count and enter the tile's short root list.
 //   2. ccl_seams   pixels on the first row / first column of a tile join the neighbours across the seam in global
 //                  memory (paths are two hops long at this point).
 //   3. ccl_gather  every local root adds its count to its global root (one atomic per local component, not per
-//                  pixel), true roots compete for the per-image (area, -root) maximum packed in one u64 atomicMax.
+//                  pixel); ccl_argmax: true roots compete for the per-image (area, -root) maximum packed in one u64
+//                  atomicMax.  Both walk the per-tile root lists (a few entries per tile) instead of scanning a dense
+//                  count array.
 //   4. ccl_select  a pixel belongs to the winner iff the root of its local root is the winning root.
 // Integer work: bit-exact against the oracle by construction.
 #include "common.cuh"
@@ -49,12 +51,20 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 }
 
 // L: -1 background, else global index (within the image) of a pixel of the same component, L[root] == root.
-// area: pixel count of the local component at its local root, 0 elsewhere.
+// area: pixel count of the local component at its local root; the other entries are never written NOR read.
+// roots: per tile, the number of local roots followed by their global indices (8-connectivity: at most 16 x 16 isolated
+// pixels per 32 x 32 tile) -- the later passes walk these short lists instead of scanning `area`.
+constexpr int CCL_MAX_ROOTS = (CT / 2) * (CT / 2);
+constexpr int CCL_LIST = 1 + CCL_MAX_ROOTS;  // ints per tile
+
 __global__ void __launch_bounds__(CT * CT / 4) ccl_tile(const uint8_t* __restrict__ mask, int* __restrict__ L,
-                                                         unsigned* __restrict__ area, unsigned long long* __restrict__ best,
-                                                         int H, int W) {
+                                                         unsigned* __restrict__ area, int* __restrict__ roots,
+                                                         unsigned long long* __restrict__ best, int H, int W) {
   __shared__ int s_lab[CT * CT];
   __shared__ unsigned s_cnt[CT * CT];
+  __shared__ int s_roots[CCL_MAX_ROOTS];
+  __shared__ int s_nroots;
+  if (threadIdx.x == 0) s_nroots = 0;
   const int b = blockIdx.z;
   const int x0 = blockIdx.x * CT, y0 = blockIdx.y * CT;
   const size_t img = (size_t)b * H * W;
@@ -110,8 +120,16 @@ __global__ void __launch_bounds__(CT * CT / 4) ccl_tile(const uint8_t* __restric
     const int i = ly * CT + lane, r = s_lab[i];
     const size_t g = (size_t)y * W + x;
     L[img + g] = r < 0 ? -1 : (y0 + r / CT) * W + (x0 + r % CT);
-    area[img + g] = (r == i) ? s_cnt[i] : 0u;
+    if (r == i) {  // a local root: its count, and an entry in the tile's list
+      area[img + g] = s_cnt[i];
+      s_roots[atomicAdd(&s_nroots, 1)] = (int)g;
+    }
   }
+  __syncthreads();
+  int* list = roots + ((size_t)(b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * CCL_LIST;
+  const int n = s_nroots;
+  if (threadIdx.x == 0) list[0] = n;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) list[1 + k] = s_roots[k];
 }
 
 // joins across the tile seams; one thread per seam pixel (first row and first column of every tile)
@@ -147,79 +165,65 @@ __global__ void ccl_seams(int* __restrict__ L, int H, int W) {
 }
 
 // local roots hand their count to their global root; then (second launch) true roots compete for the maximum
-// The three dense passes below read the label / count arrays four pixels per thread and iteration (128-bit loads) when
-// the image size allows (VEC: H W % 4 == 0, 4-byte aligned output): with one 4-byte load per thread in flight they ran
-// at ~1.2 TB/s.
-__device__ __forceinline__ void ccl_gather_one(int* Lb, unsigned* ab, int i, unsigned a) {
-  const int r = uf_find(Lb, i);
-  if (r != i) {
-    atomicAdd(ab + r, a);
-    ab[i] = 0u;
-    Lb[i] = r;  // compress: pixels of this local component reach the root in two hops
-  }
-}
-
-template <bool VEC>
-__global__ void ccl_gather(int* __restrict__ L, unsigned* __restrict__ area, int HW) {
-  const int b = blockIdx.y;
-  int* Lb = L + (size_t)b * HW;
-  unsigned* ab = area + (size_t)b * HW;
-  if (VEC) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(ab);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
-      // counts other threads are adding to at this moment belong to true roots, for which nothing is done here
-      const uint4 a = __ldcg(a4 + q);
-      if ((a.x | a.y | a.z | a.w) == 0u) continue;  // no local root among the four
-      if (a.x) ccl_gather_one(Lb, ab, 4 * q + 0, a.x);
-      if (a.y) ccl_gather_one(Lb, ab, 4 * q + 1, a.y);
-      if (a.z) ccl_gather_one(Lb, ab, 4 * q + 2, a.z);
-      if (a.w) ccl_gather_one(Lb, ab, 4 * q + 3, a.w);
-    }
-  } else {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-      const unsigned a = ab[i];
-      if (a != 0u) ccl_gather_one(Lb, ab, i, a);  // else: not a local root
+// Local roots hand their count to their global root, then (second launch) true roots compete for the maximum.  Both walk
+// the per-tile root lists: eight threads per tile (a tile of a blobby mask holds a handful of local roots).
+__global__ void ccl_gather(int* __restrict__ L, unsigned* __restrict__ area, const int* __restrict__ roots, int HW,
+                           int tiles_per_image, int n_tiles) {
+  const int sub = threadIdx.x & 7;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n_tiles; t += (gridDim.x * blockDim.x) >> 3) {
+    const int b = t / tiles_per_image;
+    int* Lb = L + (size_t)b * HW;
+    unsigned* ab = area + (size_t)b * HW;
+    const int* list = roots + (size_t)t * CCL_LIST;
+    const int n = list[0];
+    for (int k = sub; k < n; k += 8) {
+      const int i = list[1 + k];
+      const int r = uf_find(Lb, i);
+      if (r != i) {
+        atomicAdd(ab + r, ab[i]);  // only true roots are added to, and i is not one: ab[i] is still its local count
+        Lb[i] = r;                 // compress: pixels of this local component reach the root in two hops
+      }
     }
   }
 }
 
-__device__ __forceinline__ unsigned long long ccl_key(const int* Lb, int i, unsigned a, unsigned long long local) {
-  if (a != 0u && Lb[i] == i) {  // a true root
-    const unsigned long long key = ((unsigned long long)a << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
-    return key > local ? key : local;
-  }
-  return local;
-}
-
-template <bool VEC>
-__global__ void ccl_argmax(const int* __restrict__ L, const unsigned* __restrict__ area,
-                           unsigned long long* __restrict__ best, int HW) {
-  const int b = blockIdx.y;
-  const int* Lb = L + (size_t)b * HW;
-  const unsigned* ab = area + (size_t)b * HW;
-  unsigned long long local = 0ull;
-  if (VEC) {
-    const uint4* a4 = reinterpret_cast<const uint4*>(ab);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
-      const uint4 a = __ldcg(a4 + q);
-      if ((a.x | a.y | a.z | a.w) == 0u) continue;
-      local = ccl_key(Lb, 4 * q + 0, a.x, local);
-      local = ccl_key(Lb, 4 * q + 1, a.y, local);
-      local = ccl_key(Lb, 4 * q + 2, a.z, local);
-      local = ccl_key(Lb, 4 * q + 3, a.w, local);
+__global__ void ccl_argmax(const int* __restrict__ L, const unsigned* __restrict__ area, const int* __restrict__ roots,
+                           unsigned long long* __restrict__ best, int HW, int tiles_per_image, int n_tiles) {
+  const int sub = threadIdx.x & 7;
+  const int stride = (gridDim.x * blockDim.x) >> 3;
+  // warp-uniform trip count (the shuffles below need the whole warp): four tiles per warp and iteration
+  for (int t0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 2; t0 < n_tiles; t0 += stride) {
+    const int t = t0 + ((threadIdx.x & 31) >> 3);
+    unsigned long long local = 0ull;
+    int b = 0;
+    if (t < n_tiles) {
+      b = t / tiles_per_image;
+      const int* Lb = L + (size_t)b * HW;
+      const unsigned* ab = area + (size_t)b * HW;
+      const int* list = roots + (size_t)t * CCL_LIST;
+      const int n = list[0];
+      for (int k = sub; k < n; k += 8) {
+        const int i = list[1 + k];
+        if (Lb[i] == i) {  // a true root
+          const unsigned long long key = ((unsigned long long)ab[i] << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+          local = key > local ? key : local;
+        }
+      }
     }
-  } else {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
-      local = ccl_key(Lb, i, ab[i], local);
-  }
+    // the eight threads of a tile first, then only candidates that beat what the image already holds (the maximum only
+    // grows, so a stale read can only let a useless atomic through): hundreds of components per image would otherwise
+    // serialise on one address
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, local, o);
-    local = other > local ? other : local;
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, local, o);
+      local = other > local ? other : local;
+    }
+    if (sub == 0 && local && local > *reinterpret_cast<const volatile unsigned long long*>(best + b)) atomicMax(best + b, local);
   }
-  if ((threadIdx.x & 31) == 0 && local) atomicMax(best + b, local);
 }
 
+// The select pass reads the labels four pixels per thread and iteration (128-bit loads) when the image size allows
+// (VEC: H W % 4 == 0, 4-byte aligned output).
 template <bool VEC>
 __global__ void ccl_select(const int* __restrict__ L, const unsigned long long* __restrict__ best,
                            uint8_t* __restrict__ out, unsigned* __restrict__ best_area, int HW) {
@@ -258,7 +262,8 @@ using namespace wsdl;
 extern "C" size_t wsdl_keep_largest_workspace_bytes(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
   const size_t n = (size_t)B * H * W;
-  return 256 + n * 8 + ((size_t)B * 8 + 255) / 256 * 256;
+  const size_t tiles = (size_t)B * ((H + CT - 1) / CT) * ((W + CT - 1) / CT);
+  return 256 + n * 8 + ((size_t)B * 8 + 255) / 256 * 256 + tiles * CCL_LIST * sizeof(int);
 }
 
 extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8_t* out, unsigned* best_area,
@@ -273,10 +278,11 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   ws += ((size_t)B * 8 + 255) / 256 * 256;
   int* L = reinterpret_cast<int*>(ws);
   unsigned* area = reinterpret_cast<unsigned*>(ws + n * 4);
+  int* roots = reinterpret_cast<int*>(ws + n * 8);
   cudaStream_t s = (cudaStream_t)stream;
   const int tx = (W + CT - 1) / CT, ty = (H + CT - 1) / CT;
   if (ty > 65535) return WSDL_E_SHAPE;
-  ccl_tile<<<dim3(tx, ty, B), CT * CT / 4, 0, s>>>(mask, L, area, best, H, W);
+  ccl_tile<<<dim3(tx, ty, B), CT * CT / 4, 0, s>>>(mask, L, area, roots, best, H, W);
   int bx = (HW + 255) / 256;
   const int cap = (WSDL_NUM_SMS * 8 + B - 1) / B;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
@@ -287,16 +293,20 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
     if (sb > cap) sb = cap < 1 ? 1 : cap;
     ccl_seams<<<dim3(sb, B), 256, 0, s>>>(L, H, W);
   }
+  {
+    const int tiles_per_image = tx * ty;
+    const long long n_tiles = (long long)tiles_per_image * B;
+    if (n_tiles > 0x7fffffffLL / 8) return WSDL_E_SHAPE;
+    long long gb = (n_tiles * 8 + 255) / 256;
+    if (gb > WSDL_NUM_SMS * 16) gb = WSDL_NUM_SMS * 16;
+    ccl_gather<<<(int)gb, 256, 0, s>>>(L, area, roots, HW, tiles_per_image, (int)n_tiles);
+    ccl_argmax<<<(int)gb, 256, 0, s>>>(L, area, roots, best, HW, tiles_per_image, (int)n_tiles);
+  }
   if ((HW & 3) == 0 && ((uintptr_t)out & 3) == 0) {  // four pixels per thread and iteration
     int bv = (HW / 4 + 255) / 256;
     if (bv > cap) bv = cap < 1 ? 1 : cap;
-    const dim3 gv(bv, B);
-    ccl_gather<true><<<gv, 256, 0, s>>>(L, area, HW);
-    ccl_argmax<true><<<gv, 256, 0, s>>>(L, area, best, HW);
-    ccl_select<true><<<gv, 256, 0, s>>>(L, best, out, best_area, HW);
+    ccl_select<true><<<dim3(bv, B), 256, 0, s>>>(L, best, out, best_area, HW);
   } else {
-    ccl_gather<false><<<grid, 256, 0, s>>>(L, area, HW);
-    ccl_argmax<false><<<grid, 256, 0, s>>>(L, area, best, HW);
     ccl_select<false><<<grid, 256, 0, s>>>(L, best, out, best_area, HW);
   }
   WSDL_LAUNCH_CHECK();
