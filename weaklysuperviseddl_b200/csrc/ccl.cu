@@ -235,8 +235,12 @@ __global__ void ccl_select(const int* __restrict__ L, const unsigned long long* 
   if (VEC) {
     const int4* L4 = reinterpret_cast<const int4*>(Lb);
     unsigned* o4 = reinterpret_cast<unsigned*>(ob);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW / 4; q += gridDim.x * blockDim.x) {
-      const int4 p = L4[q];
+    const int nq = HW / 4, step = gridDim.x * blockDim.x;
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    int4 nxt = q < nq ? L4[q] : make_int4(-1, -1, -1, -1);
+    for (; q < nq; q += step) {
+      const int4 p = nxt;
+      if (q + step < nq) nxt = L4[q + step];  // the next group's labels travel while this group's roots are looked up
       unsigned v = 0u;
       // neighbours mostly share their local root: one find per distinct value
       const bool w0 = p.x >= 0 && uf_find(Lb, p.x) == root;
