@@ -19,6 +19,8 @@
 //                  count array.
 //   4. ccl_select  a pixel belongs to the winner iff the root of its local root is the winning root.
 // Integer work: bit-exact against the oracle by construction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wsdl {
@@ -288,7 +290,10 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   if (ty > 65535) return WSDL_E_SHAPE;
   ccl_tile<<<dim3(tx, ty, B), CT * CT / 4, 0, s>>>(mask, L, area, roots, best, H, W);
   int bx = (HW + 255) / 256;
-  const int cap = (WSDL_NUM_SMS * 8 + B - 1) / B;
+  // CTAs per SM's worth of grid for the seam / select passes: they are latency bound (dependent label look-ups), and 32
+  // waves of 256 threads per SM beat 8 by 17 % at 512^2 (tuning aid: WSDL_CCL_CAP)
+  static const int cap_mult = []() { const char* e = getenv("WSDL_CCL_CAP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
+  const int cap = (WSDL_NUM_SMS * cap_mult + B - 1) / B;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, B);
   const int seam_px = ((H - 1) / CT) * W + ((W - 1) / CT) * H;
