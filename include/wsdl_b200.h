@@ -11,8 +11,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer on the current device unless the name
  *     ends in _host; tensors are dense NCHW;
- *   - the caller owns every buffer, including workspaces; the library keeps no
- *     state, allocates nothing and never synchronises the host;
+ *   - the caller owns every buffer, including workspaces; the library allocates
+ *     nothing, never synchronises the host, reads no environment variable and keeps
+ *     no state between calls except immutable per-process caches (the resolved
+ *     cuTensorMapEncodeTiled entry point, "kernel attributes set on device d");
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
  *   - return value: 0 ok, <0 argument error (WSDL_E_*), >0 a cudaError_t from
  *     the launch; wsdl_strerror() renders either.  Nothing throws across the ABI.

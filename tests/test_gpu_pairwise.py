@@ -322,49 +322,6 @@ def test_dual_launch_equals_the_two_losses(WF, case):
     assert none is None and torch.equal(lc2, lc) and torch.equal(lb2, lb)
 
 
-def test_persistent_variant_matches_default():
-    """The opt-in persistent warp-specialised kernel (WSDL_PAIRWISE_PIPE=1, csrc/pairwise_pipe.cu) stays in parity:
-    run a few shapes in a child process with the switch and compare with this process's default kernel."""
-    import subprocess
-    import sys
-    import tempfile
-
-    shapes = [(2, 2, 64, 64, True), (1, 2, 224, 224, True), (2, 2, 45, 70, False), (1, 1, 41, 63, False)]
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    with tempfile.TemporaryDirectory() as td:
-        code = f"""
-import sys, torch
-sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
-from helpers import smooth_images
-from weaklysuperviseddl_b200 import functional as WF
-out = {{}}
-for i, (B, C, H, W, sm) in enumerate({shapes!r}):
-    gen = torch.Generator().manual_seed(70 + i)
-    v = torch.randn(B, C, H, W, generator=gen)
-    if not sm: v = torch.softmax(v * 2, 1) if C > 1 else torch.sigmoid(v)
-    img = smooth_images(gen, B, H, W)
-    l, g = WF.pairwise_loss_and_grad(v.cuda(), img.cuda(), 5, 0.1, 5.0 if not sm else None, sm, sm, not sm)
-    out[i] = (l.cpu(), g.cpu())
-torch.save(out, {os.path.join(td, 'pipe.pt')!r})
-"""
-        env = dict(os.environ, WSDL_PAIRWISE_PIPE="1")
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        pipe = torch.load(os.path.join(td, "pipe.pt"))
-    from weaklysuperviseddl_b200 import functional as WF2
-
-    for i, (B, C, H, W_, sm) in enumerate(shapes):
-        gen = torch.Generator().manual_seed(70 + i)
-        v = torch.randn(B, C, H, W_, generator=gen)
-        if not sm:
-            v = torch.softmax(v * 2, 1) if C > 1 else torch.sigmoid(v)
-        img = smooth_images(gen, B, H, W_)
-        l, g = WF2.pairwise_loss_and_grad(v.cuda(), img.cuda(), 5, 0.1, 5.0 if not sm else None, sm, sm, not sm)
-        lp, gp = pipe[i]
-        assert (l.cpu() - lp).abs().max().item() <= 2e-6 * l.abs().max().item(), i
-        assert (g.cpu() - gp).abs().max().item() <= 2e-6 * g.abs().max().item() + 1e-12, i
-
-
 def test_repeatability_stress(WF):
     """Races (named-barrier hand-offs, carries added after the barrier, band pass, loss ticket) would show up as
     run-to-run differences: every variant must reproduce itself bit for bit over repeated launches, also while another

@@ -67,9 +67,14 @@ def generate_pseudo_masks(
     run_id="default",
     content_root=CONTENT_ROOT,
     max_images=MAX_IMAGES,
+    forward_alpha=False,
 ):
     """PsuedoMasks.py:23-79.  Returns (image_save_dir, save_dir); files are `{img_id}.png` as in the reference.
-    The whole loader batch goes through the backbone at once (eval-mode BN keeps samples independent)."""
+    The whole loader batch goes through the backbone at once (eval-mode BN keeps samples independent).
+
+    `alpha` is accepted and IGNORED, exactly as in the reference: its call `layercam_gen.generate(img,
+    class_idx=...)` (PsuedoMasks.py:58) never passes it, so the CAM is always made with the generator's default
+    exponent 1.0.  `forward_alpha=True` is an extension that hands it to the generator."""
     save_dir = os.path.join(content_root, f"pseudo_masks_{run_id}")
     image_save_dir = os.path.join(content_root, f"images_{run_id}")
     for d in (save_dir, image_save_dir):
@@ -89,7 +94,8 @@ def generate_pseudo_masks(
         imgs = imgs[:take].to(device)
         labels = torch.as_tensor(labels)[:take].to(device).long()
 
-        masks, near = layercam_gen.generate_masks(imgs, cam_thresh=cam_thresh, alpha=alpha, class_idx=labels)
+        masks, near = layercam_gen.generate_masks(imgs, cam_thresh=cam_thresh, alpha=alpha if forward_alpha else 1.0,
+                                                  class_idx=labels)
         near_total += near
         if keep_largest_masks:
             masks = WF.keep_largest(masks)

@@ -12,7 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwsdl_b200.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
+STAMP = os.path.join(HERE, "build", "flags.txt")
+
+
+def effective_flags():
+    """Everything that changes the object code: part of the up-to-date check (WSDL_NVCC_EXTRA included)."""
+    return [*ARCH_FLAGS, *NVCC_FLAGS, *os.environ.get("WSDL_NVCC_EXTRA", "").split()]
 
 
 def sources():
@@ -28,6 +34,12 @@ def _deps():
 
 def up_to_date() -> bool:
     if not os.path.exists(LIB):
+        return False
+    try:
+        with open(STAMP) as fh:
+            if fh.read() != " ".join(effective_flags()):
+                return False
+    except OSError:
         return False
     t = os.path.getmtime(LIB)
     return all(os.path.getmtime(d) <= t for d in _deps())
@@ -53,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", *os.environ.get("WSDL_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
+        cmd = [nvcc, *effective_flags(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -66,6 +78,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", LIB + ".tmp", *objs]
     subprocess.check_call(cmd)
     os.replace(LIB + ".tmp", LIB)
+    with open(STAMP, "w") as fh:
+        fh.write(" ".join(effective_flags()))
     return LIB
 
 

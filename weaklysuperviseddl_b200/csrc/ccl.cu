@@ -292,7 +292,7 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   int bx = (HW + 255) / 256;
   // CTAs per SM's worth of grid for the seam / select passes: they are latency bound (dependent label look-ups), and 32
   // waves of 256 threads per SM beat 8 by 17 % at 512^2 (tuning aid: WSDL_CCL_CAP)
-  static const int cap_mult = []() { const char* e = getenv("WSDL_CCL_CAP"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 32; }();
+  static const int cap_mult = WSDL_TUNE_INT("WSDL_CCL_CAP", 32) > 0 ? WSDL_TUNE_INT("WSDL_CCL_CAP", 32) : 32;
   const int cap = (WSDL_NUM_SMS * cap_mult + B - 1) / B;
   if (bx > cap) bx = cap < 1 ? 1 : cap;
   dim3 grid(bx, B);

@@ -9,6 +9,15 @@
 
 #define WSDL_NUM_SMS 148
 
+// Tuning knobs are compiled out of the product library: it reads no environment and keeps no mutable state.
+// A measurement build (-DWSDL_TUNING, scripts/) turns them into environment look-ups.
+#ifdef WSDL_TUNING
+#include <stdlib.h>
+#define WSDL_TUNE_INT(name, dflt) ([]() { const char* e__ = getenv(name); return e__ ? atoi(e__) : (dflt); }())
+#else
+#define WSDL_TUNE_INT(name, dflt) (dflt)
+#endif
+
 #define WSDL_LAUNCH_CHECK()                    \
   do {                                         \
     cudaError_t e__ = cudaGetLastError();      \

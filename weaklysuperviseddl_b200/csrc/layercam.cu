@@ -300,6 +300,7 @@ struct UpParams {
   float* cam_out;
   uint8_t* mask_out;
   unsigned long long* near_count;
+  int vec_ok;  // out_w % 4 == 0, cam_out 16-byte and mask_out 4-byte aligned: one 128-bit / 32-bit store per row
 };
 
 struct Tap {
@@ -340,9 +341,9 @@ __global__ void __launch_bounds__(UP_THREADS) layercam_upsample_fuse(const __gri
     if (rr < rows) s_ytap[l][rr] = make_tap(P.L[l].scale_y, y_begin + rr, P.L[l].h);
   }
   __syncthreads();
-  if (x0 >= P.out_w) return;
-  const int ncol = min(UP_COLS, P.out_w - x0);
-  const bool vec = (ncol == UP_COLS) && ((P.out_w & 3) == 0);  // aligned 4-column group
+  // no early return: lanes past the right edge stay for the warp reduction of `near` (they own no column)
+  const int ncol = max(0, min(UP_COLS, P.out_w - x0));
+  const bool vec = (ncol == UP_COLS) && P.vec_ok;  // aligned 4-column group
 
   Tap xt[NL][UP_COLS];
   const float* base[NL];
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(UP_THREADS) layercam_upsample_fuse(const __gri
       if (v >= P.thresh && v > 0.f) bits |= 1u << (8 * c);  // PsuedoMasks.py:60-62
       if (count_near && c < ncol) near += (fabsf(v - P.thresh) < P.band) ? 1u : 0u;
     }
+    if (ncol == 0) continue;
     const size_t o = out_base + (size_t)rr * P.out_w;
     if (vec) {
       if (P.cam_out) *reinterpret_cast<float4*>(P.cam_out + o) = make_float4(cam[0], cam[1], cam[2], cam[3]);
@@ -657,6 +659,7 @@ extern "C" int wsdl_layercam_fused(const void* const* act, const void* const* gr
   U.cam_out = cam_out;
   U.mask_out = mask_out;
   U.near_count = near_count;
+  U.vec_ok = ((out_w & 3) == 0) && (((uintptr_t)cam_out & 15) == 0) && (((uintptr_t)mask_out & 3) == 0);
   dim3 grid((out_w + UP_THREADS - 1) / UP_THREADS, (out_h + UP_ROWS - 1) / UP_ROWS, B);
   if (grid.y > 65535) return WSDL_E_SHAPE;
   dim3 grid4((out_w + UP_THREADS * UP_COLS - 1) / (UP_THREADS * UP_COLS), grid.y, B);  // 4 columns per thread

@@ -619,8 +619,6 @@ extern "C" size_t wsdl_pairwise_workspace_bytes(int B, int H, int W) {
   size_t floats = (size_t)B * tiles;  // one partial per 32x32 tile (generic / fast kernels)
   const size_t sym = ps_workspace_floats(B, H, W);
   if (sym > floats) floats = sym;
-  const size_t pipe = pp_workspace_floats(B, H, W);
-  if (pipe > floats) floats = pipe;
   return 512 + pw_align(floats * sizeof(float));
 }
 
@@ -669,15 +667,8 @@ static int pairwise_fwd_bwd_impl(const float* values, const float* images, int B
     if (e != cudaSuccess) return (int)e;
   }
   if (pad == 2 && H > 2 * PF_PAD && W > 2 * PF_PAD) {
-    static const int no_sym = []() { const char* e = getenv("WSDL_PAIRWISE_NO_SYM"); return (e && e[0] == '1') ? 1 : 0; }();
+    static const int no_sym = WSDL_TUNE_INT("WSDL_PAIRWISE_NO_SYM", 0);
     if (!no_sym) {  // pair-symmetric kernels: the hot configurations (window 5, C <= 2)
-      // persistent, warp-specialised variant (pairwise_pipe.cu): parity green, but its 8 marching warps per SM
-      // lose to the 16 of the tile-per-CTA kernel on B200 (35 vs 41 Gpix/s); kept selectable for measurements
-      static const int use_pipe = []() { const char* e = getenv("WSDL_PAIRWISE_PIPE"); return (e && e[0] == '1') ? 1 : 0; }();
-      if (use_pipe) {
-        const int rc = pp_launch(P, s);
-        if (rc != 1) return rc;
-      }
       const int rc = ps_launch(P, s);  // one tile per CTA (pairwise_sym.cu)
       if (rc != 1) return rc;
     }

@@ -39,8 +39,4 @@ size_t ps_workspace_floats(int B, int H, int W);
 int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_bnd,
                    float* loss_bnd, float* partial_bnd, cudaStream_t s);
 
-// Persistent warp-specialised version of the same kernel (pairwise_pipe.cu); same return convention.
-int pp_launch(const PwParams& P, cudaStream_t s);
-size_t pp_workspace_floats(int B, int H, int W);
-
 }  // namespace wsdl

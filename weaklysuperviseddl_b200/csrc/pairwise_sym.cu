@@ -21,7 +21,7 @@
 // to the 2 columns either side of its strip go to the neighbouring lanes by warp shuffle when a row completes.
 // 16 strips (a half warp) span the 64 staged columns of a tile (60 owned + 2 halo each side), 8 segments span the
 // block's rows; the first two rows of a segment are completed by what its upper neighbour adds to them, through
-// shared memory after the march.  A CTA is one block: up to 30 rows of one 60-column tile of one image (grid = row blocks x
+// shared memory after the march.  A CTA is one block: up to PS_CAP = 38 rows of one 60-column tile of one image (grid = row blocks x
 // column tiles x images, a few CTAs per SM slot so that the loads of one overlap the march of the others); it
 // pays 2 warm-up rows instead of a halo in y.
 //
@@ -74,7 +74,7 @@ constexpr int PS_WARPS = PS_SEGS / 2;
 #define WSDL_PS_PACKED 1  // two-lane FP32 instructions (FADD2 / FFMA2) in the march of every variant
 #endif
 constexpr int PS_SMAX = WSDL_PS_SMAX;           // rows per segment
-constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 32 centre rows per block: 2 warm-up + 30 owned
+constexpr int PS_CENTERS = PS_SEGS * PS_SMAX;  // 40 centre rows per block: 2 warm-up + 38 owned
 constexpr int PS_ROWS = PS_CENTERS + 2;        // + 2 look-ahead rows
 constexpr int PS_CAP = PS_CENTERS - 2;         // owned rows per block
 constexpr int PS_PLANE = (PS_ROWS * PS_PITCH + 31) / 32 * 32;  // floats; planes start 128-byte aligned (TMA)
@@ -1454,7 +1454,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 // modelled time = (march steps per block + fixed cost of a block, in steps) x blocks an SM works through (a launch
 // below two blocks per SM is latency bound: more, shorter blocks keep winning there).
 static int ps_row_blocks(int B, int H, int W) {
-  static const int forced = []() { const char* e = getenv("WSDL_PS_NB"); return e ? atoi(e) : 0; }();  // tuning aid
+  static const int forced = WSDL_TUNE_INT("WSDL_PS_NB", 0);
   const int n_x = (W + PS_TW - 1) / PS_TW;
   const int nb_min = (H + PS_CAP - 1) / PS_CAP;
   if (forced >= nb_min) return forced;
@@ -1523,7 +1523,7 @@ static int ps_launch_t(PsParams& Q, const CUtensorMap& tm_img, const CUtensorMap
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  static const size_t pad = []() { const char* e = getenv("WSDL_PS_SMEM_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : 0; }();
+  static const size_t pad = (size_t)WSDL_TUNE_INT("WSDL_PS_SMEM_PAD_KB", 0) * 1024;
   if (pad) cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
   pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem + pad, s>>>(Q, tm_img, tm_val);
   WSDL_LAUNCH_CHECK();
@@ -1546,7 +1546,7 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   Q.l32 = log2f(1.5f), Q.l1g = log2f(1.f + Q.g4);
   {  // a sixteenth of a wave of tiles at ~6 TB/s (a longer hold-back helps a lone launch by 2-3 % and costs launches
      // that overlap on the device 4 %); only when the launch fills the machine
-    static const int stagger_env = []() { const char* e = getenv("WSDL_PS_STAGGER_NS"); return e ? atoi(e) : -1; }();
+    static const int stagger_env = WSDL_TUNE_INT("WSDL_PS_STAGGER_NS", -1);
     const double tile_bytes = (double)(3 + P.C) * (PS_SEGS * Q.S + 2) * PS_PITCH * 4.0;
     const long long ctas = (long long)Q.nb * Q.n_x * P.B;
     Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 24000.0) : 0u;
@@ -1554,7 +1554,7 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   }
   CUtensorMap tm_img, tm_val;
   memset(&tm_img, 0, sizeof(tm_img)), memset(&tm_val, 0, sizeof(tm_val));
-  static const int no_tma = []() { const char* e = getenv("WSDL_PAIRWISE_NO_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int no_tma = WSDL_TUNE_INT("WSDL_PAIRWISE_NO_TMA", 0);
   Q.use_tma = !no_tma && ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0) &&
               ps_encode(&tm_img, P.images, P.W, P.H, 3LL * P.B, PS_SEGS * Q.S + 2) &&
               ps_encode(&tm_val, P.values, P.W, P.H, (long long)P.C * P.B, PS_SEGS * Q.S + 2);
@@ -1581,7 +1581,7 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   Q.g1 = 1.f, Q.g4 = 1.f;
   Q.l32 = log2f(1.5f), Q.l1g = 1.f;
   {
-    static const int stagger_env = []() { const char* e = getenv("WSDL_PS_STAGGER_NS"); return e ? atoi(e) : -1; }();
+    static const int stagger_env = WSDL_TUNE_INT("WSDL_PS_STAGGER_NS", -1);
     const double tile_bytes = 5.0 * (PS_SEGS * Q.S + 2) * PS_PITCH * 4.0;
     const long long ctas = (long long)Q.nb * Q.n_x * P.B;
     Q.stagger_ns = ctas >= 2LL * WSDL_NUM_SMS ? (unsigned)(tile_bytes * WSDL_NUM_SMS / 24000.0) : 0u;
@@ -1599,7 +1599,7 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   D.l1g_b = log2f(1.f + D.g4b);
   CUtensorMap tm_img, tm_val;
   memset(&tm_img, 0, sizeof(tm_img)), memset(&tm_val, 0, sizeof(tm_val));
-  static const int no_tma = []() { const char* e = getenv("WSDL_PAIRWISE_NO_TMA"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int no_tma = WSDL_TUNE_INT("WSDL_PAIRWISE_NO_TMA", 0);
   Q.use_tma = !no_tma && ((P.W & 3) == 0) && (((uintptr_t)P.values & 15) == 0) && (((uintptr_t)P.images & 15) == 0) &&
               ps_encode(&tm_img, P.images, P.W, P.H, 3LL * P.B, PS_SEGS * Q.S + 2) &&
               ps_encode(&tm_val, P.values, P.W, P.H, 2LL * P.B, PS_SEGS * Q.S + 2);

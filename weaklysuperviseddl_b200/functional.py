@@ -118,6 +118,17 @@ def threshold_mask(cam: torch.Tensor, thresh: float, near_band: float = NEAR_BAN
     return mask, near
 
 
+def _upstream(t: Optional[torch.Tensor], n: int, dev, name: str) -> Optional[int]:
+    """Device pointer of an upstream-gradient vector handed to the C ABI (n floats), validated first."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != dev:
+        raise _native.WsdlError(f"wsdl_b200: `{name}` must be a CUDA tensor on {dev}")
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n:
+        raise ValueError(f"`{name}` must be a contiguous float32 tensor of {n} element(s), got {t.dtype} {tuple(t.shape)}")
+    return t.data_ptr()
+
+
 _PAIR_WS = {}  # (device index, stream, bytes) -> prepared workspace (wsdl_pairwise_workspace_init, then self-cleaning)
 
 
@@ -155,7 +166,7 @@ def _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softma
             values.data_ptr(), images.data_ptr(), B, C, H, W, int(window), float(sigma_color),
             float(sigma_space) if sigma_space is not None else 0.0,
             int(inner_softmax), int(divide_by_c), int(per_image),
-            grad_out.data_ptr() if grad_out is not None else None,
+            _upstream(grad_out, B if per_image else 1, dev, "grad_out"),
             loss.data_ptr(), grad.data_ptr() if grad is not None else None,
             workspace.data_ptr(), nbytes, _stream_ptr(dev),
         )
@@ -265,22 +276,28 @@ def keep_largest(mask: torch.Tensor, return_area: bool = False):
 _ELEM_CODE = {torch.uint8: 0, torch.bool: 0, torch.int32: 1, torch.int64: 2, torch.float32: 3}
 
 
-def iou_acc_counts(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
-    """ExtraUtilities.py:4-21 as one pass: (B,...) or (...) masks of one dtype -> (B,3) int64 device tensor
-    {intersection, union, equal} per image.  No host synchronisation."""
+def iou_acc_counts(pred: torch.Tensor, true: torch.Tensor, batched: Optional[bool] = None) -> torch.Tensor:
+    """ExtraUtilities.py:4-21 as one pass: masks -> (B,3) int64 device tensor {intersection, union, equal} per image.
+    No host synchronisation.  Shapes broadcast exactly as the reference's `&`, `|` and `==` do (its own loader hands
+    a (1,H,W) truth to an (H,W) prediction, LayerCAM.py:96-112); `batched` says whether dim 0 of the broadcast shape
+    indexes images (default: only when both inputs are at least 3-D and agree in dim 0)."""
     _require_cuda(pred, "pred_mask")
     _require_cuda(true, "true_mask")
+    if batched is None:
+        batched = pred.dim() >= 3 and true.dim() >= 3 and pred.shape[0] == true.shape[0]
     if pred.shape != true.shape:
-        raise ValueError(f"mask shapes differ: {tuple(pred.shape)} vs {tuple(true.shape)}")
+        pred, true = torch.broadcast_tensors(pred, true)  # raises like the reference when the shapes cannot broadcast
     if pred.dtype != true.dtype:
         common = torch.promote_types(pred.dtype, true.dtype)
         pred, true = pred.to(common), true.to(common)
     if pred.dtype not in _ELEM_CODE:
         pred, true = pred.float(), true.float()
     p, t = pred.contiguous(), true.contiguous()
-    B = p.shape[0] if p.dim() >= 3 else 1
+    B = p.shape[0] if (batched and p.dim() >= 2) else 1
     n = p.numel() // B
     counts = torch.zeros((B, 3), dtype=torch.int64, device=p.device)
+    if p.numel() == 0:
+        return counts
     with torch.cuda.device(p.device):
         rc = _native.lib().wsdl_iou_acc_counts(p.data_ptr(), t.data_ptr(), B, n, _ELEM_CODE[p.dtype], counts.data_ptr(),
                                                _stream_ptr(p.device))
@@ -326,8 +343,7 @@ def pairwise_dual_loss_and_grad(logits, images, sigma_cut=0.05, sigma_boundary=0
         rc = lib.wsdl_pairwise_dual_fwd_bwd(
             v.data_ptr(), im.data_ptr(), B, H, W, int(window_size), float(sigma_cut), float(sigma_boundary),
             float(sigma_space) if sigma_space else 0.0,
-            grad_out_cut.data_ptr() if grad_out_cut is not None else None,
-            grad_out_bnd.data_ptr() if grad_out_bnd is not None else None,
+            _upstream(grad_out_cut, 1, dev, "grad_out_cut"), _upstream(grad_out_bnd, B, dev, "grad_out_bnd"),
             loss_cut.data_ptr(), loss_bnd.data_ptr(), grad.data_ptr() if grad is not None else None,
             workspace.data_ptr(), nbytes, 1, _stream_ptr(dev))
     _native.check(rc, "wsdl_pairwise_dual_fwd_bwd")
