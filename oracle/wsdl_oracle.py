@@ -3,7 +3,8 @@
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
 `--impl reference` legs may import this file, and only as the *checker* or the
 *timed CPU baseline*; the product package (`weaklysuperviseddl_b200/`) never
-does.  Parity status: PINNED -- `tests/test_oracle.py` runs every
+does.  Parity status: PINNED (except `keep_largest`: UNPINNED, skimage cannot be had -- see
+`label_two_pass`) -- `tests/test_oracle.py` runs every
 function below against the real reference functions loaded from /root/reference
 (in the authoring container) and against the fixtures in `tests/golden/` that
 `oracle/make_golden.py` produced from the real reference (those travel to the
@@ -141,7 +142,9 @@ def keep_largest(mask: np.ndarray) -> np.ndarray:
     full (8-) connectivity, background 0, labels in raster order of first pixel;
     `max(regions, key=area)` returns the FIRST maximum, i.e. the lowest label.
     skimage is not installed here, so this restatement is pinned only against
-    scipy.ndimage and cv2 (which agree) -- tie-break order is unpinned."""
+    scipy.ndimage, cv2 and the independent two-pass restatement of skimage's own
+    algorithm below (`keep_largest_two_pass`), which all agree -- parity with
+    skimage proper is UNPINNED (see `label_two_pass`)."""
     from scipy import ndimage
 
     labeled, n = ndimage.label(mask != 0, structure=np.ones((3, 3), dtype=np.int32))
@@ -149,6 +152,83 @@ def keep_largest(mask: np.ndarray) -> np.ndarray:
         return mask
     areas = np.bincount(labeled.ravel(), minlength=n + 1)[1:]
     best = int(np.argmax(areas)) + 1  # argmax returns the first maximum
+    return (labeled == best).astype(np.uint8)
+
+
+def label_two_pass(mask: np.ndarray) -> np.ndarray:
+    """SECOND, independent restatement of `skimage.measure.label(mask)` with its defaults (connectivity = ndim
+    -> 8-connectivity in 2-D, background 0), written from skimage's published algorithm (measure/_ccomp.pyx:
+    `_label` -- a raster scan that joins every foreground pixel with its already-visited neighbours W, NW, N, NE
+    in a union-find forest whose `join_trees` always makes the SMALLER raster index the root -- followed by
+    `resolve_labels`, a second raster scan that hands out consecutive labels 1, 2, ... the moment it meets a
+    root).  Because a component's root is its minimum raster index, labels come out in raster order of each
+    component's first pixel.  Pure numpy/Python, no scipy: it shares no code with `keep_largest` above.
+
+    skimage itself is absent from the reference tree, from this image and from the offline wheelhouse
+    (`pip download scikit-image --no-index --find-links /opt/wheelhouse` finds no distribution), and the reference
+    pins no version (no requirements file): parity of keep_largest is therefore UNPINNED against skimage proper
+    and rests on two independent restatements that must agree (tests/test_oracle.py)."""
+    m = np.asarray(mask) != 0
+    H, W = m.shape
+    parent = np.arange(H * W, dtype=np.int64)
+
+    def find(i):
+        r = i
+        while parent[r] != r:
+            r = parent[r]
+        while parent[i] != r:  # path compression
+            parent[i], i = r, parent[i]
+        return r
+
+    def join(a, b):
+        ra, rb = find(a), find(b)
+        if ra < rb:
+            parent[rb] = ra
+        elif rb < ra:
+            parent[ra] = rb
+
+    for y in range(H):
+        for x in range(W):
+            if not m[y, x]:
+                continue
+            i = y * W + x
+            if x > 0 and m[y, x - 1]:
+                join(i, i - 1)
+            if y > 0:
+                if x > 0 and m[y - 1, x - 1]:
+                    join(i, i - W - 1)
+                if m[y - 1, x]:
+                    join(i, i - W)
+                if x + 1 < W and m[y - 1, x + 1]:
+                    join(i, i - W + 1)
+    out = np.zeros(H * W, dtype=np.int64)
+    nxt = 0
+    flat = m.ravel()
+    for i in range(H * W):
+        if not flat[i]:
+            continue
+        r = find(i)
+        if r == i:
+            nxt += 1
+            out[i] = nxt
+        else:
+            out[i] = out[r]  # r < i: already resolved
+    return out.reshape(H, W)
+
+
+def keep_largest_two_pass(mask: np.ndarray) -> np.ndarray:
+    """PsuedoMasks.py:15-21 on top of `label_two_pass`: `regionprops` lists regions in label order and
+    `max(regions, key=lambda r: r.area)` keeps the FIRST region of maximal area (Python's max); an empty
+    labelling returns the input object itself (:18-19)."""
+    labeled = label_two_pass(mask)
+    n = int(labeled.max())
+    if n == 0:
+        return mask
+    best, best_area = 0, -1
+    for lab in range(1, n + 1):  # label order, strict > keeps the first maximum
+        area = int((labeled == lab).sum())
+        if area > best_area:
+            best, best_area = lab, area
     return (labeled == best).astype(np.uint8)
 
 

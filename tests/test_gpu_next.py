@@ -34,11 +34,12 @@ def test_refine_batched_matches_per_image_loop(golden_dir):
             one = refine_pseudo_mask(seg, images[b], masks[b].cuda(), lambda_boundary=lam, threshold=thr, lr=lr,
                                      num_steps=steps)
             assert (out[b] != one).float().mean().item() <= 0.002, (steps, b)
-        # against the fp32 oracle port of the whole loop, on the soft state (not only the thresholded mask)
+        # against the fp32 oracle port of the whole loop started from the same S, on the soft state (the fp64-arbitrated
+        # bound lives in test_gpu_configs.py::test_refine_soft_state_vs_fp64)
         with torch.no_grad():
-            S = torch.softmax(seg(images[:1].cuda())["out"], dim=1).cpu()
-        _, Xo, Xfo = O.refine_from_probs(S, images[0], masks[0], lam, thr, lr, steps, return_state=True)
-        assert (Xf[0].cpu() - Xfo[0]).abs().max().item() <= 2e-3
+            S = torch.softmax(seg(images.cuda())["out"], dim=1).cpu()
+        _, Xo, Xfo = O.refine_from_probs(S[:1], images[0], masks[0], lam, thr, lr, steps, return_state=True)
+        assert (Xf[0].cpu() - Xfo[0]).abs().max().item() <= 1e-5
 
 
 def test_labels_from_masks_equals_png_round_trip():

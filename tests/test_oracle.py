@@ -162,6 +162,38 @@ def test_keep_largest_tie_takes_first_in_raster_order():
     assert out[1, 5:7].sum() == 2 and out[3].sum() == 0
 
 
+def test_keep_largest_two_independent_restatements_agree():
+    """skimage cannot be had (absent here and from the wheelhouse), so keep_largest parity is UNPINNED against it;
+    what we can pin: the scipy-based restatement and the from-scratch two-pass restatement of skimage's own
+    union-find labelling (min raster index = root, labels in raster order of the first pixel) agree on labels
+    AND on the kept component, ties included."""
+    from scipy import ndimage
+
+    rng = np.random.default_rng(17)
+    cases = [(rng.random((41, 57)) < d).astype(np.uint8) for d in (0.2, 0.45, 0.55, 0.62, 0.9)]
+    tie = np.zeros((9, 12), np.uint8)
+    tie[6, 0:3] = 1   # three components of area 3; the one whose first pixel comes first in raster order wins
+    tie[2, 8:11] = 1
+    tie[4:7, 5] = 1
+    cases.append(tie)
+    snake = np.zeros((12, 12), np.uint8)  # U shape: the two arms get provisional labels that must be merged late
+    snake[0:10, 1] = 1
+    snake[0:10, 9] = 1
+    snake[10, 1:10] = 1
+    cases.append(snake)
+    checker = (np.indices((10, 10)).sum(0) % 2).astype(np.uint8)  # 8-connectivity joins the whole checkerboard
+    cases.append(checker)
+    for m in cases:
+        lab_a = O.label_two_pass(m)
+        lab_b, _ = ndimage.label(m != 0, structure=np.ones((3, 3), dtype=np.int32))
+        assert np.array_equal(lab_a, lab_b)  # same components AND same label numbering (raster order)
+        assert np.array_equal(O.keep_largest_two_pass(m), O.keep_largest(m))
+    assert O.keep_largest_two_pass(tie)[2, 8:11].sum() == 3
+    z = np.zeros((4, 4), np.uint8)
+    assert O.keep_largest_two_pass(z) is z
+    assert O.label_two_pass(checker).max() == 1
+
+
 def test_png_label_roundtrip():
     m = (np.random.default_rng(0).random((224, 224)) > 0.5).astype(np.uint8)
     png = O.mask_to_png_array(m)

@@ -7,7 +7,6 @@ import torch
 import torch.nn.functional as F
 
 from . import functional as WF
-from .ExtraUtilities import compute_iou_and_acc
 
 
 class LayerCAMGenerator:
@@ -74,36 +73,37 @@ class LayerCAMGenerator:
         return (mask, near, cam) if return_cam else (mask, near)
 
 
+MAX_EVAL_ITEMS = 11  # the reference stops after the item with index 10 (LayerCAM.py:119-120)
+
+
+def _cam_truth_counts(layercam_gen, img, label, true_mask, alpha, cam_thresh):
+    """One test item (LayerCAM.py:96-115) without a host synchronisation: fused CAM -> threshold on the device,
+    nearest resize when the truth has another shape (it always has with the reference's loader: (1,H,W) against
+    (H,W), :109), and the three counters of compute_iou_and_acc as a (1,3) device tensor."""
+    true_fg = (true_mask.cuda() == 1).long()
+    cls = torch.tensor([label.item() if isinstance(label, torch.Tensor) else label], device=true_fg.device)
+    mask, _ = layercam_gen.generate_masks(img.cuda(), cam_thresh=cam_thresh, alpha=alpha, class_idx=cls)
+    pred = mask.squeeze(0).long()
+    if pred.shape != true_fg.shape:
+        pred = F.interpolate(pred[None, None].float(), size=true_fg.shape[-2:], mode='nearest').squeeze().long()
+    return WF.iou_acc_counts(pred, true_fg, batched=False), true_fg.numel()
+
+
 def evaluate_layercam_on_test_set(layercam_gen, test_loader, alpha=1.0, cam_thresh=0.3):
-    """reference LayerCAM.py:84-130 (same loop, same 11-image cut-off, same return dict)."""
-    ious_fg, accs_fg = [], []
-
-    for i, (img, (label, true_mask)) in enumerate(test_loader):
-        img = img[0].cuda()
-        true_mask = true_mask[0].cuda()
-
-        true_mask = (true_mask == 1).long()
-        label = label[0].item() if isinstance(label[0], torch.Tensor) else label[0]
-        class_tensor = torch.tensor([label]).to(img.device)
-
-        mask, _ = layercam_gen.generate_masks(img, cam_thresh=cam_thresh, alpha=alpha, class_idx=class_tensor)
-        pred_fg_mask = mask.squeeze(0).long()
-
-        if pred_fg_mask.shape != true_mask.shape:
-            pred_fg_mask = F.interpolate(pred_fg_mask.unsqueeze(0).unsqueeze(0).float(), size=true_mask.shape[-2:],
-                                         mode='nearest').squeeze().long()
-
-        iou_fg, acc_fg = compute_iou_and_acc(pred_fg_mask, true_mask)
-        ious_fg.append(iou_fg)
-        accs_fg.append(acc_fg)
-
-        if i >= 10:
+    """reference LayerCAM.py:84-130: mean foreground IoU / pixel accuracy of the thresholded CAM over the first 11
+    items of a batch-size-1 test loader yielding (img, (label, true_mask)); same printout, same return dict.  The
+    per-item `.item()` reads of the reference (three per image) are one device->host copy at the end."""
+    counts, totals = [], []
+    for img, (label, true_mask) in test_loader:
+        c, n = _cam_truth_counts(layercam_gen, img[0], label[0], true_mask[0], alpha, cam_thresh)
+        counts.append(c)
+        totals.append(n)
+        if len(counts) >= MAX_EVAL_ITEMS:
             break
-
+    host = torch.cat(counts).tolist()
+    ious_fg = [inter / (union + 1e-8) for inter, union, _ in host]      # ExtraUtilities.py:17-20
+    accs_fg = [correct / n for (_, _, correct), n in zip(host, totals)]
+    result = {"layercam_fg_iou": sum(ious_fg) / len(ious_fg), "layercam_fg_acc": sum(accs_fg) / len(accs_fg)}
     print("\n Evaluation of CAMs on test set:")
-    print(f" - LayerCam FG: Avg IoU: {sum(ious_fg)/len(ious_fg):.4f} | Acc: {sum(accs_fg)/len(accs_fg):.4f}")
-
-    return {
-        "layercam_fg_iou": sum(ious_fg) / len(ious_fg),
-        "layercam_fg_acc": sum(accs_fg) / len(accs_fg)
-    }
+    print(f" - LayerCam FG: Avg IoU: {result['layercam_fg_iou']:.4f} | Acc: {result['layercam_fg_acc']:.4f}")
+    return result
