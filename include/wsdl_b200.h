@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WSDL_VERSION 100 /* major*10000 + minor*100 + patch */
+#define WSDL_VERSION 200 /* major*10000 + minor*100 + patch */
 
 #define WSDL_E_NULL (-1)      /* required pointer is NULL */
 #define WSDL_E_SHAPE (-2)     /* bad extent (<=0, too many layers/classes, window even or > 2*min(H,W)-1 ...) */
@@ -44,6 +44,8 @@ extern "C" {
 #define WSDL_F32 0
 #define WSDL_BF16 1
 #define WSDL_F16 2
+#define WSDL_U8 3  /* images as 8-bit pixels (read as value / 255), labels as bytes */
+#define WSDL_I64 4 /* labels as int64 (torch.long) */
 
 int wsdl_version(void);
 const char* wsdl_strerror(int rc);
@@ -141,6 +143,38 @@ int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* images, int B, 
                                float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_cut,
                                const float* grad_out_bnd, float* loss_cut, float* loss_bnd, float* grad_logits,
                                void* workspace, size_t workspace_bytes, int prepared, void* stream);
+
+/* The whole loss of a weakly-supervised training step on a two-class batch in ONE launch:
+ *     total = lam_ce * CE(logits, labels) + go_cut * cut(logits, images) + sum_b go_bnd[b] * boundary(softmax(logits)[b], images[b])
+ * i.e. the criterion of SegmentationModel.py:96-113 (F.cross_entropy, mean over the labels that are not ignore_index)
+ * plus the two regularisers above (AlternatingDirectionCutLoss.py:71-105, AlternatingDirectionBoundaryLoss.py:20-44)
+ * weighted as AlternatingDirectionCutLoss.py:709 / AlternatingDirectionBoundaryLoss.py:159 weight them.
+ *   logits (B,2,H,W) WSDL_F32 | WSDL_BF16 (the network's autocast output; arithmetic is f32 on the values as given);
+ *   images (B,3,H,W) WSDL_F32 | WSDL_U8 (the dataset's 8-bit pixels, read as value / 255 exactly like ToTensor);
+ *   labels nullable (no CE term), (B,H,W) WSDL_U8 | WSDL_I64, class ids 0 / 1; ignore_index and any other value are skipped;
+ *   ce_inv_count nullable device scalar 1 / #(labels != ignore_index) (wsdl_count_valid_labels); NULL = 1 / (B H W);
+ *   grad_out_cut / grad_out_bnd nullable device pointers (1 / B floats), NULL = 1.0 -- the lambdas go in here;
+ *   loss_ce (nullable without labels), loss_cut: 1 float each, loss_bnd: B floats -- the UNWEIGHTED loss values;
+ *   loss_total nullable, 1 float: the weighted total above;
+ *   grad_logits nullable (B,2,H,W) WSDL_F32 | WSDL_BF16: d total / d logits;
+ *   window must be 5; H, W >= 6; row strides and bases 16-byte aligned (W % 4 == 0 for f32, % 8 for bf16 logits, % 16
+ *   for u8 images), else WSDL_E_SHAPE / WSDL_E_ALIGN: compose wsdl_pairwise_fwd_bwd calls instead;
+ *   workspace >= wsdl_weak_loss_workspace_bytes(), prepared as for wsdl_pairwise_fwd_bwd_prepared (prepared = 0: the
+ *   call zeroes the control block itself).
+ * One persistent CTA per SM streams tiles from a queue (csrc/pairwise_stream.cu). */
+size_t wsdl_weak_loss_workspace_bytes(int B, int H, int W);
+
+int wsdl_weak_loss_fwd_bwd(const void* logits, int logits_dtype, const void* images, int images_dtype, const void* labels,
+                           int labels_dtype, long long ignore_index, int B, int H, int W, int window, float sigma_cut,
+                           float sigma_bnd, float sigma_space, float lam_ce, const float* ce_inv_count,
+                           const float* grad_out_cut, const float* grad_out_bnd, float* loss_ce, float* loss_cut,
+                           float* loss_bnd, float* loss_total, void* grad_logits, int grad_dtype, void* workspace,
+                           size_t workspace_bytes, int prepared, void* stream);
+
+/* inv_count[0] = 1 / #(labels[i] != ignore_index), i < n (F.cross_entropy's mean denominator); labels WSDL_U8 | WSDL_I64.
+ * scratch: 16 bytes, 8-byte aligned, that the call zeroes and uses; all on `stream`. */
+int wsdl_count_valid_labels(const void* labels, int labels_dtype, size_t n, long long ignore_index,
+                            unsigned long long* scratch, float* inv_count, void* stream);
 
 /* compute_affinities / compute_affinities_single (AlternatingDirectionCutLoss.py:612-637,
  * AlternatingDirectionBoundaryLoss.py:46-70): images (B,3,H,W) -> out (K,B,H,W) with

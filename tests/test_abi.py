@@ -37,7 +37,7 @@ def test_header_symbols_exported_and_bound(lib):
 
 
 def test_version_and_strerror(lib):
-    assert lib.wsdl_version() == 100
+    assert lib.wsdl_version() == 200
     assert lib.wsdl_strerror(0) == b"ok"
     for rc in range(-6, 0):
         assert lib.wsdl_strerror(rc).startswith(b"wsdl:")

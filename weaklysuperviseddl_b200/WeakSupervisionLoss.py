@@ -39,8 +39,23 @@ class WeakSupervisionLoss(nn.Module):
         self.ignore_index = ignore_index
 
     def forward(self, logits, images, labels):
-        """logits (B,C,H,W) any float dtype (bf16 under autocast), images (B,3,H,W), labels (B,H,W) int64.
-        Returns (total, dict of the three detached terms).  The pairwise terms run in fp32."""
+        """logits (B,C,H,W) any float dtype (bf16 under autocast), images (B,3,H,W) float or uint8 (8-bit pixels, read
+        as value / 255), labels (B,H,W) int64 or uint8.  Returns (total, dict of the three detached terms).
+        Arithmetic is fp32 on the values as given.
+
+        Two classes, window 5 (the reference's binary pet / background problem): ONE launch computes the three loss
+        values and d total / d logits straight from the tensors as they are -- no fp32 copies of a bf16 network
+        output, no separate cross-entropy, no gradient rescaling pass (wsdl_weak_loss_fwd_bwd)."""
+        if not logits.is_contiguous():  # a channels_last network hands over NHWC-strided logits
+            logits = logits.contiguous()
+        if WF.weak_loss_supported(logits, images, labels, self.window_size):
+            total, ce, cut, bnd_b = WF.weak_supervision_loss(
+                logits, images, labels, 1.0, self.lambda_cut, self.lambda_boundary, self.sigma_cut, self.sigma_boundary,
+                self.sigma_space, self.window_size, self.ignore_index)
+            return total, {"ce": ce, "cut": cut, "boundary": bnd_b.mean()}
+        if images.dtype == torch.uint8:
+            images = images.float() / 255.0
+        labels = labels.long()
         ce = F.cross_entropy(logits.float(), labels, ignore_index=self.ignore_index)
         x = logits.float()
         img = images.float()

@@ -14,6 +14,7 @@
 // s(e) whenever z is >= pad pixels from every border, so CTAs whose tile is >= 2*pad from the border
 // take a table-free path.  With an inner softmax, dL/dlogit_c = p_c (g_c - sum_j p_j g_j).
 #include <stdlib.h>
+#include <string.h>
 
 #include "pairwise.cuh"
 
@@ -707,9 +708,18 @@ extern "C" int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* 
                                per_image_loss, grad_out, loss_out, grad_values, workspace, workspace_bytes, stream, true);
 }
 
+static size_t sg_bytes(int B, int H, int W) { return 512 + pw_align(sg_workspace_floats(B, H, W) * sizeof(float)); }
+
 extern "C" size_t wsdl_pairwise_dual_workspace_bytes(int B, int H, int W) {
   const size_t one = wsdl_pairwise_workspace_bytes(B, H, W);
-  return one ? 2 * one : 0;
+  if (!one) return 0;
+  const size_t sg = sg_bytes(B, H, W);
+  return 2 * one > sg ? 2 * one : sg;
+}
+
+extern "C" size_t wsdl_weak_loss_workspace_bytes(int B, int H, int W) {
+  if (B < 1 || H < 1 || W < 1) return 0;
+  return sg_bytes(B, H, W) + 256;
 }
 
 extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* images, int B, int H, int W, int window,
@@ -724,8 +734,27 @@ extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* imag
       (grad_logits && ((uintptr_t)grad_logits % 4)))
     return WSDL_E_ALIGN;
   const size_t one = wsdl_pairwise_workspace_bytes(B, H, W);
-  if (workspace_bytes < 2 * one) return WSDL_E_WORKSPACE;
+  if (workspace_bytes < wsdl_pairwise_dual_workspace_bytes(B, H, W)) return WSDL_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
+  static const int no_stream = WSDL_TUNE_INT("WSDL_PAIRWISE_NO_STREAM", 0);
+  if (!no_stream) {  // persistent tile-streaming kernel (pairwise_stream.cu); declines shapes TMA cannot address
+    SgLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.logits = logits, L.images = images, L.grad = grad_logits, L.go_cut = grad_out_cut, L.go_bnd = grad_out_bnd;
+    L.loss_cut = loss_cut, L.loss_bnd = loss_bnd;
+    const uintptr_t w0 = ((uintptr_t)workspace + 255) / 256 * 256;
+    L.ctrl = reinterpret_cast<unsigned*>(w0);
+    L.partial = reinterpret_cast<float*>(w0 + 256);
+    L.B = B, L.H = H, L.W = W;
+    L.logit_dtype = WSDL_F32, L.image_dtype = WSDL_F32, L.grad_dtype = WSDL_F32;
+    L.sigma_cut = sigma_cut, L.sigma_bnd = sigma_bnd, L.sigma_space = sigma_space;
+    if (!prepared) {
+      cudaError_t e = cudaMemsetAsync(L.ctrl, 0, 8, s);
+      if (e != cudaSuccess) return (int)e;
+    }
+    const int rc = sg_launch(L, s);
+    if (rc != 1) return rc;
+  }
   PwParams P;
   P.values = logits;
   P.images = images;
@@ -745,11 +774,92 @@ extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* imag
   P.inv_2ss = 0.f;
   P.ks_unit = 0.f;
   P.kappa = 1.0 / (24.0 * (double)B * (double)H * (double)W * 2.0);
-  if (!prepared) {
+  if (!prepared && no_stream) {
     cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
     if (e != cudaSuccess) return (int)e;
   }
   const int rc = ps_launch_dual(P, sigma_cut, sigma_bnd, sigma_space, grad_out_bnd, loss_bnd, partial_bnd, s);
+  return rc == 1 ? WSDL_E_SHAPE : rc;
+}
+
+__global__ void count_valid_labels_kernel(const void* labels, int dtype, size_t n, long long ignore_index,
+                                          unsigned long long* scratch, unsigned* done, float* inv_count) {
+  unsigned long long c = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const long long v = dtype == WSDL_U8 ? (long long)__ldg(reinterpret_cast<const unsigned char*>(labels) + i)
+                                         : __ldg(reinterpret_cast<const long long*>(labels) + i);
+    c += v != ignore_index;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  __shared__ unsigned long long s_c[8];
+  if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_c[i];
+    atomicAdd(scratch, t);
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {  // last block: exact integer count -> reciprocal, as torch divides
+      __threadfence();
+      const unsigned long long total = *reinterpret_cast<volatile unsigned long long*>(scratch);
+      inv_count[0] = __fdiv_rn(1.f, (float)total);
+    }
+  }
+}
+
+extern "C" int wsdl_count_valid_labels(const void* labels, int labels_dtype, size_t n, long long ignore_index,
+                                       unsigned long long* scratch, float* inv_count, void* stream) {
+  if (!labels || !scratch || !inv_count) return WSDL_E_NULL;
+  if (labels_dtype != WSDL_U8 && labels_dtype != WSDL_I64) return WSDL_E_DTYPE;
+  if (((uintptr_t)scratch % 8) || (labels_dtype == WSDL_I64 && ((uintptr_t)labels % 8))) return WSDL_E_ALIGN;
+  if (n == 0) return WSDL_E_SHAPE;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, 16, s);  // the count and the block check-in word behind it
+  if (e != cudaSuccess) return (int)e;
+  size_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > (size_t)WSDL_NUM_SMS * 4) blocks = (size_t)WSDL_NUM_SMS * 4;
+  count_valid_labels_kernel<<<(unsigned)blocks, 256, 0, s>>>(labels, labels_dtype, n, ignore_index, scratch,
+                                                             reinterpret_cast<unsigned*>(scratch + 1), inv_count);
+  WSDL_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int wsdl_weak_loss_fwd_bwd(const void* logits, int logits_dtype, const void* images, int images_dtype,
+                                      const void* labels, int labels_dtype, long long ignore_index, int B, int H, int W,
+                                      int window, float sigma_cut, float sigma_bnd, float sigma_space, float lam_ce,
+                                      const float* ce_inv_count, const float* grad_out_cut, const float* grad_out_bnd,
+                                      float* loss_ce, float* loss_cut, float* loss_bnd, float* loss_total,
+                                      void* grad_logits, int grad_dtype, void* workspace, size_t workspace_bytes, int prepared, void* stream) {
+  if (!logits || !images || !loss_cut || !loss_bnd || !workspace || (labels && !loss_ce)) return WSDL_E_NULL;
+  if (B < 1 || B > 65535 || H < 6 || W < 6 || window != 5) return WSDL_E_SHAPE;
+  if (!(sigma_cut > 0.f) || !(sigma_bnd > 0.f)) return WSDL_E_ARG;
+  if (logits_dtype != WSDL_F32 && logits_dtype != WSDL_BF16) return WSDL_E_DTYPE;
+  if (images_dtype != WSDL_F32 && images_dtype != WSDL_U8) return WSDL_E_DTYPE;
+  if (labels && labels_dtype != WSDL_U8 && labels_dtype != WSDL_I64) return WSDL_E_DTYPE;
+  if (grad_logits && grad_dtype != WSDL_F32 && grad_dtype != WSDL_BF16) return WSDL_E_DTYPE;
+  if (((uintptr_t)loss_cut % 4) || ((uintptr_t)loss_bnd % 4) || (loss_ce && ((uintptr_t)loss_ce % 4)) ||
+      (labels && labels_dtype == WSDL_I64 && ((uintptr_t)labels % 8)))
+    return WSDL_E_ALIGN;
+  if (workspace_bytes < wsdl_weak_loss_workspace_bytes(B, H, W)) return WSDL_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  SgLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.logits = logits, L.images = images, L.labels = labels, L.grad = grad_logits;
+  L.go_cut = grad_out_cut, L.go_bnd = grad_out_bnd, L.ce_inv_n_dev = ce_inv_count;
+  L.loss_cut = loss_cut, L.loss_bnd = loss_bnd, L.loss_ce = loss_ce, L.loss_total = loss_total;
+  const uintptr_t w0 = ((uintptr_t)workspace + 255) / 256 * 256;
+  L.ctrl = reinterpret_cast<unsigned*>(w0);
+  L.partial = reinterpret_cast<float*>(w0 + 256);
+  L.ignore_index = ignore_index;
+  L.B = B, L.H = H, L.W = W;
+  L.logit_dtype = logits_dtype, L.image_dtype = images_dtype, L.label_dtype = labels_dtype, L.grad_dtype = grad_dtype;
+  L.sigma_cut = sigma_cut, L.sigma_bnd = sigma_bnd, L.sigma_space = sigma_space, L.lam_ce = lam_ce;
+  if (!prepared) {
+    cudaError_t e = cudaMemsetAsync(L.ctrl, 0, 8, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int rc = sg_launch(L, s);
   return rc == 1 ? WSDL_E_SHAPE : rc;
 }
 

@@ -39,4 +39,28 @@ size_t ps_workspace_floats(int B, int H, int W);
 int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_bnd,
                    float* loss_bnd, float* partial_bnd, cudaStream_t s);
 
+// Persistent tile-streaming kernel for the whole weak-supervision loss of a two-class batch (pairwise_stream.cu):
+// cut + boundary (+ cross-entropy) forward and d/dlogits in one launch, f32 / bf16 logits, f32 / u8 images.
+struct SgLaunch {
+  const void* logits;   // (B,2,H,W) logit_dtype
+  const void* images;   // (B,3,H,W) image_dtype (u8: 0..255, read as value / 255)
+  const void* labels;   // nullable (B,H,W) label_dtype
+  void* grad;           // nullable (B,2,H,W) grad_dtype
+  const float* go_cut;  // nullable, 1
+  const float* go_bnd;  // nullable, B
+  const float* ce_inv_n_dev;  // nullable, 1
+  float* loss_cut;      // 1
+  float* loss_bnd;      // B
+  float* loss_ce;       // 1 (nullable)
+  float* loss_total;    // 1 (nullable)
+  float* partial;       // sg_workspace_floats()
+  unsigned* ctrl;       // 2 words, zero before the call, zero after it
+  long long ignore_index;
+  int B, H, W;
+  int logit_dtype, image_dtype, label_dtype, grad_dtype;
+  float sigma_cut, sigma_bnd, sigma_space, lam_ce;
+};
+int sg_launch(const SgLaunch& L, cudaStream_t s);  // 1: not its shape, 0: ok, else a CUDA error
+size_t sg_workspace_floats(int B, int H, int W);
+
 }  // namespace wsdl

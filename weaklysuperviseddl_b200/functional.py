@@ -11,6 +11,7 @@ import torch
 from . import _native
 
 _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_U8, _I64 = 3, 4  # WSDL_U8 / WSDL_I64 (include/wsdl_b200.h)
 NEAR_BAND = 1e-6  # north_star: pixels within 1e-6 of the threshold are counted and reported
 
 
@@ -384,3 +385,121 @@ def pairwise_dual_weighted(logits, images, lam_cut, lam_bnd, sigma_cut=0.05, sig
     v, im = _prep_pair(logits, images)
     return _PairwiseDual.apply(v, im, float(sigma_cut), float(sigma_boundary), float(sigma_space) if sigma_space else 0.0,
                                int(window_size), float(lam_cut), float(lam_bnd))
+
+
+# ------------------------------------------------------------------------------------------------ one-launch loss
+def _tma_ok(t: torch.Tensor) -> bool:
+    """Row stride and base 16-byte aligned: what the tile-streaming kernel's TMA loads need."""
+    return t.is_contiguous() and t.data_ptr() % 16 == 0 and (t.shape[-1] * t.element_size()) % 16 == 0
+
+
+def weak_loss_supported(logits: torch.Tensor, images: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                        window_size: int = 5) -> bool:
+    """Whether `weak_loss_and_grad` can take these tensors as they are (two classes, window 5, H, W >= 6, CUDA,
+    f32 / bf16 logits, f32 / u8 images, u8 / int64 labels, TMA-addressable rows)."""
+    if not (logits.is_cuda and images.is_cuda and logits.dim() == 4 and images.dim() == 4):
+        return False
+    B, C, H, W = logits.shape
+    if C != 2 or window_size != 5 or H < 6 or W < 6 or images.shape != (B, 3, H, W):
+        return False
+    if logits.dtype not in (torch.float32, torch.bfloat16) or images.dtype not in (torch.float32, torch.uint8):
+        return False
+    if labels is not None and (labels.dtype not in (torch.uint8, torch.int64) or labels.shape != (B, H, W) or W % 4):
+        return False
+    return _tma_ok(logits) and _tma_ok(images) and W % 4 == 0
+
+
+def weak_loss_and_grad(logits, images, labels=None, lam_ce=1.0, grad_out_cut=None, grad_out_bnd=None, sigma_cut=0.05,
+                       sigma_boundary=0.1, sigma_space=5.0, window_size=5, ignore_index=-100, want_grad=True,
+                       ce_inv_count: Optional[torch.Tensor] = None):
+    """ONE launch (wsdl_weak_loss_fwd_bwd) for the loss of a weakly-supervised training step on a two-class batch:
+    total = lam_ce * CE(logits, labels) + go_cut * cut(logits, images) + sum_b go_bnd[b] * boundary(softmax(logits)[b],
+    images[b]).  logits (B,2,H,W) f32 | bf16, images (B,3,H,W) f32 | u8 (8-bit pixels, read as value / 255), labels
+    (B,H,W) u8 | int64 or None.  Returns (total (1,), ce (1,) or None, cut (1,), bnd (B,), d total / d logits in the
+    logits' dtype or None); the three loss values are unweighted."""
+    _require_cuda(logits, "logits")
+    _require_cuda(images, "images")
+    logits, images = logits.detach(), images.detach()
+    if not weak_loss_supported(logits, images, labels, window_size):
+        raise _native.WsdlError("wsdl_weak_loss_fwd_bwd does not take these tensors (see weak_loss_supported); "
+                                "compose pairwise_loss calls instead")
+    B, _, H, W = logits.shape
+    dev = logits.device
+    lib = _native.lib()
+    with torch.cuda.device(dev):
+        nbytes = lib.wsdl_weak_loss_workspace_bytes(B, H, W)
+        workspace = _pairwise_workspace(lib, dev, nbytes)
+        out = torch.empty(3 + B, dtype=torch.float32, device=dev)  # total, ce, cut, bnd[B]
+        grad = torch.empty_like(logits) if want_grad else None
+        lab_ptr, lab_code, inv_ptr = None, 0, None
+        if labels is not None:
+            _require_cuda(labels, "labels")
+            labels = labels.contiguous()
+            lab_ptr, lab_code = labels.data_ptr(), (_U8 if labels.dtype == torch.uint8 else _I64)
+            can_ignore = labels.dtype != torch.uint8 or 0 <= int(ignore_index) <= 255
+            if ce_inv_count is None and can_ignore:  # F.cross_entropy's mean is over the labels that are not ignored
+                scratch = torch.empty(3, dtype=torch.int64, device=dev)
+                ce_inv_count = scratch[2:].view(torch.float32)[:1]
+                _native.check(lib.wsdl_count_valid_labels(lab_ptr, lab_code, labels.numel(), int(ignore_index),
+                                                          scratch.data_ptr(), ce_inv_count.data_ptr(), _stream_ptr(dev)),
+                              "wsdl_count_valid_labels")
+            inv_ptr = _upstream(ce_inv_count, 1, dev, "ce_inv_count") if ce_inv_count is not None else None
+        rc = lib.wsdl_weak_loss_fwd_bwd(
+            logits.data_ptr(), _DTYPE_CODE[logits.dtype], images.data_ptr(), _U8 if images.dtype == torch.uint8 else 0,
+            lab_ptr, lab_code, int(ignore_index), B, H, W, int(window_size), float(sigma_cut), float(sigma_boundary),
+            float(sigma_space) if sigma_space else 0.0, float(lam_ce), inv_ptr,
+            _upstream(grad_out_cut, 1, dev, "grad_out_cut"), _upstream(grad_out_bnd, B, dev, "grad_out_bnd"),
+            out[1:].data_ptr() if labels is not None else None, out[2:].data_ptr(), out[3:].data_ptr(), out.data_ptr(),
+            grad.data_ptr() if grad is not None else None, _DTYPE_CODE[logits.dtype], workspace.data_ptr(), nbytes, 1,
+            _stream_ptr(dev))
+    _native.check(rc, "wsdl_weak_loss_fwd_bwd")
+    return out[0:1], (out[1:2] if labels is not None else None), out[2:3], out[3:], grad
+
+
+_WEIGHTS = {}  # (device index, lam_cut, lam_bnd, B) -> (go_cut (1,), go_bnd (B,)): constant device vectors, made once
+
+
+def _loss_weights(dev, lam_cut: float, lam_bnd: float, B: int):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), float(lam_cut), float(lam_bnd), B)
+    w = _WEIGHTS.get(key)
+    if w is None or torch.cuda.is_current_stream_capturing():
+        if len(_WEIGHTS) > 64:
+            _WEIGHTS.clear()
+        w = (torch.full((1,), float(lam_cut), dtype=torch.float32, device=dev),
+             torch.full((B,), float(lam_bnd) / B, dtype=torch.float32, device=dev))
+        if not torch.cuda.is_current_stream_capturing():
+            _WEIGHTS[key] = w
+    return w
+
+
+class _WeakLoss(torch.autograd.Function):
+    """total = lam_ce CE + lam_cut cut + lam_bnd mean_b bnd from one launch; backward scales the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, images, labels, lam_ce, lam_cut, lam_bnd, sigma_cut, sigma_bnd, sigma_space, window,
+                ignore_index):
+        go_c, go_b = _loss_weights(logits.device, lam_cut, lam_bnd, logits.shape[0])
+        need = ctx.needs_input_grad[0]
+        total, ce, cut, bnd, g = weak_loss_and_grad(logits, images, labels, lam_ce, go_c, go_b, sigma_cut, sigma_bnd,
+                                                    sigma_space, window, ignore_index, want_grad=need)
+        ctx.save_for_backward(g if need else torch.empty(0, device=logits.device))
+        total = total.reshape(())
+        outs = (total, ce.reshape(()) if ce is not None else total.new_zeros(()), cut.reshape(()), bnd)
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_total, _g_ce, _g_cut, _g_bnd):
+        (g,) = ctx.saved_tensors
+        if g.numel() == 0:
+            return (None,) * 11
+        return (g * g_total.to(g.dtype),) + (None,) * 10
+
+
+def weak_supervision_loss(logits, images, labels=None, lam_ce=1.0, lam_cut=0.1, lam_bnd=0.5, sigma_cut=0.05,
+                          sigma_boundary=0.1, sigma_space=5.0, window_size=5, ignore_index=-100):
+    """Differentiable (w.r.t. logits) lam_ce * CE + lam_cut * cut + lam_bnd * mean_b boundary, one launch.
+    Returns (total, ce, cut, per-image boundary losses); all but `total` are detached values."""
+    return _WeakLoss.apply(logits, images, labels, float(lam_ce), float(lam_cut), float(lam_bnd), float(sigma_cut),
+                           float(sigma_boundary), float(sigma_space) if sigma_space else 0.0, int(window_size),
+                           int(ignore_index))
