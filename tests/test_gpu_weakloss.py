@@ -94,8 +94,10 @@ def test_weak_loss_vs_oracle(WF, case):
     assert none is None and torch.equal(t2, total) and torch.equal(bnd2, bnd)
     t3, ce3, cut3, bnd3, g3 = WF.weak_loss_and_grad(logits.cuda(), img.cuda(), None, 0.0, go_c.cuda(), go_b.cuda())
     assert ce3 is None and torch.equal(cut3, cut) and torch.equal(bnd3, bnd)
+    # the two-regulariser entry (one tile per CTA) runs the same march: equal to rounding
     lc, lb, gd = WF.pairwise_dual_loss_and_grad(logits.cuda(), img.cuda(), grad_out_cut=go_c.cuda(), grad_out_bnd=go_b.cuda())
-    assert torch.equal(lc, cut) and torch.equal(lb, bnd) and torch.equal(gd, g3)  # the dual entry is the same kernel
+    assert abs(lc.item() - cut.item()) <= 2e-6 * abs(cut.item()) and (lb - bnd).abs().max() <= 2e-6 * bnd.abs().max()
+    assert (gd - g3).abs().max().item() <= 2e-6 * g3.abs().max().item()
 
 
 def test_element_wise_gradient_error_is_reported(WF, capsys):

@@ -12,14 +12,16 @@
 // band columns and its loss partial (1.6-2 us) -- and all the time it holds a third of the SM's registers.  Here
 //   * one CTA per SM lives for the whole launch: three MARCH GROUPS of four warps (the old CTA; 12 marching warps at
 //     168 registers are all the registers an SM has, so there is no producer warp);
-//   * tiles come from a global queue (short row blocks last).  A tile's five raw planes are streamed with TMA into
-//     a staging buffer that is NOT one of the groups' working sets, so the load of the next tile runs under the
-//     marches;
-//   * a group that finishes a tile takes the next staged tile, converts it OUT OF PLACE into its own planes
-//     (image * sqrt(-kc), logits -> p0; f32 / bf16 logits and f32 / u8 images are told apart here, nowhere else),
-//     and the moment its four warps have read the staging buffer its last warp draws the next tile id and issues
-//     the TMA that refills it.  The groups drift out of phase by construction: while one converts or finishes
-//     heads, the other two march, and the latency-bound phases cost issue slots only;
+//   * tiles come from a global queue (short row blocks last); shared memory is FOUR tile slots for three groups.
+//     f32 inputs: the slots rotate.  A group that finishes a tile hands its slot to the next tile of the queue (one
+//     TMA box per raw plane, started at once) and takes the slot that was loading meanwhile; it converts that tile
+//     in place (image * sqrt(-kc), logits -> p0) and marches.  Nobody ever waits for HBM after the first tile;
+//   * bf16 logits / u8 images (the training step's and the dataset's own types): raw tiles do not have the f32
+//     layout, so slot 3 is a staging buffer; the group that takes a staged tile converts it OUT OF PLACE into its
+//     own slot, and the moment its four warps have read the staging buffer its last warp starts the TMA that
+//     refills it.  Types are told apart in the conversion, nowhere else;
+//   * the groups drift out of phase by construction: while one converts or finishes heads, the other two march,
+//     and the latency-bound phases cost issue slots only;
 //   * loss partials are per tile (bit-reproducible whichever group computed them); the last CTA to check in adds
 //     them per image in a fixed order in double -- nobody spins on anybody.
 #include <cuda.h>
@@ -37,13 +39,15 @@ constexpr int SG_THREADS = SG_GROUPS * SG_GTHREADS;
 // ticket k, so a barrier is handed to ticket k + 8 long after every waiter of ticket k has seen it complete: no parity
 // aliasing with up to three groups waiting on consecutive tickets.
 constexpr int SG_RING = 8;
-constexpr int SG_MAX_STAGES = 2;                          // staging buffers (2 when the raw tile is small: u8 / bf16)
+constexpr int SG_MAX_STAGES = 2;                          // staging buffers (2 when the raw tile is small: u8 + bf16)
+constexpr int SG_SLOTS = SG_GROUPS + 1;                   // tile slots: one per group + a spare / the staging area
+constexpr int SG_SLOT_FLOATS = 5 * PS_PLANE;              // a raw f32 tile: 3 image planes + 2 logit planes
 constexpr int SG_HEAD_FLOATS = (PS_SEGS - 1) * 2 * 2 * 64;
 constexpr int SG_GBAND_FLOATS = PS_ROWS * 12;
+static_assert(SG_HEAD_FLOATS + SG_GBAND_FLOATS <= PS_PLANE, "segment heads + band G live in the dead fifth plane");
 constexpr int SG_WX_FLOATS = 2 * 6 * 10;
-constexpr int SG_REGION_FLOATS = 4 * PS_PLANE + SG_HEAD_FLOATS + SG_GBAND_FLOATS + SG_WX_FLOATS;
-constexpr int SG_STAGE_BYTES = 5 * PS_PLANE * 4;  // room for one raw f32 tile (or two u8 + bf16 ones)
-constexpr size_t SG_SMEM_BYTES = (size_t)SG_STAGE_BYTES + (size_t)SG_GROUPS * SG_REGION_FLOATS * 4;
+constexpr int SG_STAGE_BYTES = SG_SLOT_FLOATS * 4;
+constexpr size_t SG_SMEM_BYTES = (size_t)SG_SLOTS * SG_SLOT_FLOATS * 4 + SG_WX_FLOATS * 4;
 constexpr unsigned SG_SPIN_LIMIT = 400000u;  // x 20 us suspend hint: a barrier that never opens traps instead of hanging
 
 struct SgParams {
@@ -58,7 +62,7 @@ struct SgParams {
   float* loss_ce;            // 1, nullable
   float* loss_total;         // 1, nullable: lam_ce * ce + go_cut * cut + sum_b go_bnd[b] * bnd[b]
   float* partial;            // [n_tiles][3]: cut, boundary, cross-entropy sums of a tile
-  unsigned* ctrl;            // [0] tile queue, [1] CTA check-in; both 0 before and after a launch
+  unsigned* ctrl;            // [1] CTA check-in; 0 before and after a launch
   long long ignore_index;
   int B, H, W;
   int n_x, nb, n_tiles, S;   // column tiles per image, row blocks per column tile, tiles, rows per segment
@@ -66,11 +70,43 @@ struct SgParams {
   int img_pitch_b, img_plane_b, val_pitch_b, val_plane_b;  // staged raw layout, bytes
   int img_align, val_align;  // elements per 16 bytes: a TMA box must START on a 16-byte boundary of its row
   int stage_bytes, n_stages;
+  unsigned stagger_ns;       // hold-back between the first tiles of a CTA's groups
+  int rotate;                // 1: f32 logits and images -- tiles load straight into a spare slot and are converted in place
   unsigned tile_tx_bytes;
   float img_scale;           // sqrt(-kc_cut) (u8 images: applied after the exact / 255)
   float ratio, ksu_b, g1b, g4b, l1g_b, l32;
   float lam_ce, ce_inv_n_host;
   double kappa_cut, kappa_bnd;
+};
+
+#ifdef WSDL_PS_TRACE  // debug aid (scripts/trace_stream.py): per group and tile, timestamps of the phase boundaries
+__device__ unsigned long long sg_trace_buf[WSDL_NUM_SMS * SG_GROUPS * 8 * 8];
+#define SG_TR(slot_)                                                                                       \
+  do {                                                                                                     \
+    if (gt == 0 && n_done < 8) {                                                                           \
+      unsigned long long t__;                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                              \
+      sg_trace_buf[((blockIdx.x * SG_GROUPS + g) * 8 + n_done) * 8 + (slot_)] = t__;                       \
+    }                                                                                                      \
+  } while (0)
+#else
+#define SG_TR(slot_)
+#endif
+
+// Kernel variants.  The conversion loop is latency bound and the march loop issue bound: a run-time `if` on a type costs
+// the first its load/compute overlap (the compiler cannot hoist loads across the branch) and the second ~180
+// instructions per step, so the hot configurations are compiled with their types known:
+//   0: f32 logits + f32 images, no labels (the cut + boundary launch of BASELINE configs[1])
+//   1: f32 logits + f32 images + labels (cross-entropy fused in)
+//   2: anything else (bf16 logits, u8 images): types read from the parameters
+template <int MODE>
+struct SgMode {
+  static constexpr bool known = MODE < 2;
+  __device__ static __forceinline__ bool ce(const SgParams& P) { return MODE == 0 ? false : (MODE == 1 ? true : P.labels != nullptr); }
+  __device__ static __forceinline__ bool rotate(const SgParams& P) { return known ? true : P.rotate != 0; }
+  __device__ static __forceinline__ bool img_f32(const SgParams& P) { return known ? true : P.image_dtype == WSDL_F32; }
+  __device__ static __forceinline__ bool val_f32(const SgParams& P) { return known ? true : P.logit_dtype == WSDL_F32; }
+  __device__ static __forceinline__ bool grad_f32(const SgParams& P) { return known ? true : P.grad_dtype == WSDL_F32; }
 };
 
 __device__ __forceinline__ void sg_bar_wait(unsigned bar, unsigned parity) {
@@ -118,30 +154,35 @@ __device__ __forceinline__ unsigned sg_load_labels4(const SgParams& P, size_t ro
 
 // Rows [r0, r1) of the staged raw tile -> the group's planes: image * sqrt(-kc) (sentinel outside the image), logits -> p0.
 // With labels: also the cross-entropy VALUE of the tile's own pixels, from z = v1 - v0 (not from the rounded p0).
+template <int MODE>
 __device__ __forceinline__ void sg_rows_convert(const SgParams& P, const PsBlk& K, const unsigned char* raw, float* s_img,
                                                 float* s_p, int r0, int r1, int lane, float& lsum_ce) {
+  using M = SgMode<MODE>;
   const int H = P.H, W = P.W;
   const float sc = P.img_scale;
-  const bool want_ce = P.labels != nullptr;
+  const bool want_ce = M::ce(P);
+  const bool img_f32 = M::img_f32(P), val_f32 = M::val_f32(P);
   // the staged boxes start on 16-byte boundaries: canonical column 0 (image x0 - 4) sits `shift` elements into a raw row
-  const int ib = (K.x0 - 4 - sg_box_x(K.x0, P.img_align)) * (P.image_dtype == WSDL_F32 ? 4 : 1);
-  const int vb = (K.x0 - 4 - sg_box_x(K.x0, P.val_align)) * (P.logit_dtype == WSDL_F32 ? 4 : 2);
-#pragma unroll 2
+  const int ib = M::known ? 0 : (K.x0 - 4 - sg_box_x(K.x0, P.img_align)) * (img_f32 ? 4 : 1);
+  const int vb = M::known ? 0 : (K.x0 - 4 - sg_box_x(K.x0, P.val_align)) * (val_f32 ? 4 : 2);
+  const int img_plane_b = M::known ? PS_PLANE * 4 : P.img_plane_b, val_plane_b = M::known ? PS_PLANE * 4 : P.val_plane_b;
+  const int img_pitch_b = M::known ? PS_PITCH * 4 : P.img_pitch_b, val_pitch_b = M::known ? PS_PITCH * 4 : P.val_pitch_b;
+#pragma unroll 4
   for (int it = r0 * PS_Q + lane; it < r1 * PS_Q; it += 32) {
     const int t = it / PS_Q, q = it - t * PS_Q;
     const int y = K.ys - 2 + t, xb = K.x0 - 4 + 4 * q;
     const bool row_in = y >= 0 && y < H;
     float4 v[3];
-    if (P.image_dtype == WSDL_F32) {
+    if (img_f32) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float4 r = *reinterpret_cast<const float4*>(raw + c * P.img_plane_b + t * P.img_pitch_b + ib + 16 * q);
+        const float4 r = *reinterpret_cast<const float4*>(raw + c * img_plane_b + t * img_pitch_b + ib + 16 * q);
         v[c] = make_float4(r.x * sc, r.y * sc, r.z * sc, r.w * sc);
       }
     } else {  // u8: the dataset's 8-bit pixels; value / 255 exactly as ToTensor's .div(255), then the kernel scale
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const unsigned r = *reinterpret_cast<const unsigned*>(raw + c * P.img_plane_b + t * P.img_pitch_b + ib + 4 * q);
+        const unsigned r = *reinterpret_cast<const unsigned*>(raw + c * img_plane_b + t * img_pitch_b + ib + 4 * q);
         v[c] = make_float4(__fdiv_rn((float)(r & 0xffu), 255.f) * sc, __fdiv_rn((float)((r >> 8) & 0xffu), 255.f) * sc,
                            __fdiv_rn((float)((r >> 16) & 0xffu), 255.f) * sc, __fdiv_rn((float)(r >> 24), 255.f) * sc);
       }
@@ -161,14 +202,14 @@ __device__ __forceinline__ void sg_rows_convert(const SgParams& P, const PsBlk& 
 #pragma unroll
     for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = v[c];
     float z[4];  // v1 - v0
-    const unsigned char* rv = raw + 3 * P.img_plane_b + vb;
-    if (P.logit_dtype == WSDL_F32) {
-      const float4 a = *reinterpret_cast<const float4*>(rv + t * P.val_pitch_b + 16 * q);
-      const float4 b = *reinterpret_cast<const float4*>(rv + P.val_plane_b + t * P.val_pitch_b + 16 * q);
+    const unsigned char* rv = raw + 3 * img_plane_b + vb;
+    if (val_f32) {
+      const float4 a = *reinterpret_cast<const float4*>(rv + t * val_pitch_b + 16 * q);
+      const float4 b = *reinterpret_cast<const float4*>(rv + val_plane_b + t * val_pitch_b + 16 * q);
       z[0] = b.x - a.x, z[1] = b.y - a.y, z[2] = b.z - a.z, z[3] = b.w - a.w;
     } else {
-      const uint2 a = *reinterpret_cast<const uint2*>(rv + t * P.val_pitch_b + 8 * q);
-      const uint2 b = *reinterpret_cast<const uint2*>(rv + P.val_plane_b + t * P.val_pitch_b + 8 * q);
+      const uint2 a = *reinterpret_cast<const uint2*>(rv + t * val_pitch_b + 8 * q);
+      const uint2 b = *reinterpret_cast<const uint2*>(rv + val_plane_b + t * val_pitch_b + 8 * q);
       z[0] = sg_bf16_lo(b.x) - sg_bf16_lo(a.x), z[1] = sg_bf16_hi(b.x) - sg_bf16_hi(a.x);
       z[2] = sg_bf16_lo(b.y) - sg_bf16_lo(a.y), z[3] = sg_bf16_hi(b.y) - sg_bf16_hi(a.y);
     }
@@ -193,15 +234,16 @@ __device__ __forceinline__ void sg_rows_convert(const SgParams& P, const PsBlk& 
 }
 
 // Final value of one pixel's gradient w.r.t. logit 0 (logit 1 gets the negative): pairwise part + cross-entropy part.
-__device__ __forceinline__ float sg_px_grad(float p0, float gc, float gb, float scale_c, float scale_b, float cw,
-                                            unsigned lab) {
+__device__ __forceinline__ float sg_px_grad(bool want_ce, float p0, float gc, float gb, float scale_c, float scale_b,
+                                            float cw, unsigned lab) {
   const float p1 = 1.f - p0;
   float o = 2.f * p0 * p1 * fmaf(scale_c, gc, scale_b * gb);
-  if (lab < 2u) o = fmaf(cw, lab == 0u ? -p1 : p0, o);  // cw (p0 - [label == 0])
+  if (want_ce && lab < 2u) o = fmaf(cw, lab == 0u ? -p1 : p0, o);  // cw (p0 - [label == 0])
   return o;
 }
 
 // 4 finished pixels of centre row t (columns xs .. xs+3 of image row y)
+template <int MODE>
 __device__ __forceinline__ void sg_emit(const SgParams& P, const PsBlk& K, float scale_b, float cw, int t, int strip,
                                         int okmask, unsigned labs, const float (&G)[4][2], const float (&pc)[4],
                                         float* s_gband, float& lsum_c, float& lsum_b) {
@@ -222,7 +264,7 @@ __device__ __forceinline__ void sg_emit(const SgParams& P, const PsBlk& K, float
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float p0 = pc[j];
-    out[j] = sg_px_grad(p0, G[j][0], G[j][1], K.scale2, scale_b, cw, (labs >> (8 * j)) & 0xffu);
+    out[j] = sg_px_grad(SgMode<MODE>::ce(P), p0, G[j][0], G[j][1], K.scale2, scale_b, cw, (labs >> (8 * j)) & 0xffu);
     if ((okmask >> j) & 1) {
       lsum_c = fmaf(p0 + p0 - 1.f, G[j][0], lsum_c);
       lsum_b = fmaf(p0 + p0 - 1.f, G[j][1], lsum_b);
@@ -231,7 +273,7 @@ __device__ __forceinline__ void sg_emit(const SgParams& P, const PsBlk& K, float
   if (!P.grad) return;
   const size_t plane = (size_t)H * W;
   const size_t o = (size_t)K.b * 2 * plane + (size_t)y * W + xs;  // xs is even and W % 4 == 0: pairs never straddle W
-  if (P.grad_dtype == WSDL_F32) {
+  if (SgMode<MODE>::grad_f32(P)) {
     float* go = reinterpret_cast<float*>(P.grad) + o;
     if (okmask & 1) {
       *reinterpret_cast<float2*>(go) = make_float2(out[0], out[1]);
@@ -254,14 +296,22 @@ __device__ __forceinline__ void sg_emit(const SgParams& P, const PsBlk& K, float
   }
 }
 
+// Column tile of the j-th tile of (image b, row block rb): rotated by b + rb.  A CTA takes tiles CTA + n * grid; with a
+// plain j the 148 SMs / 4 column tiles of a 224-wide image would hand some CTAs nothing but border-column tiles (which
+// carry the band pass) and others none.
+__device__ __forceinline__ int sg_tile_column(int j, int b, int rb, int n_x) { return (j + b + rb) % n_x; }
+
 // Stage ticket k (one thread): draw a tile id from the global queue and start the TMA loads of its five raw planes into
-// staging buffer k % n_stages, or -- queue empty / `end` -- publish an end marker.  The buffer is free: either it has
-// never been used or the caller has just seen its "empty" barrier complete.
+// `dst_smem`, or -- queue empty / `end` -- publish an end marker.  The destination is free: it has never been used, or
+// the caller's group has finished with it (rotating slots), or the caller has seen its "empty" barrier complete.
 __device__ __forceinline__ void sg_stage_tile(const SgParams& P, const CUtensorMap& tm_img, const CUtensorMap& tm_val,
-                                              unsigned char* smem, unsigned long long* s_full, int* s_tile, unsigned k,
-                                              bool end) {
+                                              unsigned char* dst_smem, unsigned long long* s_full, int* s_tile,
+                                              unsigned* s_next, unsigned k, bool end) {
   const unsigned full = ps_smem_u32(&s_full[k % SG_RING]);
-  const int id = end ? P.n_tiles : (int)atomicAdd(P.ctrl, 1u);
+  // Tiles are dealt to the CTAs round robin (tile = CTA + n * grid, short row blocks last) and to a CTA's groups on
+  // demand.  A global first-come queue was measured and is worse: a CTA prefetches one tile ahead, early CTAs drew up to
+  // 8 tiles where 5.2 is the mean, and their third round set the launch time.
+  const int id = end ? P.n_tiles : (int)(blockIdx.x + atomicAdd(s_next, 1u) * gridDim.x);
   if (id >= P.n_tiles) {
     s_tile[k % SG_RING] = -1;
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
@@ -270,10 +320,10 @@ __device__ __forceinline__ void sg_stage_tile(const SgParams& P, const CUtensorM
   s_tile[k % SG_RING] = id;
   const int per_rb = P.n_x * P.B;
   const int rb = id / per_rb, rest = id - rb * per_rb;
-  const int b = rest / P.n_x, tx = rest - b * P.n_x;
+  const int b = rest / P.n_x, tx = sg_tile_column(rest - b * P.n_x, b, rb, P.n_x);
   const int x0 = tx * PS_TW, ys = rb * (PS_SEGS * P.S - 2);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(P.tile_tx_bytes) : "memory");
-  const unsigned dst = ps_smem_u32(smem) + (k % (unsigned)P.n_stages) * (unsigned)P.stage_bytes;
+  const unsigned dst = ps_smem_u32(dst_smem);
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
     const CUtensorMap* tm = c < 3 ? &tm_img : &tm_val;
@@ -286,6 +336,7 @@ __device__ __forceinline__ void sg_stage_tile(const SgParams& P, const CUtensorM
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(SG_THREADS, 1)
     weak_loss_stream_kernel(const __grid_constant__ SgParams P, const __grid_constant__ CUtensorMap tm_img,
                             const __grid_constant__ CUtensorMap tm_val) {
@@ -293,14 +344,20 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
   __shared__ __align__(8) unsigned long long s_full[SG_RING];        // tile k staged (TMA bytes landed / end marker)
   __shared__ __align__(8) unsigned long long s_empty[SG_MAX_STAGES]; // staging buffer read by all 4 warps of its group
   __shared__ int s_tile[SG_RING];
+  __shared__ int s_slot[SG_RING];             // rotating slots: where ticket k was loaded
   __shared__ unsigned s_cons;                 // next ticket of the consumer groups
+  __shared__ unsigned s_prod;                 // rotating slots: next ticket to stage
+  __shared__ unsigned s_next;                 // tiles this CTA has drawn
   __shared__ unsigned s_ticket[SG_GROUPS];
   __shared__ float s_red[SG_GROUPS][3][4];
   __shared__ int s_last;
   __shared__ double s_dred[SG_THREADS / 32];
 
+  using M = SgMode<MODE>;
+  const bool rotate = M::rotate(P);
   const int tid = threadIdx.x;
   const int H = P.H, W = P.W, S = P.S;
+  float* s_wx = reinterpret_cast<float*>(sg_smem) + SG_SLOTS * SG_SLOT_FLOATS;  // [2][6][2][5]: column weights, cut then boundary
   if (tid == 0) {
     for (int i = 0; i < SG_RING; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ps_smem_u32(&s_full[i])));
@@ -308,51 +365,69 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(ps_smem_u32(&s_empty[i])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_cons = 0;
+    s_prod = SG_SLOTS;
+    s_next = 0;
+  }
+  if (tid >= 128 && tid < 248) {  // column weights of the band slots (depend on W only): gamma = 1 (cut), gamma_b (boundary)
+    const int i = tid - 128, which = i / 60, e = i - which * 60, slot = e / 10, rem = e - slot * 10, j = rem % 5;
+    const float g1 = which ? P.g1b : 1.f, g4 = which ? P.g4b : 1.f;
+    const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
+    float w = 0.f;
+    if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, g1, g4) : ps_w1d(xb, x, W, g1, g4);
+    s_wx[i] = w;
   }
   __syncthreads();
 
-  if (tid == 0)
-    for (int k = 0; k < P.n_stages; ++k) sg_stage_tile(P, tm_img, tm_val, sg_smem, s_full, s_tile, (unsigned)k, false);
+  if (tid == 0) {
+    if (rotate) {  // every slot starts loading a tile
+      for (int k = 0; k < SG_SLOTS; ++k) {
+        s_slot[k] = k;
+        if (k > 0 && P.stagger_ns) __nanosleep(P.stagger_ns);  // de-phase the groups: see sg_launch
+        sg_stage_tile(P, tm_img, tm_val, sg_smem + (size_t)k * SG_STAGE_BYTES, s_full, s_tile, &s_next, (unsigned)k, false);
+      }
+    } else {
+      for (int k = 0; k < P.n_stages; ++k)
+        sg_stage_tile(P, tm_img, tm_val, sg_smem + (size_t)SG_GROUPS * SG_STAGE_BYTES + (size_t)k * P.stage_bytes, s_full,
+                      s_tile, &s_next, (unsigned)k, false);
+    }
+  }
   {
     const int g = tid / SG_GTHREADS, gt = tid - g * SG_GTHREADS;
     const int lane = gt & 31, warp = gt >> 5;
     const int seg = warp * 2 + (lane >> 4), strip = lane & 15;
-    float* region = reinterpret_cast<float*>(sg_smem + SG_STAGE_BYTES) + (size_t)g * SG_REGION_FLOATS;
-    float* s_img = region;                       // [3][PS_ROWS][PS_PITCH] scaled for sigma_cut
-    float* s_p = region + 3 * PS_PLANE;          // [PS_ROWS][PS_PITCH] p0
-    float* s_head = region + 4 * PS_PLANE;       // [7][2][2][64]: G (cut, boundary) of the segment heads
-    float* s_gband = s_head + SG_HEAD_FLOATS;    // [row t][6 slots][cut, boundary]
-    float* s_wx = s_gband + SG_GBAND_FLOATS;     // [2][6][2][5]: column weights, cut then boundary
+    unsigned char* const stage0 = sg_smem + (size_t)SG_GROUPS * SG_STAGE_BYTES;  // staging area (not rotating): slot 3
     const int per_rb = P.n_x * P.B;
     const float ksu = P.ksu_b, ratio = P.ratio;
-    const bool want_ce = P.labels != nullptr;
+    const bool want_ce = M::ce(P);
     const float ce_inv_n = P.ce_inv_n_dev ? __ldg(P.ce_inv_n_dev) : P.ce_inv_n_host;
     const float cw = want_ce ? P.lam_ce * ce_inv_n : 0.f;
-    if (gt < 120) {  // column weights of the band slots (depend on W only): gamma = 1 (cut), gamma_b (boundary)
-      const int which = gt / 60, e = gt - which * 60, slot = e / 10, rem = e - slot * 10, j = rem % 5;
-      const float g1 = which ? P.g1b : 1.f, g4 = which ? P.g4b : 1.f;
-      const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
-      float w = 0.f;
-      if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, g1, g4) : ps_w1d(xb, x, W, g1, g4);
-      s_wx[gt] = w;
-    }
+    int n_done = 0;
+    (void)n_done;
     for (;;) {
+      SG_TR(0);
       if (gt == 0) s_ticket[g] = atomicAdd(&s_cons, 1u);
       sg_group_sync(g);  // also: everybody is done with the previous tile's planes, heads and s_red
       const unsigned k = s_ticket[g];
       sg_bar_wait(ps_smem_u32(&s_full[k % SG_RING]), (k / SG_RING) & 1);
+      SG_TR(1);
       const int id = s_tile[k % SG_RING];
-      if (id < 0) {  // queue empty: pass the end marker on to whoever draws the next ticket of this stage, and leave
-        if (gt == 0) sg_stage_tile(P, tm_img, tm_val, sg_smem, s_full, s_tile, k + (unsigned)P.n_stages, true);
+      if (id < 0) {  // queue empty.  Staging mode: pass the end marker on to whoever draws the next ticket of this stage
+        if (!rotate && gt == 0) sg_stage_tile(P, tm_img, tm_val, stage0, s_full, s_tile, &s_next, k + (unsigned)P.n_stages, true);
         break;
       }
       const unsigned stage = k % (unsigned)P.n_stages;
-      const unsigned char* raw = sg_smem + stage * (unsigned)P.stage_bytes;
+      const int slot = rotate ? s_slot[k % SG_RING] : g;
+      float* region = reinterpret_cast<float*>(sg_smem) + (size_t)slot * SG_SLOT_FLOATS;
+      float* s_img = region;                       // [3][PS_ROWS][PS_PITCH] scaled for sigma_cut
+      float* s_p = region + 3 * PS_PLANE;          // [PS_ROWS][PS_PITCH] p0
+      float* s_head = region + 4 * PS_PLANE;       // [7][2][2][64]: G (cut, boundary) of the segment heads, in the plane
+      float* s_gband = s_head + SG_HEAD_FLOATS;    // [row t][6 slots][cut, boundary]     the second logit leaves dead
+      const unsigned char* raw = rotate ? reinterpret_cast<const unsigned char*>(region) : stage0 + stage * (unsigned)P.stage_bytes;
 
       PsBlk K;
       const int rb = id / per_rb, rest = id - rb * per_rb;
       K.b = rest / P.n_x;
-      K.x0 = (rest - K.b * P.n_x) * PS_TW;
+      K.x0 = sg_tile_column(rest - K.b * P.n_x, K.b, rb, P.n_x) * PS_TW;
       K.ys = rb * (PS_SEGS * S - 2);
       K.n = min(PS_SEGS * S - 2, H - K.ys);
       K.nc = K.n + 2;
@@ -369,26 +444,32 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
       }
       float lsum_c = 0.f, lsum_b = 0.f, lsum_ce = 0.f;
 
-      // ---- convert this warp's rows out of the staging buffer, then let the producer refill it ----
+      // ---- convert this warp's rows (in place / out of the staging buffer, which is then refilled) ----
       {
         const int r0 = min(2 * warp * S, rows), r1 = warp == PS_WARPS - 1 ? rows : min(2 * (warp + 1) * S, rows);
         const int re = min(r0 + 2, r1);  // the two rows the warp above looks ahead into
-        sg_rows_convert(P, K, raw, s_img, s_p, r0, re, lane, lsum_ce);
-        if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(1 + 4 * g + warp) : "memory");  // pairs with warp - 1
-        sg_rows_convert(P, K, raw, s_img, s_p, re, r1, lane, lsum_ce);
+        sg_rows_convert<MODE>(P, K, raw, s_img, s_p, r0, re, lane, lsum_ce);
+        if (!rotate && warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(1 + 4 * g + warp) : "memory");  // pairs with warp - 1
+        sg_rows_convert<MODE>(P, K, raw, s_img, s_p, re, r1, lane, lsum_ce);
         __syncwarp();
-        if (lane == 0) {
-          const unsigned empty = ps_smem_u32(&s_empty[stage]);
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty) : "memory");
-          if (warp == PS_WARPS - 1) {  // converts two rows more than the others: usually the last one in
-            sg_bar_wait(empty, (k / (unsigned)P.n_stages) & 1);  // all four warps have read the staging buffer
-            sg_stage_tile(P, tm_img, tm_val, sg_smem, s_full, s_tile, k + (unsigned)P.n_stages, false);
+        if (rotate) {
+          sg_group_sync(g);  // the second logit plane has been read by everybody: it now holds heads and band G
+        } else {
+          if (lane == 0) {
+            const unsigned empty = ps_smem_u32(&s_empty[stage]);
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty) : "memory");
+            if (warp == PS_WARPS - 1) {  // converts two rows more than the others: usually the last one in
+              sg_bar_wait(empty, (k / (unsigned)P.n_stages) & 1);  // all four warps have read the staging buffer
+              sg_stage_tile(P, tm_img, tm_val, stage0 + stage * (unsigned)P.stage_bytes, s_full, s_tile,
+                            &s_next, k + (unsigned)P.n_stages, false);
+            }
           }
+          __syncwarp();
+          if (warp < PS_WARPS - 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + 4 * g + warp + 1) : "memory");
         }
-        __syncwarp();
-        if (warp < PS_WARPS - 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + 4 * g + warp + 1) : "memory");
       }
 
+      SG_TR(2);
       // ---- march ----
       const int t0 = seg * S, t1 = min(t0 + S, K.nc);
       float oy[4][2], oz[4][2];
@@ -426,7 +507,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
           ps_exchangep<2>(A, own, strip);
           if (act) {
             if (s >= 2) {
-              sg_emit(P, K, scale_b, cw, t, strip, okmask, labs, own, pc, s_gband, lsum_c, lsum_b);
+              sg_emit<MODE>(P, K, scale_b, cw, t, strip, okmask, labs, own, pc, s_gband, lsum_c, lsum_b);
             } else if (seg > 0) {
 #pragma unroll
               for (int c = 0; c < 2; ++c)
@@ -442,7 +523,9 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
         ps_exchangep<2>(A, oy, strip);
         ps_exchangep<2>(Bq, oz, strip);
       }
+      SG_TR(3);
       sg_group_sync(g);  // every head row holds its own segment's part
+      SG_TR(4);
       if (seg < PS_SEGS - 1) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -480,11 +563,12 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
             pc[0] = p01.x, pc[1] = p01.y, pc[2] = p23.x, pc[3] = p23.y;
             unsigned labs = 0x02020202u;
             if (want_ce && okmask) labs = sg_load_labels4(P, ((size_t)K.b * H + (K.ys - 2 + t)) * W, xs);
-            sg_emit(P, K, scale_b, cw, t, strip, okmask, labs, G, pc, s_gband, lsum_c, lsum_b);
+            sg_emit<MODE>(P, K, scale_b, cw, t, strip, okmask, labs, G, pc, s_gband, lsum_c, lsum_b);
           }
         }
       }
 
+      SG_TR(5);
       // ---- band columns (and corners) ----
       if (K.xband) {
         sg_group_sync(g);
@@ -505,9 +589,9 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
             const float gc = ac[0] + s_gband[(ty + 2) * 12 + slot * 2 + 0];
             const float gb = ab[0] + s_gband[(ty + 2) * 12 + slot * 2 + 1];
             const unsigned lab = want_ce ? (sg_load_labels4(P, ((size_t)K.b * H + y) * W, x) & 0xffu) : 2u;
-            const float o = sg_px_grad(p0, gc, gb, K.scale2, scale_b, cw, lab);
+            const float o = sg_px_grad(want_ce, p0, gc, gb, K.scale2, scale_b, cw, lab);
             const size_t off = (size_t)K.b * 2 * plane + (size_t)y * W + x;
-            if (P.grad_dtype == WSDL_F32) {
+            if (M::grad_f32(P)) {
               float* go = reinterpret_cast<float*>(P.grad) + off;
               go[0] = o, go[plane] = -o;
             } else {
@@ -518,6 +602,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
         }
       }
 
+      SG_TR(6);
       // ---- the tile's three sums ----
       {
         const float wc = warp_sum(lsum_c), wb = warp_sum(lsum_b), we = warp_sum(lsum_ce);
@@ -531,13 +616,21 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
           __stcg(dst + 0, 2.f * tc);
           __stcg(dst + 1, 2.f * tb);
           __stcg(dst + 2, te);
-          __threadfence();
+          if (rotate) {  // the slot is free (every thread of the group is past its last read: the barrier above): hand it
+                         // to the next tile of the queue, which loads while the three groups work on theirs
+            const unsigned n = atomicAdd(&s_prod, 1u);
+            s_slot[n % SG_RING] = slot;
+            sg_stage_tile(P, tm_img, tm_val, reinterpret_cast<unsigned char*>(region), s_full, s_tile, &s_next, n, false);
+          }
         }
       }
+      SG_TR(7);
+      ++n_done;
     }
   }
 
   // ------------------------------------------------------------------ check in; the last CTA adds the partials up
+  if ((tid & (SG_GTHREADS - 1)) == 0) __threadfence();  // this group leader's partial stores, before the CTA checks in
   __syncthreads();
   if (tid == 0) {
     __threadfence();
@@ -547,7 +640,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (tid == 0) P.ctrl[0] = 0u, P.ctrl[1] = 0u;  // every CTA has checked in: ready for the next launch
+  if (tid == 0) P.ctrl[1] = 0u;  // every CTA has checked in: ready for the next launch
   const int warp = tid >> 5, lane = tid & 31, n_warps = SG_THREADS / 32;
   const int per_rb = P.n_x * P.B;
   double wtot_c = 0.0, wtot_e = 0.0, wtot_b = 0.0;
@@ -682,8 +775,14 @@ int sg_launch(const SgLaunch& L, cudaStream_t s) {
   const int val_box_w = L.logit_dtype == WSDL_BF16 ? 72 : PS_PITCH;
   P.img_pitch_b = img_box_w * esz_img, P.val_pitch_b = val_box_w * esz_val;
   P.img_align = 16 / esz_img, P.val_align = 16 / esz_val;
-  P.img_plane_b = (rows * P.img_pitch_b + 127) / 128 * 128;
-  P.val_plane_b = (rows * P.val_pitch_b + 127) / 128 * 128;
+  P.rotate = (L.image_dtype == WSDL_F32 && L.logit_dtype == WSDL_F32 && !WSDL_TUNE_INT("WSDL_SG_NO_ROTATE", 0)) ? 1 : 0;
+  if (P.rotate) {  // the raw tile IS the working layout: planes at the canonical offsets
+    P.img_plane_b = P.val_plane_b = PS_PLANE * 4;
+  } else {
+    P.img_plane_b = (rows * P.img_pitch_b + 127) / 128 * 128;
+    P.val_plane_b = (rows * P.val_pitch_b + 127) / 128 * 128;
+  }
+  P.stagger_ns = (unsigned)WSDL_TUNE_INT("WSDL_SG_STAGGER_NS", 0);
   P.stage_bytes = 3 * P.img_plane_b + 2 * P.val_plane_b;
   if (P.stage_bytes > SG_STAGE_BYTES) return 1;
   P.n_stages = SG_STAGE_BYTES / P.stage_bytes >= 2 ? 2 : 1;
@@ -711,15 +810,31 @@ int sg_launch(const SgLaunch& L, cudaStream_t s) {
   int dev_id = 0;
   if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0, attr_done[0] = false;
   if (!attr_done[dev_id]) {
-    cudaError_t e = cudaFuncSetAttribute(weak_loss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(weak_loss_stream_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(weak_loss_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(weak_loss_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_done[dev_id] = true;
   }
   int grid = (P.n_tiles + SG_GROUPS - 1) / SG_GROUPS;
   if (grid > WSDL_NUM_SMS) grid = WSDL_NUM_SMS;
-  weak_loss_stream_kernel<<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
+  const bool f32_in = L.image_dtype == WSDL_F32 && L.logit_dtype == WSDL_F32 && (!L.grad || L.grad_dtype == WSDL_F32) && P.rotate;
+  if (f32_in && !L.labels)
+    weak_loss_stream_kernel<0><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
+  else if (f32_in)
+    weak_loss_stream_kernel<1><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
+  else
+    weak_loss_stream_kernel<2><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
   WSDL_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace wsdl
+
+#ifdef WSDL_PS_TRACE
+extern "C" int wsdl_sg_trace_read(unsigned long long* host, int n_words) {
+  return (int)cudaMemcpyFromSymbol(host, wsdl::sg_trace_buf, (size_t)n_words * sizeof(unsigned long long));
+}
+#endif
