@@ -4,10 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload pairwise|layercam]
 
 Default workload = BASELINE.json configs[1]: AlternatingDirectionCutLoss + BoundaryLoss forward+backward on
-synthetic 32x2x224x224 maps with smooth RGB affinities.  One "step" = one cut-loss fwd+bwd launch + one
-boundary-loss fwd+bwd launch over one batch; the metric counts pixels once per loss (2*B*H*W per step).
-`--workload layercam` runs configs[2] instead (fused LayerCAM->normalise->threshold at 512x512, image-sharded);
-the default run reports it too, under "also".
+synthetic 32x2x224x224 maps with smooth RGB affinities.  One "step" = both losses (values and d/dlogits) of one
+32-image batch -- one fused launch; the metric counts pixels once per loss (2*B*H*W per step).
+`--workload layercam` runs configs[2] instead (fused LayerCAM->normalise->threshold over the 3680-image set at
+512x512, image-sharded, strong scaling); `--workload trainstep` config 4; the default run reports both too, at
+every N, under "also".
 
 One JSON line on stdout (rank 0).  Under torchrun every rank processes its own batch (weak scaling, no
 data-path collective); the elapsed time is the max over ranks.
@@ -26,6 +27,16 @@ sys.path.insert(0, ROOT)
 PAIR = dict(B=32, C=2, H=224, W=224, window=5, sigma_cut=0.05, sigma_bnd=0.1, sigma_space=5.0)
 LCAM = dict(S=512, layers=((1024, 32, 32), (2048, 32, 32)), chunk=128, thresh=0.3, alpha=1.0, n_images=3680)
 N_SETS = 8  # rotated input sets: 8 x 45 MB > 126 MB L2
+# `config` is the same object in the B200 arm and in the reference arm: both run THIS workload, batch and all
+PAIR_CONFIG = {
+    "workload": "configs[1]: AlternatingDirectionCutLoss + BoundaryLoss fwd/bwd, 32x2x224x224 per GPU, smooth RGB affinities "
+                "(SURVEY.md 8d)",
+    "batch": "32 images per step: cut loss fwd+bwd on the logits (sigma 0.05) + boundary loss fwd+bwd on softmax(logits) of "
+             "every image (sigma 0.1 / 5); pixels counted once per loss (2 x 32 x 224 x 224 per step)",
+    "sharding": "one batch per rank, no data-path collective",
+}
+PHYS_BYTES_PER_PIX = 28  # what ONE fused launch must move per pixel: 20 B in (2 logits + 3 rgb), 8 B gradient out
+MIN_TIMED_MS = 20.0      # a short --steps run repeats its K steps until the timed region is at least this long
 BYTES_PER_PIX = 28  # 20 B read (2 logits + 3 rgb) + 8 B gradient written, C=2
 L2_MB = 126
 NCU_TRAFFIC_BYTES = 32_230_000  # dram read 32.18 MB + write 0.05 MB per launch (ncu --set full, round 1)
@@ -203,8 +214,10 @@ def run_reference_layercam(args):
         "impl": "reference", "metric": "pseudo-masks/s", "value": value, "unit": "masks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(times) / len(times) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: LayerCAM->normalise->threshold after the backbone, 512x512, layers 3+4",
-                   "sample": f"{n_img} images per step, one at a time"},
+        "config": {"workload": "configs[2]: fused LayerCAM->normalise->threshold over a synthetic 3680-image Pet-sized set at "
+                               "512x512, image-sharded i % world == rank; one step = one pass over the set",
+                   "l2": "2 rotated resident chunks of 3.2 GB per rank"},
+        "how": f"{n_img} images per step, one at a time as the reference does (a bounded sample of the 3680-image pass)",
         "cpu_baseline": {"value": value, "unit": "masks/s", "cores": threads, "kind": "port",
                          "sample": f"{n_img} images per step; oracle port of LayerCAM.py:52-76 + PsuedoMasks.py:59-62 "
                                    f"(torch {torch.__version__} CPU)"},
@@ -222,7 +235,7 @@ def run_reference(args):
     import torch
 
     threads = os.cpu_count() or 1
-    sample_B = 2
+    sample_B = PAIR["B"]  # the whole 32-image batch of the B200 arm: same configuration, not a sample
     times = []
     for i in range(args.warmup + args.steps):
         _, t = cpu_pairwise_sample(sample_B, 1, threads)
@@ -235,11 +248,13 @@ def run_reference(args):
         "impl": "reference", "metric": "cut+boundary loss fwd+bwd throughput", "value": value, "unit": "Gpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: cut + boundary loss fwd/bwd, 2x224x224 maps, smooth RGB",
-                   "sample": f"{sample_B} of 32 images per step"},
+        "config": dict(PAIR_CONFIG),
+        "how": "the reference's own op sequence (oracle port of AlternatingDirectionCutLoss.py:71-105 and "
+               "AlternatingDirectionBoundaryLoss.py:20-70 incl. autograd backward) on the host cores, the full 32-image batch "
+               "per step; /root/reference does not exist on the GPU box and is a directory of scripts without an installer",
         "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_B}x2x224x224 per step, oracle port of the reference ATen op sequence "
-                                   f"(torch {torch.__version__} CPU, autograd backward)"},
+                         "sample": f"{sample_B}x2x224x224 per step (the full batch), oracle port of the reference ATen op "
+                                   f"sequence (torch {torch.__version__} CPU, autograd backward)"},
         "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -452,9 +467,15 @@ def bench_pairwise(args, lib, dev, rank, world):
         if rem:
             some_steps(range(rem))
 
+    # A K-step region of this workload is 0.5 ms at K = 20: too short for a stable number (and for NVML to see).  The
+    # timed region is `repeats` x K steps -- the same K-step sequence over and over -- and everything below is per step.
+    probe_ms, _ = _timed(run_steps, args.warmup, args.steps, dev, world, None)
+    repeats = max(1, int(MIN_TIMED_MS / max(probe_ms, 1e-3)) + 1)
     sampler = ClockSampler(dev.index) if rank == 0 else None
-    ms, clocks = _timed(run_steps, args.warmup, args.steps, dev, world, sampler)
-    if rank == 0 and clocks is not None and ms < 400.0:  # too short for NVML to see: probe the same load, untimed
+    ms, clocks = _timed(lambda n: [run_steps(args.steps) for _ in range(n // args.steps)], 0, args.steps * repeats, dev, world,
+                        sampler)
+    timed_steps = args.steps * repeats
+    if rank == 0 and clocks is not None and ms < 400.0:  # still short for NVML's sampling period: probe the same load, untimed
         probe = ClockSampler(dev.index)
         probe.start()
         t0 = time.time()
@@ -463,15 +484,14 @@ def bench_pairwise(args, lib, dev, rank, world):
             torch.cuda.synchronize(dev)
         clocks = dict(probe.stop(), note="sampled over an untimed 0.6 s repeat of the same steps (timed region < 0.4 s)")
     pix_per_step = 2 * B * H * W  # counted once per loss
-    value = world * pix_per_step * args.steps / (ms * 1e-3) / 1e9
-    ms_per_step = ms / args.steps
+    value = world * pix_per_step * timed_steps / (ms * 1e-3) / 1e9
+    ms_per_step = ms / timed_steps
     peak, peak_src = peaks()
-    # dominant kernel: pairwise_sym_kernel<2,*> (csrc/pairwise_sym.cu), two launches per step (cut: <2,true>,
-    # boundary: <2,false>) and nothing else (prepared workspace: no per-call memset)
     launches_per_step = 1 if fused else 2
     launch_ms = ms_per_step / launches_per_step
     # algorithmic bytes: 28 B per pixel PER LOSS; the fused launch processes 2 B H W loss-pixels
     alg_bytes = BYTES_PER_PIX * B * H * W * (2 if fused else 1)
+    phys_bytes = PHYS_BYTES_PER_PIX * B * H * W  # what a launch physically has to move (inputs once, one gradient)
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965
     instr = NCU_WARP_INSTR["fused"] if fused else 0.5 * (NCU_WARP_INSTR["cut"] + NCU_WARP_INSTR["boundary"])
@@ -487,30 +507,43 @@ def bench_pairwise(args, lib, dev, rank, world):
                     launch_dual(i, sp(), fl[0])
                 else:
                     (launch_cut if which == 0 else launch_bnd)(i, sp(), ws)
-        t_ms, _ = _timed(only, 20, 200, dev, world, None)
-        per_kernel[name] = t_ms / 200
+        t_ms, _ = _timed(only, 20, 500, dev, world, None)
+        per_kernel[name] = t_ms / 500
+    alone_ms = per_kernel["fused cut+boundary"] if fused else 0.5 * (per_kernel["cut"] + per_kernel["boundary"])
+    gbs = lambda nbytes, t_ms: nbytes / (t_ms * 1e-3) / 1e9
+    fractions = {
+        "survey_bytes_at_step_time": gbs(alg_bytes, launch_ms) / peak,
+        "survey_bytes_at_kernel_duration": gbs(alg_bytes, alone_ms) / peak,
+        "physical_bytes_at_step_time": gbs(phys_bytes, launch_ms) / peak if fused else None,
+        "physical_bytes_at_kernel_duration": gbs(phys_bytes, alone_ms) / peak if fused else None,
+        "definitions": "survey bytes = SURVEY.md 8(d): 28 B per pixel per LOSS x the loss-pixels a launch processes (the fused "
+                       "launch computes both losses: 89.9 MB); physical bytes = what that one launch must move (20 B in + 8 B "
+                       "gradient out per pixel: 45.0 MB); step time = timed region / steps with consecutive steps overlapping on "
+                       f"{'4 streams' if two else 'one stream'} (what a stream of independent batches sees); kernel duration = the same launch "
+                       "alone on one stream, back to back, 500 launches between CUDA events (what a training step sees); all "
+                       f"over the {'measured' if 'measured' in peak_src else 'fallback'} HBM peak",
+    }
     res = {
         "metric": "cut+boundary loss fwd+bwd throughput", "value": value, "unit": "Gpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": "configs[1]: AlternatingDirectionCutLoss + BoundaryLoss fwd/bwd, 32x2x224x224 per GPU, "
-                        "smooth RGB affinities (SURVEY.md 8d)",
-            "step": ("1 fused launch: cut loss fwd+bwd on the logits (sigma 0.05) + boundary loss fwd+bwd on "
-                     "softmax(logits) (32 images, sigma 0.1/5), both loss values and d/dlogits; " if fused else
-                     "1 cut fwd+bwd launch (logits, sigma 0.05) + 1 boundary fwd+bwd launch (32 images, sigma 0.1/5); ") +
-                    "pixels counted once per loss",
+        "config": dict(PAIR_CONFIG),
+        "how": {
+            "step": ("1 fused launch (wsdl_pairwise_dual_fwd_bwd): both loss values and d/dlogits" if fused else
+                     "1 cut fwd+bwd launch + 1 boundary fwd+bwd launch"),
+            "timed": f"{repeats} x {args.steps} steps between one pair of CUDA events ({ms:.2f} ms); ms_per_step = region / "
+                     f"{timed_steps}",
             "l2": f"rotating {N_SETS} input sets ({N_SETS * 45} MB) > {L2_MB} MB L2",
             "launch": (f"CUDA graph of {G_STEPS} steps" if graph is not None else "direct C-ABI calls") +
                       ((f"; consecutive steps rotate over {n_streams} streams (independent work, own workspaces)" if fused else
                         f"; the cut and the boundary launch of a step on two streams, consecutive steps on {n_pairs} stream "
                         "pairs (independent work, own workspaces)") if two else "; one stream"),
-            "sharding": "batch per rank, no data-path collective",
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES,
                      "kernel": "pairwise_dual_kernel" if fused else "pairwise_sym_kernel<2,true|false>",
-                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes, "physical_bytes_per_launch": phys_bytes if fused else alg_bytes,
+                     "launch_ms": launch_ms, "kernel_ms_alone": alone_ms, "fractions": fractions,
                      "peak_source": peak_src, "per_kernel_ms_direct_launch": per_kernel,
                      "issue_roof": {"warp_instructions_per_launch": instr, "floor_ms": issue_floor_ms,
                                     "frac": issue_floor_ms / launch_ms,
@@ -521,14 +554,13 @@ def bench_pairwise(args, lib, dev, rank, world):
                                        "note": "third roof: MUFU.EX2 + MUFU.RCP lane-ops / measured 4.63 T/s; the march "
                                                "needs 768 MUFU cycles, 775 issue slots and ~680 FP32-pipe cycles per "
                                                "warp step: the three pipes are balanced"}} if fused else {}),
-                     "note": "launch duration = timed step / launches per step (CUDA events on the stream the steps are forked "
-                             "from and joined to, inside the graph; launches on different streams overlap, so this is the "
-                             "time the step spends per launch, not a kernel duration: those are in "
-                             "per_kernel_ms_direct_launch); algorithmic bytes = 28 B per pixel per loss x the loss-pixels "
-                             "one launch processes (the fused launch computes both losses from one read of the inputs); traffic = dram__bytes_read+write per launch from profiles/r01_c_ncu_full_sym.txt "
-                             "(the 12.8 MB gradient is still dirty in L2 when the kernel ends); the kernel is bound by "
-                             "FP32/MUFU issue, not HBM (DESIGN.md 4.2)"},
-        "gpu_launches": launches_per_step * args.steps,
+                     "note": "`frac` = survey bytes at step time (the contract's definition: algorithmic bytes / average launch "
+                             "duration over the timed region; launches of consecutive steps overlap on the device).  The same "
+                             "bytes at the kernel's own duration and the physical bytes at both are in `fractions`.  traffic = "
+                             "dram__bytes_read+write per launch (ncu --set full, profiles/): below the algorithmic bytes because the "
+                             "12.8 MB gradient is still dirty in L2 when the kernel ends; the kernel is bound by MUFU / FP32 / "
+                             "issue, not HBM (DESIGN.md 4.2)"},
+        "gpu_launches": launches_per_step * timed_steps,
         "clocks": clocks,
     }
     e2e = e2e_pairwise(dev, world, max(3, min(50, args.steps)), max(3, min(5, args.warmup)))
@@ -536,14 +568,32 @@ def bench_pairwise(args, lib, dev, rank, world):
         res["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, t = cpu_pairwise_sample(8, 2, threads)
+            v, t = cpu_pairwise_sample(PAIR["B"], 2, threads)
             res["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": threads, "kind": "port",
-                                   "sample": f"8 of 32 images (8x2x224x224), best of 2, {t:.2f} s; oracle port of the "
+                                   "sample": f"the full 32x2x224x224 batch, best of 2, {t:.2f} s per step; oracle port of the "
                                              "reference ATen op sequence incl. autograd backward"}
-        if world == 1 and not args.no_also:
-            res["also"] = {"layercam_512": bench_layercam_core(lib, dev, 0, 1, 30, 5),
-                           "eager_torch_cuda": eager_torch_pairwise(dev)}
+    if not args.no_also:  # configs 3 and 4 ride along at every N (collective: every rank runs them, rank 0 reports)
+        also = {}
+        for key, fn in (("layercam_3680", lambda: bench_layercam_sharded(dev, rank, world, 3, 1)),
+                        ("trainstep", lambda: _trainstep_brief(bench_trainstep(argparse.Namespace(
+                            steps=12, warmup=4, no_cpu_baseline=True), dev, rank, world)))):
+            try:
+                also[key] = fn()
+            except Exception as e:  # a side measurement must never take the headline line down
+                also[key] = {"error": repr(e)[:300]}
+        if world == 1:
+            try:
+                also["eager_torch_cuda"] = eager_torch_pairwise(dev)
+            except Exception as e:
+                also["eager_torch_cuda"] = {"error": repr(e)[:300]}
+        if rank == 0:
+            res["also"] = also
     return res
+
+
+def _trainstep_brief(r):
+    return {k: r[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "stage_share") if k in r} | {
+        "config": r["config"]["workload"], "e2e_h2d_bytes_per_step": r["e2e"]["h2d_bytes_per_step"]}
 
 
 def eager_torch_pairwise(dev):
@@ -617,91 +667,122 @@ def _native_check(rc):
 
 
 def e2e_pairwise(dev, world, steps, warmup):
-    """Same metric through the public modules with HOST buffers: H2D of logits+images from pinned memory,
-    LocalNormalizedCutLoss + batched ConstrainToBoundaryLossSingle, backward, D2H of loss and gradient.
+    """Same metric through the public API with HOST buffers: every step copies its logits and images from pinned host
+    memory, runs the loss forward + backward, and copies the gradient and the loss values back.  Three variants:
+
+      u8   (the headline): images as the dataset stores them, 8-bit RGB; the kernel reads value / 255 exactly as
+           ToTensor does, so the result is bit-identical to the f32-image call on the same pixels -- 3 B instead of 12 B
+           per pixel over PCIe.  f32 logits in, f32 gradient out.  One launch: functional.weak_loss_and_grad
+           (wsdl_weak_loss_fwd_bwd).
+      f32  round 1's path: f32 images, LocalNormalizedCutLoss + ConstrainToBoundaryLossSingle modules + .backward().
+      bf16 u8 images, bf16 logits in, bf16 gradient out (what a bf16-autocast network hands over and takes back).
+
     Every rank runs its own batch concurrently (shared host links included); max time over ranks."""
     import torch
     import torch.distributed as dist
 
     import weaklysuperviseddl_b200 as Wm
+    from weaklysuperviseddl_b200 import functional as WF
 
     B, C, H, W = PAIR["B"], PAIR["C"], PAIR["H"], PAIR["W"]
     gen = torch.Generator().manual_seed(1)
-    h_logits = torch.randn(B, C, H, W, generator=gen).pin_memory()
-    h_img = smooth_images(gen, B, H, W, "cpu").pin_memory()
+    logits32 = torch.randn(B, C, H, W, generator=gen)
+    img8 = (smooth_images(gen, B, H, W, "cpu") * 255).round().to(torch.uint8)
     cut = Wm.LocalNormalizedCutLoss(PAIR["sigma_cut"], PAIR["window"])
     bnd = Wm.ConstrainToBoundaryLossSingle(PAIR["sigma_bnd"], PAIR["sigma_space"], PAIR["window"])
-
-    # Three streams, two buffer sets: the H2D copy of step k+1 and the D2H read-back of step k-1 run under the
-    # compute of step k (PCIe is full duplex).  Every step still moves its own inputs and results.
     main = torch.cuda.current_stream(dev)
-    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    NB = 2
-    d_logits = [torch.empty(B, C, H, W, device=dev) for _ in range(NB)]
-    d_img = [torch.empty(B, 3, H, W, device=dev) for _ in range(NB)]
-    h_grads = [torch.empty(B, C, H, W).pin_memory() for _ in range(NB)]
-    h_losses = [torch.empty(1).pin_memory() for _ in range(NB)]
-    ev_in = [torch.cuda.Event() for _ in range(NB)]
-    ev_done = [torch.cuda.Event() for _ in range(NB)]
-    ev_out = [torch.cuda.Event() for _ in range(NB)]
-    state = {"k": 0}
+    go_c = torch.ones(1, device=dev)
+    go_b = torch.full((B,), 1.0 / B, device=dev)
 
-    def step():
-        k = state["k"]
-        i = k % NB
-        state["k"] = k + 1
-        if k >= NB:
-            ev_out[i].synchronize()  # the host has the results of the step that last used this buffer set
-        with torch.cuda.stream(s_in):
+    def run(kind):
+        h_logits = (logits32.to(torch.bfloat16) if kind == "bf16" else logits32).pin_memory()
+        h_img = (img8.float() / 255 if kind == "f32" else img8).pin_memory()
+        # Three streams, two buffer sets: the H2D copy of step k+1 and the D2H read-back of step k-1 run under the
+        # compute of step k (PCIe is full duplex).  Every step still moves its own inputs and results.
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        NB = 2
+        d_logits = [torch.empty_like(h_logits, device=dev) for _ in range(NB)]
+        d_img = [torch.empty_like(h_img, device=dev) for _ in range(NB)]
+        h_grads = [torch.empty_like(h_logits).pin_memory() for _ in range(NB)]
+        h_losses = [torch.empty(2 + B).pin_memory() for _ in range(NB)]
+        ev_in = [torch.cuda.Event() for _ in range(NB)]
+        ev_done = [torch.cuda.Event() for _ in range(NB)]
+        ev_out = [torch.cuda.Event() for _ in range(NB)]
+        state = {"k": 0}
+
+        def step():
+            k = state["k"]
+            i = k % NB
+            state["k"] = k + 1
             if k >= NB:
-                s_in.wait_event(ev_done[i])  # its inputs are no longer being read
-            d_logits[i].copy_(h_logits, non_blocking=True)
-            d_img[i].copy_(h_img, non_blocking=True)
-            ev_in[i].record(s_in)
-        main.wait_event(ev_in[i])
-        logits = d_logits[i].detach().requires_grad_(True)
-        img = d_img[i]
-        loss = cut(logits, img) + bnd(torch.softmax(logits, dim=1), img).mean()
-        loss.backward()
-        ev_done[i].record(main)
-        g, l = logits.grad, loss.detach().reshape(1)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_done[i])
-            h_grads[i].copy_(g, non_blocking=True)
-            h_losses[i].copy_(l, non_blocking=True)
-            g.record_stream(s_out)
-            l.record_stream(s_out)
-            ev_out[i].record(s_out)
+                ev_out[i].synchronize()  # the host has the results of the step that last used this buffer set
+            with torch.cuda.stream(s_in):
+                if k >= NB:
+                    s_in.wait_event(ev_done[i])  # its inputs are no longer being read
+                d_logits[i].copy_(h_logits, non_blocking=True)
+                d_img[i].copy_(h_img, non_blocking=True)
+                ev_in[i].record(s_in)
+            main.wait_event(ev_in[i])
+            if kind == "f32":
+                logits = d_logits[i].detach().requires_grad_(True)
+                loss = cut(logits, d_img[i]) + bnd(torch.softmax(logits, dim=1), d_img[i]).mean()
+                loss.backward()
+                g, l = logits.grad, loss.detach().reshape(1).expand(2 + B).contiguous()
+            else:
+                total, _, lc, lb, g = WF.weak_loss_and_grad(d_logits[i], d_img[i], None, 0.0, go_c, go_b, PAIR["sigma_cut"],
+                                                            PAIR["sigma_bnd"], PAIR["sigma_space"], PAIR["window"])
+                l = torch.cat([total, lc, lb])
+            ev_done[i].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[i])
+                h_grads[i].copy_(g, non_blocking=True)
+                h_losses[i].copy_(l, non_blocking=True)
+                g.record_stream(s_out)
+                l.record_stream(s_out)
+                ev_out[i].record(s_out)
 
-    def drain():
-        for e in ev_out:
-            e.synchronize()
-        torch.cuda.synchronize(dev)
+        def drain():
+            for e in ev_out:
+                e.synchronize()
+            torch.cuda.synchronize(dev)
 
-    for _ in range(warmup):
-        step()
-    drain()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(main)
-    for _ in range(steps):
-        step()
-    main.wait_stream(s_out)  # the last read-backs are inside the timed region
-    main.wait_stream(s_in)
-    e1.record(main)
-    drain()
-    ms = e0.elapsed_time(e1)
-    h_grad = h_grads[0]
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return {"value": world * 2 * B * H * W * steps / (ms * 1e-3) / 1e9, "unit": "Gpix/s",
-            "h2d_bytes_per_step": h_logits.numel() * 4 + h_img.numel() * 4,
-            "d2h_bytes_per_step": h_grad.numel() * 4 + 4, "steps": steps, "ms_per_step": ms / steps,
-            "api": "LocalNormalizedCutLoss()(logits, images) + ConstrainToBoundaryLossSingle()(softmax, images).mean(); "
-                   ".backward(); pinned host buffers; H2D / compute / D2H of consecutive steps pipelined on three streams"}
+        for _ in range(warmup):
+            step()
+        drain()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for _ in range(steps):
+            step()
+        main.wait_stream(s_out)  # the last read-backs are inside the timed region
+        main.wait_stream(s_in)
+        e1.record(main)
+        drain()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return {"value": world * 2 * B * H * W * steps / (ms * 1e-3) / 1e9, "unit": "Gpix/s",
+                "h2d_bytes_per_step": h_logits.numel() * h_logits.element_size() + h_img.numel() * h_img.element_size(),
+                "d2h_bytes_per_step": h_grads[0].numel() * h_grads[0].element_size() + h_losses[0].numel() * 4,
+                "steps": steps, "ms_per_step": ms / steps}, h_losses[(steps + warmup - 1) % NB].clone()
+
+    u8, l_u8 = run("u8")
+    f32, l_f32 = run("f32")
+    bf16, _ = run("bf16")
+    u8["api"] = ("weaklysuperviseddl_b200.functional.weak_loss_and_grad(logits f32, images u8) -> wsdl_weak_loss_fwd_bwd: cut + "
+                 "mean boundary loss values and d/dlogits in one launch; pinned host buffers; H2D / compute / D2H of consecutive "
+                 "steps pipelined on three streams")
+    u8["images"] = "uint8 RGB as the dataset stores them (read as value / 255, bit-identical to ToTensor's floats)"
+    u8["total_loss_vs_f32_image_path_rel"] = abs(float(l_u8[0]) - float(l_f32[0])) / abs(float(l_f32[0]))
+    u8["variants"] = {
+        "f32_images_modules": dict(f32, api="LocalNormalizedCutLoss()(logits, images) + ConstrainToBoundaryLossSingle()(softmax, "
+                                           "images).mean(); .backward() -- round 1's e2e path, f32 images"),
+        "bf16_logits_u8_images": dict(bf16, api="weak_loss_and_grad(logits bf16, images u8): bf16 gradient back"),
+    }
+    return u8
 
 
 # ------------------------------------------------------------------------------------------ configs[2]
@@ -763,19 +844,72 @@ def bench_layercam_core(lib, dev, rank, world, steps, warmup):
             "l2": "2 rotated chunks of 3.2 GB", "streams": 2}
 
 
+def bench_layercam_sharded(dev, rank, world, passes, warmup_passes):
+    """BASELINE config 3 as north_star states it: the fused LayerCAM -> normalise -> threshold kernels over the WHOLE
+    synthetic 3680-image Pet-sized set at 512x512 (layer3 + layer4 hooks, fp32), image-sharded i % world == rank through
+    the product entry `generate_pseudo_masks_sharded` (resident chunks of 128 images, two streams, counters all-reduced
+    at the end).  STRONG scaling: the set is fixed, every rank walks its 3680 / world images.  The hooks of a chunk are
+    synthetic and resident (two rotated 3.2 GB chunks defeat the L2; generating 93.6 GB of random numbers is not part of
+    the path); one pass = the whole set."""
+    import torch
+
+    from weaklysuperviseddl_b200.PsuedoMasks import generate_pseudo_masks_sharded
+
+    chunk, S, layers, n_images = LCAM["chunk"], LCAM["S"], LCAM["layers"], LCAM["n_images"]
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    sets = []
+    for _ in range(2):
+        acts = [torch.randn(chunk, C, h, w, device=dev, generator=gen).relu_() for (C, h, w) in layers]
+        grads = [torch.randn(chunk, C, h, w, device=dev, generator=gen).mul_(1e-3) for (C, h, w) in layers]
+        sets.append((acts, grads))
+    calls = {"n": 0}
+
+    def hooks(indices):
+        acts, grads = sets[calls["n"] % 2]
+        calls["n"] += 1
+        n = len(indices)
+        return [a[:n] for a in acts], [g[:n] for g in grads]
+
+    last = {}
+
+    def one_pass():
+        last["res"] = generate_pseudo_masks_sharded(hooks, n_images, (S, S), cam_thresh=LCAM["thresh"], alpha=LCAM["alpha"],
+                                                    chunk=chunk, rank=rank, world=world, streams=2,
+                                                    sink=lambda idx, m: last.__setitem__("mask", m))
+
+    ms, _ = _timed(lambda n: [one_pass() for _ in range(n)], warmup_passes, passes, dev, world, None)
+    per_image = sum(2 * C * h * w * 4 for (C, h, w) in layers) + S * S
+    masks_per_s = n_images * passes / (ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = per_image * masks_per_s / 1e9 / world  # per GPU
+    return {"metric": "pseudo-masks/s over the 3680-image set (fused LayerCAM->normalise->threshold, 512x512, layers 3+4 fp32)",
+            "value": masks_per_s, "unit": "masks/s", "n_gpus": world, "scaling": "strong", "passes": passes,
+            "ms_per_pass": ms / passes, "images": n_images, "images_per_rank": len(range(rank, n_images, world)),
+            "gpix_per_s": masks_per_s * S * S / 1e9, "counters": last["res"]["counters"],
+            "api": "weaklysuperviseddl_b200.generate_pseudo_masks_sharded (i % world == rank, chunks of 128, 2 streams)",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_image": per_image, "peak_source": peak_src,
+                         "note": "per GPU: algorithmic bytes of the images a rank processed / the pass time (max over ranks); "
+                                 "both kernels of every call, the per-call control memset, the per-chunk counter sums and the "
+                                 "one host read at the end of the pass"}}
+
+
 def bench_layercam(args, lib, dev, rank, world):
-    steps, warmup = args.steps, args.warmup
-    core = bench_layercam_core(lib, dev, rank, world, steps, warmup)
+    passes = max(1, min(args.steps, 10))
+    core = bench_layercam_sharded(dev, rank, world, passes, 1)
+    chunk_core = bench_layercam_core(lib, dev, rank, world, 30, 5)  # round 1's resident-chunk loop, for continuity
     # end to end for this stage = images from the host through the classifier's hooks (cuDNN) to masks on the host
     pm = bench_pseudomask(argparse.Namespace(steps=20, warmup=4, no_cpu_baseline=True), dev, rank, world, S=LCAM["S"], B=16,
                           cpu_baseline=False)
     return {
-        "metric": "pseudo-masks/s", "value": core["value"], "unit": "masks/s", "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": core["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "metric": "pseudo-masks/s", "value": core["value"], "unit": "masks/s", "n_gpus": world, "steps": passes,
+        "warmup": 1, "ms_per_step": core["ms_per_pass"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[2]: fused LayerCAM->normalise->threshold, 512x512, image-sharded; "
-                               f"{LCAM['chunk']} images per step per GPU", "l2": core["l2"]},
-        "roofline": core["roofline"], "gpu_launches": 2 * steps, "extra": core,
+        "config": {"workload": "configs[2]: fused LayerCAM->normalise->threshold over a synthetic 3680-image Pet-sized set at "
+                               "512x512, image-sharded i % world == rank; one step = one pass over the set",
+                   "l2": "2 rotated resident chunks of 3.2 GB per rank"},
+        "roofline": core["roofline"], "gpu_launches": 2 * passes * ((core["images_per_rank"] + LCAM["chunk"] - 1) // LCAM["chunk"]),
+        "extra": {"sharded_pass": core, "resident_chunk_loop": chunk_core},
         "e2e": dict(pm["e2e"], stage_share=pm["stage_share"],
                     note="16x3x512x512 host images per step -> H2D -> ResNet-50 forward + backward to the layer3/layer4 hooks "
                          "(cuDNN, out of scope) -> fused LayerCAM -> mask -> keep_largest -> D2H masks"),
@@ -947,7 +1081,7 @@ def bench_trainstep(args, dev, rank, world):
     """BASELINE config 4: the weakly-supervised segmentation train step.  DeepLabV3-R50 (2 classes, random init, bf16
     autocast, cuDNN: out of scope by north_star) on 32x3x224x224 per GPU; pseudo-labels made ONCE (untimed) by the fused
     LayerCAM -> mask kernel from synthetic hooks; loss = CE + 0.1 cut + 0.5 mean boundary through WeakSupervisionLoss
-    (one fused pairwise launch); Adam; DistributedDataParallel over NCCL when world > 1.  Every step copies its images
+    (ONE launch: cross-entropy + cut + boundary, wsdl_weak_loss_fwd_bwd); Adam; DistributedDataParallel over NCCL when world > 1.  Every step copies its images
     and labels from pinned host memory and reads the loss back."""
     import torch
     import torch.distributed as dist
@@ -963,7 +1097,11 @@ def bench_trainstep(args, dev, rank, world):
     net = torchvision.models.segmentation.deeplabv3_resnet50(weights=None, weights_backbone=None, num_classes=2)
     net = net.to(dev).to(memory_format=fmt).train()
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index])
+        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], gradient_as_bucket_view=True)
+        if os.environ.get("WSDL_DDP_FP32") != "1":  # bf16 backbone: all-reduce the gradient buckets in bf16 as well
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
     crit = WeakSupervisionLoss()
     g = torch.Generator().manual_seed(11 + rank)
@@ -980,7 +1118,7 @@ def bench_trainstep(args, dev, rank, world):
 
     def step(measure=False):
         imgs = h_imgs.to(dev, non_blocking=True)  # NCHW for the pairwise kernels, channels-last copy for cuDNN
-        labels = h_labels.to(dev, non_blocking=True).long()
+        labels = h_labels.to(dev, non_blocking=True)  # u8 {0,1}: the fused loss reads them as they are
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = net(imgs.contiguous(memory_format=fmt))["out"]
@@ -1018,7 +1156,7 @@ def bench_trainstep(args, dev, rank, world):
         "data": "synthetic",
         "config": {"workload": "config 4: DeepLabV3-R50 (2 classes, random init) bf16 autocast, 32x3x224x224 per GPU, "
                                "pseudo-labels from the fused LayerCAM->mask kernels, loss = CE + 0.1 cut + 0.5 mean boundary "
-                               "(WeakSupervisionLoss: one fused pairwise launch), Adam" +
+                               "(WeakSupervisionLoss: one launch for all three terms on the bf16 logits), Adam" +
                                (", DistributedDataParallel over NCCL" if world > 1 else ""),
                    "l2": "activations of the backbone (> 126 MB) pass through L2 between the loss launches"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": h_imgs.numel() * 4 + h_labels.numel(),

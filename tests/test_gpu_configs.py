@@ -224,3 +224,40 @@ def test_generate_bg_cam_vs_oracle(golden_dir):
         assert (m_bg.cpu().double() - r_bg).abs().max().item() <= 1e-6
         assert (m_fg.cpu().double() - r_fg).abs().max().item() <= 1e-6
         assert m_bg.min().item() >= 0.0 and m_bg.max().item() <= 1.0
+
+
+# ------------------------------------------------------------------------------------------------ config 3
+def test_sharded_pseudo_masks_on_device(WF):
+    """generate_pseudo_masks_sharded with the fused launch: four simulated ranks (explicit rank / world, no process
+    group) partition 21 images; their union equals the single-rank run bit for bit and the masks equal the oracle's
+    outside the threshold band."""
+    from weaklysuperviseddl_b200.PsuedoMasks import generate_pseudo_masks_sharded
+
+    layers = ((64, 16, 16), (128, 8, 8))
+
+    def hooks(indices):
+        acts, grads = [], []
+        for (C, h, w) in layers:
+            a, g = [], []
+            for i in indices:
+                gen = torch.Generator().manual_seed(i)  # seed = image index (SURVEY.md 8d)
+                a.append(torch.randn(C, h, w, generator=gen).relu())
+                g.append(torch.randn(C, h, w, generator=gen) * 1e-3)
+            acts.append(torch.stack(a).cuda())
+            grads.append(torch.stack(g).cuda())
+        return acts, grads
+
+    single = generate_pseudo_masks_sharded(hooks, 21, (96, 96), chunk=8, rank=0, world=1, keep_largest_masks=True)
+    assert single["masks"].shape == (21, 96, 96) and single["counters"]["masks"] == 21
+    fg = 0
+    for r in range(4):
+        part = generate_pseudo_masks_sharded(hooks, 21, (96, 96), chunk=3, rank=r, world=4, keep_largest_masks=True)
+        assert part["indices"].tolist() == list(range(r, 21, 4))
+        for j, i in enumerate(part["indices"].tolist()):
+            assert torch.equal(part["masks"][j], single["masks"][i]), (r, i)
+        fg += part["counters"]["foreground_pixels"]
+    assert fg == single["counters"]["foreground_pixels"] == int(single["masks"].sum().item())
+    acts, grads = hooks([5])
+    ref = O.layercam_from_hooks([a.cpu() for a in acts], [g.cpu() for g in grads], (96, 96), dtype=torch.float64)[0]
+    plain = generate_pseudo_masks_sharded(hooks, 6, (96, 96), chunk=4, rank=0, world=1)["masks"][5]
+    assert_masks_match(plain, ref, 0.3)

@@ -66,6 +66,67 @@ def test_image_sharding_world2(tmp_path):
         assert torch.equal(m, (data[i] >= 0.5).to(torch.uint8))
 
 
+def _hooks_for(indices):
+    """Synthetic hooks, seed = image index, tiny shapes."""
+    acts, grads = [], []
+    for (C, h, w) in ((6, 5, 5), (4, 3, 3)):
+        a, g = [], []
+        for i in indices:
+            gen = torch.Generator().manual_seed(1000 + i)
+            a.append(torch.randn(C, h, w, generator=gen))
+            g.append(torch.randn(C, h, w, generator=gen) * 1e-3)
+        acts.append(torch.stack(a))
+        grads.append(torch.stack(g))
+    return acts, grads
+
+
+def _oracle_mask_fn(acts, grads):
+    from oracle import wsdl_oracle as O
+
+    cam = O.layercam_from_hooks(acts, grads, (24, 20))
+    return ((cam >= 0.3) & (cam > 0)).to(torch.uint8), ((cam - 0.3).abs() < 1e-6).sum().reshape(1)
+
+
+def _sharded_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from weaklysuperviseddl_b200.PsuedoMasks import generate_pseudo_masks_sharded
+
+        res = generate_pseudo_masks_sharded(_hooks_for, 23, (24, 20), chunk=4, mask_fn=_oracle_mask_fn)  # rank/world from the group
+        torch.save(res, os.path.join(out_dir, f"sharded{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_pseudo_masks_union_equals_single_rank(tmp_path):
+    """generate_pseudo_masks_sharded (the config-3 product entry) at world size 2 over gloo: the union of the two shards
+    is the single-rank result bit for bit, image by image, and both ranks agree on the all-reduced counters.  The fused
+    launch is replaced by the oracle (mask_fn) so that the host logic runs without a GPU; the GPU twin of this test is
+    tests/test_gpu_configs.py::test_sharded_pseudo_masks_on_device."""
+    from weaklysuperviseddl_b200.PsuedoMasks import generate_pseudo_masks_sharded
+
+    world = 2
+    mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    single = generate_pseudo_masks_sharded(_hooks_for, 23, (24, 20), chunk=5, rank=0, world=1, mask_fn=_oracle_mask_fn)
+    assert single["indices"].tolist() == list(range(23)) and single["counters"]["masks"] == 23
+    seen = {}
+    for r in range(world):
+        part = torch.load(os.path.join(tmp_path, f"sharded{r}.pt"))
+        assert part["counters"] == single["counters"]  # summed over ranks == the single-rank totals
+        assert part["indices"].tolist() == list(range(r, 23, world))
+        for j, i in enumerate(part["indices"].tolist()):
+            seen[i] = part["masks"][j]
+    assert sorted(seen) == list(range(23))
+    for i in range(23):
+        assert torch.equal(seen[i], single["masks"][i]), i
+    # a sink takes the masks instead of the return value
+    got = {}
+    res = generate_pseudo_masks_sharded(_hooks_for, 7, (24, 20), chunk=3, rank=0, world=1, mask_fn=_oracle_mask_fn,
+                                        sink=lambda idx, m: got.update({i: m[j] for j, i in enumerate(idx)}))
+    assert res["masks"] is None and sorted(got) == list(range(7)) and torch.equal(got[3], single["masks"][3])
+
+
 def test_chunking_and_argument_checks():
     idx = list(sharding.shard_indices(10, 1, 4))
     assert idx == [1, 5, 9]

@@ -4,11 +4,13 @@ components on the GPU as well (csrc/ccl.cu).  One device->host copy per loader b
 from __future__ import annotations
 
 import os
+from contextlib import nullcontext as _nullcontext
 
 import numpy as np
 import torch
 
 from . import functional as WF
+from . import sharding
 
 CONTENT_ROOT = "/content"  # the reference hard-codes Colab's /content (PsuedoMasks.py:31-32)
 MAX_IMAGES = 500           # PsuedoMasks.py:49-50
@@ -110,3 +112,63 @@ def generate_pseudo_masks(
     print(f"Images saved to: {image_save_dir}")
     generate_pseudo_masks.last_near_threshold_pixels = int(near_total.item())
     return image_save_dir, save_dir
+
+
+def generate_pseudo_masks_sharded(hook_source, n_images, out_size, cam_thresh=0.3, alpha=1.0, keep_largest_masks=False,
+                                  chunk=128, rank=None, world=None, sink=None, mask_fn=None, device=None, streams=1):
+    """Pseudo-mask generation over a whole image set, sharded by image across the GPUs of a box (BASELINE config 3;
+    the per-image loop of PsuedoMasks.py:41-76 without its 500-image cap and without files).
+
+    One process per GPU.  Image i belongs to rank i % world (`sharding.shard_indices`); a rank walks its images in
+    resident chunks of `chunk`: `hook_source(indices)` returns the hooked activations and gradients of those images
+    (lists of (len(indices), C_l, h_l, w_l) tensors -- in the reference's pipeline the classifier's forward/backward
+    through LayerCAMGenerator's hooks, in the benchmark synthetic hooks seeded by image index), the fused LayerCAM ->
+    normalise -> upsample -> threshold launch turns them into u8 masks (optionally reduced to their largest
+    component), and `sink(indices, masks)` takes them (default: they are kept and returned).  No pixel ever crosses
+    ranks: the only collective is the sum of three counters at the end.
+
+    `streams=2` alternates consecutive chunks between two CUDA streams, so that the (instruction-bound, L2-resident)
+    upsample / threshold kernel of one chunk runs under the (HBM-bound) channel sum of the next.
+    `mask_fn(acts, grads) -> (mask u8 (B,H,W), near_threshold_count)` replaces the fused launch (the CPU tests hand in
+    the oracle to check the sharding logic without a GPU).  Returns {"indices", "masks" (None with a sink),
+    "counters": {"masks", "near_threshold_pixels", "foreground_pixels"} summed over ranks}."""
+    if rank is None or world is None:
+        rank, world = sharding.rank_world()
+    mine = sharding.shard_indices(int(n_images), rank, world)
+    if mask_fn is None:
+        def mask_fn(acts, grads):
+            _, m, near = WF.layercam_fused(acts, grads, out_size, alpha=alpha, thresh=cam_thresh, want_cam=False)
+            return m, near
+    kept, n_masks = [], 0
+    lanes = max(1, int(streams)) if torch.cuda.is_available() else 1
+    side = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else [None]
+    near_total, fg_total = [None] * lanes, [None] * lanes
+    cur = torch.cuda.current_stream() if lanes > 1 else None
+    for s_ in side:
+        if s_ is not None:
+            s_.wait_stream(cur)
+    for c, idx in enumerate(sharding.chunk(mine, int(chunk))):
+        lane = c % lanes
+        with torch.cuda.stream(side[lane]) if side[lane] is not None else _nullcontext():
+            acts, grads = hook_source(list(idx))
+            masks, near = mask_fn(acts, grads)
+            if keep_largest_masks:
+                masks = WF.keep_largest(masks)
+            near_total[lane] = near.clone() if near_total[lane] is None else near_total[lane] + near
+            fg = masks.sum(dtype=torch.int64)
+            fg_total[lane] = fg if fg_total[lane] is None else fg_total[lane] + fg
+            n_masks += masks.shape[0]
+            if sink is not None:
+                sink(list(idx), masks)
+            else:
+                kept.append(masks)
+    for s_ in side:
+        if s_ is not None:
+            cur.wait_stream(s_)
+    dev = device if device is not None else (kept[0].device if kept else None)
+    local = [n_masks, sum(int(t.sum().item()) for t in near_total if t is not None),
+             sum(int(t.item()) for t in fg_total if t is not None)]  # the only host reads: after the last chunk
+    total = sharding.all_reduce_counters(local, device=dev if (dev is not None and torch.device(dev).type == "cuda") else None)
+    return {"indices": torch.tensor(list(mine), dtype=torch.int64),
+            "masks": (torch.cat(kept) if kept else None) if sink is None else None,
+            "counters": {"masks": total[0], "near_threshold_pixels": total[1], "foreground_pixels": total[2]}}

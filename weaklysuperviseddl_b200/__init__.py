@@ -10,7 +10,7 @@ from .AlternatingDirectionCutLoss import (  # noqa: F401
     LocalNormalizedCutLoss, compute_affinities, refine_pseudo_mask, refine_pseudo_masks_batched)
 from .ExtraUtilities import compute_iou_and_acc, compute_iou_and_acc_batched  # noqa: F401
 from .LayerCAM import LayerCAMGenerator, evaluate_layercam_on_test_set  # noqa: F401
-from .PsuedoMasks import generate_pseudo_masks, keep_largest  # noqa: F401
+from .PsuedoMasks import generate_pseudo_masks, generate_pseudo_masks_sharded, keep_largest  # noqa: F401
 from .WeakSupervisionLoss import WeakSupervisionLoss  # noqa: F401
 
 __version__ = "0.1.0"
