@@ -874,7 +874,7 @@ def bench_layercam_sharded(dev, rank, world, passes, warmup_passes):
 
     def one_pass():
         last["res"] = generate_pseudo_masks_sharded(hooks, n_images, (S, S), cam_thresh=LCAM["thresh"], alpha=LCAM["alpha"],
-                                                    chunk=chunk, rank=rank, world=world, streams=2,
+                                                    chunk=chunk, rank=rank, world=world, streams=2, count_foreground=False,
                                                     sink=lambda idx, m: last.__setitem__("mask", m))
 
     ms, _ = _timed(lambda n: [one_pass() for _ in range(n)], warmup_passes, passes, dev, world, None)

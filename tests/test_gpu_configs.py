@@ -247,11 +247,11 @@ def test_sharded_pseudo_masks_on_device(WF):
             grads.append(torch.stack(g).cuda())
         return acts, grads
 
-    single = generate_pseudo_masks_sharded(hooks, 21, (96, 96), chunk=8, rank=0, world=1, keep_largest_masks=True)
+    single = generate_pseudo_masks_sharded(hooks, 21, (96, 96), chunk=8, rank=0, world=1, keep_largest_masks=True, count_foreground=True)
     assert single["masks"].shape == (21, 96, 96) and single["counters"]["masks"] == 21
     fg = 0
     for r in range(4):
-        part = generate_pseudo_masks_sharded(hooks, 21, (96, 96), chunk=3, rank=r, world=4, keep_largest_masks=True)
+        part = generate_pseudo_masks_sharded(hooks, 21, (96, 96), chunk=3, rank=r, world=4, keep_largest_masks=True, count_foreground=True, streams=2)
         assert part["indices"].tolist() == list(range(r, 21, 4))
         for j, i in enumerate(part["indices"].tolist()):
             assert torch.equal(part["masks"][j], single["masks"][i]), (r, i)

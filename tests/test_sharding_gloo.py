@@ -93,7 +93,7 @@ def _sharded_worker(rank, world, port, out_dir):
     try:
         from weaklysuperviseddl_b200.PsuedoMasks import generate_pseudo_masks_sharded
 
-        res = generate_pseudo_masks_sharded(_hooks_for, 23, (24, 20), chunk=4, mask_fn=_oracle_mask_fn)  # rank/world from the group
+        res = generate_pseudo_masks_sharded(_hooks_for, 23, (24, 20), chunk=4, mask_fn=_oracle_mask_fn, count_foreground=True)  # rank/world from the group
         torch.save(res, os.path.join(out_dir, f"sharded{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -108,7 +108,7 @@ def test_sharded_pseudo_masks_union_equals_single_rank(tmp_path):
 
     world = 2
     mp.spawn(_sharded_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    single = generate_pseudo_masks_sharded(_hooks_for, 23, (24, 20), chunk=5, rank=0, world=1, mask_fn=_oracle_mask_fn)
+    single = generate_pseudo_masks_sharded(_hooks_for, 23, (24, 20), chunk=5, rank=0, world=1, mask_fn=_oracle_mask_fn, count_foreground=True)
     assert single["indices"].tolist() == list(range(23)) and single["counters"]["masks"] == 23
     seen = {}
     for r in range(world):

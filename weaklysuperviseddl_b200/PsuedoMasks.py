@@ -115,7 +115,8 @@ def generate_pseudo_masks(
 
 
 def generate_pseudo_masks_sharded(hook_source, n_images, out_size, cam_thresh=0.3, alpha=1.0, keep_largest_masks=False,
-                                  chunk=128, rank=None, world=None, sink=None, mask_fn=None, device=None, streams=1):
+                                  chunk=128, rank=None, world=None, sink=None, mask_fn=None, device=None, streams=1,
+                                  count_foreground=False):
     """Pseudo-mask generation over a whole image set, sharded by image across the GPUs of a box (BASELINE config 3;
     the per-image loop of PsuedoMasks.py:41-76 without its 500-image cap and without files).
 
@@ -131,44 +132,71 @@ def generate_pseudo_masks_sharded(hook_source, n_images, out_size, cam_thresh=0.
     upsample / threshold kernel of one chunk runs under the (HBM-bound) channel sum of the next.
     `mask_fn(acts, grads) -> (mask u8 (B,H,W), near_threshold_count)` replaces the fused launch (the CPU tests hand in
     the oracle to check the sharding logic without a GPU).  Returns {"indices", "masks" (None with a sink),
-    "counters": {"masks", "near_threshold_pixels", "foreground_pixels"} summed over ranks}."""
+    "counters": {"masks", "near_threshold_pixels", "foreground_pixels"} summed over ranks}; `count_foreground=True`
+    adds the per-chunk pixel count (one extra read of every mask; the counter is 0 otherwise)."""
     if rank is None or world is None:
         rank, world = sharding.rank_world()
     mine = sharding.shard_indices(int(n_images), rank, world)
-    if mask_fn is None:
-        def mask_fn(acts, grads):
-            _, m, near = WF.layercam_fused(acts, grads, out_size, alpha=alpha, thresh=cam_thresh, want_cam=False)
-            return m, near
-    kept, n_masks = [], 0
-    lanes = max(1, int(streams)) if torch.cuda.is_available() else 1
+    own_kernel = mask_fn is None
+    out_h, out_w = int(out_size[0]), int(out_size[1])
+    lanes = max(1, int(streams)) if (own_kernel and torch.cuda.is_available()) else 1
     side = [torch.cuda.Stream() for _ in range(lanes)] if lanes > 1 else [None]
     near_total, fg_total = [None] * lanes, [None] * lanes
+    # buffers are made once: the masks of the whole shard (or one chunk-sized buffer per stream when a sink takes them),
+    # one workspace and one near-threshold counter per stream; the kernels write straight into them
+    result, lane_mask, lane_ws, n_masks, pos = None, [None] * lanes, [None] * lanes, 0, 0
     cur = torch.cuda.current_stream() if lanes > 1 else None
     for s_ in side:
         if s_ is not None:
             s_.wait_stream(cur)
+    kept = []
     for c, idx in enumerate(sharding.chunk(mine, int(chunk))):
         lane = c % lanes
         with torch.cuda.stream(side[lane]) if side[lane] is not None else _nullcontext():
             acts, grads = hook_source(list(idx))
-            masks, near = mask_fn(acts, grads)
-            if keep_largest_masks:
-                masks = WF.keep_largest(masks)
-            near_total[lane] = near.clone() if near_total[lane] is None else near_total[lane] + near
-            fg = masks.sum(dtype=torch.int64)
-            fg_total[lane] = fg if fg_total[lane] is None else fg_total[lane] + fg
-            n_masks += masks.shape[0]
-            if sink is not None:
-                sink(list(idx), masks)
+            n = len(idx)
+            if own_kernel:
+                dev_ = acts[0].device
+                if lane_ws[lane] is None:  # allocate on the caller's stream: the buffers outlive the side streams' work
+                    with torch.cuda.stream(cur) if cur is not None else _nullcontext():
+                        if sink is None and result is None:
+                            result = torch.empty((len(mine), out_h, out_w), dtype=torch.uint8, device=dev_)
+                        if sink is not None:
+                            lane_mask[lane] = torch.empty((int(chunk), out_h, out_w), dtype=torch.uint8, device=dev_)
+                        shapes = [tuple(a.shape[1:]) for a in acts]
+                        lane_ws[lane] = torch.empty(WF.layercam_workspace_bytes(shapes, int(chunk), acts[0].dtype),
+                                                    dtype=torch.uint8, device=dev_)
+                        near_total[lane] = torch.zeros(1, dtype=torch.int64, device=dev_)
+                    if side[lane] is not None:
+                        side[lane].wait_stream(cur)  # the zero fill of the counter
+                dst = result[pos:pos + n] if sink is None else lane_mask[lane][:n]
+                _, masks, _ = WF.layercam_fused(acts, grads, (out_h, out_w), alpha=alpha, thresh=cam_thresh, want_cam=False,
+                                                near_count=near_total[lane], mask_out=dst, workspace=lane_ws[lane])
+                if keep_largest_masks:
+                    masks = WF.keep_largest(masks, out=masks)
             else:
-                kept.append(masks)
+                masks, near = mask_fn(acts, grads)
+                near_total[lane] = near.clone() if near_total[lane] is None else near_total[lane] + near
+                if keep_largest_masks:
+                    masks = WF.keep_largest(masks)
+                if sink is None:
+                    kept.append(masks)
+            if count_foreground:
+                fg = masks.sum(dtype=torch.int64)
+                fg_total[lane] = fg if fg_total[lane] is None else fg_total[lane] + fg
+            n_masks += n
+            pos += n
+            if sink is not None:
+                sink(list(idx), masks)  # with several streams the buffer is reused `streams` chunks later
     for s_ in side:
         if s_ is not None:
             cur.wait_stream(s_)
-    dev = device if device is not None else (kept[0].device if kept else None)
+    if not own_kernel and sink is None:
+        result = torch.cat(kept) if kept else None
+    dev = device if device is not None else (result.device if result is not None else None)
     local = [n_masks, sum(int(t.sum().item()) for t in near_total if t is not None),
              sum(int(t.item()) for t in fg_total if t is not None)]  # the only host reads: after the last chunk
     total = sharding.all_reduce_counters(local, device=dev if (dev is not None and torch.device(dev).type == "cuda") else None)
     return {"indices": torch.tensor(list(mine), dtype=torch.int64),
-            "masks": (torch.cat(kept) if kept else None) if sink is None else None,
+            "masks": result if sink is None else None,
             "counters": {"masks": total[0], "near_threshold_pixels": total[1], "foreground_pixels": total[2]}}

@@ -44,10 +44,14 @@ def layercam_fused(
     want_mask: Optional[bool] = None,
     near_band: float = NEAR_BAND,
     near_count: Optional[torch.Tensor] = None,
+    mask_out: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
 ):
     """LayerCAM.py:52-76 (+ PsuedoMasks.py:59-62 when `thresh` is given) in two kernel launches.
 
     acts/grads: per target layer, (B, C_l, h_l, w_l) CUDA tensors of one dtype (f32 / bf16 / f16).
+    `mask_out` (contiguous (B,H,W) u8) and `workspace` (u8, at least layercam_workspace_bytes) let a caller that walks
+    many chunks reuse its buffers instead of allocating per call; `near_count` (int64, 1 element) is ADDED to.
     Returns (cam (B,H,W) f32 or None, mask (B,H,W) u8 or None, near_count u64 tensor or None)."""
     if len(acts) != len(grads) or len(acts) == 0:
         raise ValueError("need one activation and one gradient per target layer")
@@ -84,9 +88,18 @@ def layercam_fused(
         nbytes = lib.wsdl_layercam_workspace_bytes(Cs, hs, ws, n, B, code)
         if nbytes == 0:
             raise _native.WsdlError("wsdl_layercam_workspace_bytes rejected the shapes")
-        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if workspace is None:
+            workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        elif workspace.dtype != torch.uint8 or workspace.numel() < nbytes or workspace.device != dev or not workspace.is_contiguous():
+            raise ValueError(f"workspace must be a contiguous uint8 CUDA tensor of at least {nbytes} bytes")
         cam = torch.empty((B, out_h, out_w), dtype=torch.float32, device=dev) if want_cam else None
-        mask = torch.empty((B, out_h, out_w), dtype=torch.uint8, device=dev) if want_mask else None
+        if want_mask and mask_out is not None:
+            if (mask_out.dtype != torch.uint8 or tuple(mask_out.shape) != (B, out_h, out_w) or not mask_out.is_contiguous()
+                    or mask_out.device != dev):
+                raise ValueError(f"mask_out must be a contiguous uint8 CUDA tensor of shape {(B, out_h, out_w)}")
+            mask = mask_out
+        else:
+            mask = torch.empty((B, out_h, out_w), dtype=torch.uint8, device=dev) if want_mask else None
         if near_count is None and thresh is not None:
             near_count = torch.zeros(1, dtype=torch.int64, device=dev)
         rc = lib.wsdl_layercam_fused(
@@ -99,7 +112,7 @@ def layercam_fused(
             cam.data_ptr() if cam is not None else None,
             mask.data_ptr() if mask is not None else None,
             near_count.data_ptr() if (near_count is not None and thresh is not None) else None,
-            workspace.data_ptr(), nbytes, _stream_ptr(dev),
+            workspace.data_ptr(), workspace.numel(), _stream_ptr(dev),
         )
     _native.check(rc, "wsdl_layercam_fused")
     return cam, mask, near_count
@@ -249,9 +262,17 @@ def affinities(images: torch.Tensor, sigma_color=0.1, sigma_space=5, window_size
     return out
 
 
-def keep_largest(mask: torch.Tensor, return_area: bool = False):
+def layercam_workspace_bytes(layer_shapes: Sequence[Tuple[int, int, int]], B: int, dtype=torch.float32) -> int:
+    """Workspace of layercam_fused for per-layer (C, h, w) hooks of a batch of B."""
+    n = len(layer_shapes)
+    IntArr = ctypes.c_int * n
+    return int(_native.lib().wsdl_layercam_workspace_bytes(IntArr(*[s[0] for s in layer_shapes]), IntArr(*[s[1] for s in layer_shapes]),
+                                                           IntArr(*[s[2] for s in layer_shapes]), n, int(B), _DTYPE_CODE[dtype]))
+
+
+def keep_largest(mask: torch.Tensor, return_area: bool = False, out: Optional[torch.Tensor] = None):
     """PsuedoMasks.py:15-21 on the GPU: (B,H,W) or (H,W) u8/bool CUDA mask -> same shape u8 {0,1} holding only
-    the largest 8-connected component (ties: first in raster order)."""
+    the largest 8-connected component (ties: first in raster order).  `out` may be the (u8, contiguous) input itself."""
     _require_cuda(mask, "mask")
     single = mask.dim() == 2
     m = mask.unsqueeze(0) if single else mask
@@ -262,7 +283,12 @@ def keep_largest(mask: torch.Tensor, return_area: bool = False):
     B, H, W = m.shape
     dev = m.device
     lib = _native.lib()
-    out = torch.empty_like(m)
+    if out is None:
+        out = torch.empty_like(m)
+    else:
+        out = out.unsqueeze(0) if single else out
+        if out.dtype != torch.uint8 or out.shape != m.shape or not out.is_contiguous() or out.device != dev:
+            raise ValueError("out must be a contiguous uint8 CUDA tensor of the mask's shape")
     area = torch.empty(B, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib.wsdl_keep_largest_workspace_bytes(B, H, W)
