@@ -197,6 +197,25 @@ int wsdl_labels_from_masks(const uint8_t* mask, int B, int H, int W, int out_siz
 int wsdl_iou_acc_counts(const void* pred, const void* truth, int B, size_t n, int elem, unsigned long long* counts,
                         void* stream);
 
+/* refine_pseudo_mask (AlternatingDirectionCutLoss.py:709-767) for a batch of independent images, the element-wise half
+ * of a step: X (B,2,H,W) free variable, S = softmax(model(image)) (B,2,H,W).  One call FINISHES step `step` and BEGINS
+ * the next one in a single pass:
+ *   with g_cut != NULL: d/dXn of  KL(S || Xn) + lam * kl_in[b] / (loss_cut[b] + 1e-6) * cut_b  (g_cut = d cut_b / d Xn for an
+ *     upstream gradient of 1, loss_cut: the per-image cut losses -- both from one wsdl_pairwise_fwd_bwd call on the Xn this
+ *     function wrote last time, inner_softmax = 1, divide_by_c = 1, per_image_loss = 1), through the softmax, Adam update
+ *     (torch defaults' arithmetic; `step` is Adam's 1-based step count) of X, exp_avg, exp_avg_sq in place;
+ *   always: Xn_out = softmax(X), kl_out[b] = sum S (log S - log(Xn + 1e-8)) of image b (:737-740), and, when mask_out is
+ *     given, mask_out (B,H,W) = (Xn[:,1] > threshold) as 0 / 1 floats (:759-760).
+ * The first call of a refinement passes g_cut = NULL (nothing to finish yet).  A step is this launch + the cut launch:
+ * the dynamic weight (:748, two host reads per step in the reference) never leaves the device.
+ * workspace >= wsdl_refine_workspace_bytes(), prepared as for the pairwise calls (0: the call zeroes its tickets). */
+size_t wsdl_refine_workspace_bytes(int B, int H, int W);
+
+int wsdl_refine_step(float* X, const float* S, const float* g_cut, const float* loss_cut, const float* kl_in, float* exp_avg,
+                     float* exp_avg_sq, float* Xn_out, float* kl_out, float* mask_out, int B, int H, int W, float lam,
+                     float lr, float beta1, float beta2, float eps, int step, float threshold, void* workspace,
+                     size_t workspace_bytes, int prepared, void* stream);
+
 /* Scale of a saved gradient by a device scalar (autograd backward of the fused launch, whose
  * gradient was computed for an upstream gradient of 1): dst[i] = src[i] * scale[per ? i / per : 0].
  * dst may alias src. */

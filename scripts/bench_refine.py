@@ -23,3 +23,13 @@ for fn_name in ("per-image loop", "batched"):
             out = torch.stack([refine_pseudo_mask(seg, images[i], masks[i], 0.1, 0.3, 1e-4, steps) for i in range(N)])
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"{fn_name:15s}: {dt*1e3:8.2f} ms for {N} images x {steps} steps  ({N/dt:8.1f} images/s)  fg fraction {out.mean().item():.4f}")
+
+# the step loop alone (one CUDA graph: 2 x steps + 1 launches), CUDA events around 20 replays
+from weaklysuperviseddl_b200 import AlternatingDirectionCutLoss as ADC
+ref = next(r for k, r in ADC._REFINERS.items() if k[1] == N)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); e0.record()
+for _ in range(20):
+    ref.graph.replay()
+e1.record(); torch.cuda.synchronize()
+print(f"captured step loop  : {e0.elapsed_time(e1) / 20:8.3f} ms per {steps}-step refinement of {N} images ({2 * steps + 1} launches + 2 memsets)")

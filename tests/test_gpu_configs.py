@@ -135,6 +135,26 @@ def test_refine_soft_state_vs_fp64(golden_dir, steps, lam, thr, lr):
     assert (out[0].cpu().numpy() != d[f"refined_s{steps}"]).mean() <= 0.002
 
 
+def test_refine_graph_replay_equals_direct_launches(golden_dir):
+    """The captured step loop (one CUDA graph per shape / hyper-parameter set, replayed on later calls) gives the same
+    bits as launching the 2 * steps + 1 kernels directly, call after call, and B = 1 equals the batched run's image."""
+    from weaklysuperviseddl_b200.AlternatingDirectionCutLoss import refine_pseudo_mask, refine_pseudo_masks_batched
+
+    torch.manual_seed(11)
+    seg = FixedLogitsNet().eval().cuda()
+    gen = torch.Generator().manual_seed(6)
+    images = smooth_images(gen, 4, 64, 80).cuda()
+    masks = ((torch.rand(4, 64, 80, generator=gen) > 0.5).long() * 255).cuda()
+    a = refine_pseudo_masks_batched(seg, images, masks, num_steps=7, return_state=True, use_graph=True)
+    b = refine_pseudo_masks_batched(seg, images, masks, num_steps=7, return_state=True, use_graph=False)
+    c = refine_pseudo_masks_batched(seg, images, masks, num_steps=7, return_state=True, use_graph=True)  # cached graph
+    for x, y, z in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(x, z)
+    assert a[0].shape == (4, 64, 80) and set(a[0].unique().tolist()) <= {0.0, 1.0}
+    one = refine_pseudo_mask(seg, images[2], masks[2], num_steps=7)
+    assert one.shape == (64, 80) and (one != a[0][2]).float().mean().item() <= 1e-3  # S of a batch of one: cuDNN may differ in the last bit
+
+
 # ------------------------------------------------------------------------------------------------ boundary callables
 class _Loader:
     """Batch-size-1 loader in the reference's format: (img (1,3,H,W), (label (1,), true_mask (1,1,h,w)))

@@ -79,6 +79,12 @@ SIGNATURES = {
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p],
     ),
+    "wsdl_refine_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "wsdl_refine_step": (
+        ctypes.c_int,
+        [ctypes.c_void_p] * 10 + [ctypes.c_int] * 3 + [ctypes.c_float] * 5 + [ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
+                                                                           ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p],
+    ),
     "wsdl_scale": (
         ctypes.c_int,
         [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p],
