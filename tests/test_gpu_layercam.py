@@ -88,6 +88,54 @@ def test_random_shapes(WF, case, alpha, mode):
     assert torch.equal(mask, mask2)
 
 
+# small batches take the one-launch cluster path (csrc/layercam.cu: layercam_cluster_kernel): 16 CTAs per image meet
+# through distributed shared memory.  Eligible: <= 4 layers, low-resolution maps of <= 1024 pixels (a multiple of the
+# 128-bit vector), <= 12 MB of hooks per image, B <= 16.
+CLUSTER_SHAPES = [
+    (1, [(1024, 14, 14), (2048, 14, 14)], (224, 224)),                       # the reference's own call: one image
+    (8, [(1024, 14, 14), (2048, 14, 14)], (224, 224)),                       # BASELINE config 1
+    (5, [(512, 28, 28), (1024, 14, 14), (2048, 14, 14)], (224, 224)),        # the variant's three layers
+    (2, [(64, 16, 16)], (100, 75)),                                          # single layer, ragged output
+    (4, [(32, 32, 32), (64, 16, 16), (128, 8, 8), (256, 8, 8)], (256, 256)), # four stages
+    (16, [(8, 2, 2), (40, 4, 4)], (33, 1021)),                               # tiny maps, widest output, fewer channels than ranks
+    (3, [(1, 8, 8), (2, 4, 4), (700, 12, 12)], (64, 64)),                    # one channel: most ranks of the cluster idle
+]
+
+
+@pytest.mark.parametrize("case", range(len(CLUSTER_SHAPES)))
+@pytest.mark.parametrize("alpha,mode", [(1.0, 0), (0.5, 0), (2.0, 1)])
+def test_small_batch_cluster_path(WF, case, alpha, mode):
+    B, layers, out = CLUSTER_SHAPES[case]
+    gen = torch.Generator().manual_seed(500 + case)
+    acts, grads = [], []
+    for (C, h, w) in layers:
+        a, g = synth_act_grad(gen, B, C, h, w)
+        acts.append(a)
+        grads.append(g)
+    cam, mask, near = WF.layercam_fused(_cuda(acts), _cuda(grads), out, alpha=alpha, alpha_mode=mode, thresh=0.3)
+    ref64 = O.layercam_from_hooks(acts, grads, out, alpha=alpha, alpha_mode=mode, dtype=torch.float64)
+    assert_cam_close(cam, ref64, f"cluster case {case}")
+    assert_masks_match(mask, ref64, 0.3)
+    assert int(near.item()) == int(((cam - 0.3).abs() < 1e-6).sum().item())
+    _, mask2, _ = WF.layercam_fused(_cuda(acts), _cuda(grads), out, alpha=alpha, alpha_mode=mode, thresh=0.3, want_cam=False)
+    assert torch.equal(mask, mask2)
+    cam3, _, _ = WF.layercam_fused(_cuda(acts), _cuda(grads), out, alpha=alpha, alpha_mode=mode)
+    assert torch.equal(cam, cam3)  # deterministic: peers are added in rank order
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_half_inputs_cluster_path(WF, dtype):
+    gen = torch.Generator().manual_seed(17)
+    acts, grads = [], []
+    for (C, h, w) in [(256, 16, 16), (512, 8, 8)]:
+        a, g = synth_act_grad(gen, 3, C, h, w)
+        acts.append(a.to(dtype))
+        grads.append((g * 100).to(dtype))
+    cam, _, _ = WF.layercam_fused(_cuda(acts), _cuda(grads), (128, 128))
+    ref = O.layercam_from_hooks([a.float() for a in acts], [g.float() for g in grads], (128, 128), dtype=torch.float64)
+    assert_cam_close(cam, ref, str(dtype))
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_half_inputs(WF, dtype):
     gen = torch.Generator().manual_seed(7)

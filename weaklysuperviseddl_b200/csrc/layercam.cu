@@ -21,9 +21,14 @@
 //     (ATen/native/UpSample.h: horizontal first, then vertical).  Layers are averaged,
 //     clamp(0) ** alpha applied and the pixel is thresholded; only the u8 mask (and, on
 //     request, the f32 CAM) ever reaches HBM.
+#include <cooperative_groups.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace wsdl {
+
+namespace cg = cooperative_groups;
 
 constexpr int LC_THREADS = 256;
 constexpr int LC_UNROLL = 4;
@@ -486,6 +491,248 @@ __global__ void threshold_mask_kernel(const float* __restrict__ cam, size_t n, f
 }
 
 // ------------------------------------------------------------------------------------------
+// Small batches: ONE launch, one thread-block cluster of 16 CTAs per image.
+//
+// The reference calls generate() one image at a time (LayerCAM.py:38) and BASELINE config 1 is B = 8: a few MB of
+// hooks per call, where the two-kernel path above spends its time on launches, the control memset and the tickets
+// through L2 (35 us for 6 us of HBM traffic at B = 8).  Here the 16 CTAs of a cluster share an image: they split the
+// channels of its layers, meet through DISTRIBUTED SHARED MEMORY (each layer's leader CTA adds its peers' partial maps
+// in rank order, applies the outer ReLU and the per-image min-max), every CTA copies the finished low-resolution maps
+// from the leaders, and each upsamples / fuses / thresholds a sixteenth of the output rows.  No workspace, no memset,
+// no atomics except the near-threshold counter.
+// ------------------------------------------------------------------------------------------
+constexpr int SC_CLUSTER = 16;
+constexpr int SC_MAX_LOW = 4096;  // floats of all low-resolution maps of one image (16 KB)
+constexpr int SC_MAX_HW = 1024;   // pixels of one low-resolution map
+// channels in flight per thread (template SC_UNROLL): 16 SMs must pull a whole image, so bytes in flight decide (Little's
+// law).  8 for up to 8 images (13.4 vs 15.1 us at B = 1, 17.3 vs 18.1 us at B = 8), 4 beyond (23 vs 31 us at B = 16: two
+// waves of clusters).
+
+struct ScParams {
+  const void* act[4];
+  const void* grad[4];
+  int C[4], h[4], w[4], hw[4], low_off[4];
+  int first[4], count[4], ch_per_cta[4];  // the cluster ranks that work on a layer, channels each of them takes
+  int rank_layer[SC_CLUSTER];
+  float scale_y[4], scale_x[4];
+  int n_layers, B, out_h, out_w, rows_per_cta;
+  float alpha;
+  int alpha_mode;
+  float thresh, band, inv_layers, n_layers_f;
+  float* cam_out;
+  uint8_t* mask_out;
+  unsigned long long* near_count;
+  int vec_ok;
+};
+
+template <int DTYPE, int VEC, int NL, int SC_UNROLL>
+__global__ void __launch_bounds__(LC_THREADS) layercam_cluster_kernel(const __grid_constant__ ScParams P) {
+  constexpr int ESIZE = (DTYPE == WSDL_F32) ? 4 : 2;
+  __shared__ __align__(16) float s_acc[LC_THREADS * VEC];
+  __shared__ __align__(16) float s_part[SC_MAX_HW];  // this CTA's channel-partial map; at a leader then the finished map
+  __shared__ __align__(16) float s_low[SC_MAX_LOW];  // all finished maps of the image
+  __shared__ float s_red[16];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / SC_CLUSTER;
+  const int tid = threadIdx.x;
+  const int l = P.rank_layer[rank];
+  const int hw = P.hw[l], npg = hw / VEC;
+  const int slices = min(LC_THREADS / npg, P.ch_per_cta[l]);
+  const int slice = tid / npg, p = tid - slice * npg;
+  const bool active = slice < slices;
+
+  // ---- channel sum of this CTA's share: relu(grad * act), LayerCAM.py:57 ----
+  float acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  if (active) {
+    const int j = rank - P.first[l];
+    const int c_begin = j * P.ch_per_cta[l], c_end = min(P.C[l], c_begin + P.ch_per_cta[l]);
+    const size_t plane_bytes = (size_t)hw * ESIZE;
+    const size_t base = ((size_t)b * P.C[l] * hw + (size_t)p * VEC) * ESIZE;
+    const char* pa = reinterpret_cast<const char*>(P.act[l]) + base;
+    const char* pg = reinterpret_cast<const char*>(P.grad[l]) + base;
+    for (int c = c_begin + slice; c < c_end; c += slices * SC_UNROLL) {
+      float a[SC_UNROLL][VEC], g[SC_UNROLL][VEC];
+#pragma unroll
+      for (int u = 0; u < SC_UNROLL; ++u) {
+        const int cc = c + u * slices;
+        if (cc < c_end) {
+          load_vec<DTYPE, VEC>(pa + (size_t)cc * plane_bytes, a[u]);
+          load_vec<DTYPE, VEC>(pg + (size_t)cc * plane_bytes, g[u]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) a[u][v] = 0.f, g[u][v] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < SC_UNROLL; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += fmaxf(g[u][v] * a[u][v], 0.f);
+    }
+  }
+  if (active && slice > 0) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s_acc[(slice * npg + p) * VEC + v] = acc[v];
+  }
+  __syncthreads();
+  if (active && slice == 0) {  // slices of this CTA in a fixed order
+    for (int s = 1; s < slices; ++s)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] += s_acc[(s * npg + p) * VEC + v];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) s_part[p * VEC + v] = acc[v];
+  }
+  cluster.sync();  // every CTA's partial map is in its shared memory
+
+  // ---- the layer's leader: peers in rank order, outer ReLU (LayerCAM.py:59), per-image min-max (:62-67) ----
+  if (rank == P.first[l]) {
+    float x[4], mn = __int_as_float(0x7f800000), mx = 0.f;  // up to 4 pixels per thread (hw <= 1024)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * LC_THREADS;
+      x[q] = 0.f;
+      if (i < hw) {
+        float sum = 0.f;
+        for (int j = 0; j < P.count[l]; ++j) sum += cluster.map_shared_rank(s_part, rank + j)[i];
+        x[q] = fmaxf(sum, 0.f);
+        mn = fminf(mn, x[q]), mx = fmaxf(mx, x[q]);
+      }
+    }
+    cluster.sync();  // (leaders and non-leaders meet here: the peers' partial maps have been read)
+    MinMax mm = block_minmax(mn, mx, s_red);
+    const float den = (mm.mx - mm.mn) + 1e-8f;  // max is taken after the subtraction in the reference
+    if (P.alpha_mode == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + q * LC_THREADS;
+        if (i < hw) s_part[i] = __fdiv_rn(x[q] - mm.mn, den);
+      }
+    } else {  // variant (AlternatingDirectionCutLoss.py:271-279): normalise, ** alpha, normalise again
+      float mn2 = __int_as_float(0x7f800000), mx2 = -__int_as_float(0x7f800000);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + q * LC_THREADS;
+        if (i < hw) {
+          x[q] = pow_like_torch(__fdiv_rn(x[q] - mm.mn, den), P.alpha);
+          mn2 = fminf(mn2, x[q]), mx2 = fmaxf(mx2, x[q]);
+        }
+      }
+      MinMax m2 = block_minmax(mn2, mx2, s_red);
+      const float den2 = (m2.mx - m2.mn) + 1e-8f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = tid + q * LC_THREADS;
+        if (i < hw) s_part[i] = __fdiv_rn(x[q] - m2.mn, den2);
+      }
+    }
+  } else {
+    cluster.sync();
+  }
+  cluster.sync();  // the leaders hold the finished maps
+
+  // ---- every CTA takes a copy of all maps of the image ----
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+    const float* src = cluster.map_shared_rank(s_part, P.first[k]);
+    for (int i = tid; i < P.hw[k]; i += LC_THREADS) s_low[P.low_off[k] + i] = src[i];
+  }
+  cluster.sync();  // nobody's shared memory is needed by a peer any more
+
+  // ---- upsample + fuse + threshold this CTA's rows (LayerCAM.py:69-76, PsuedoMasks.py:59-62) ----
+  const int groups_x = (P.out_w + UP_COLS - 1) / UP_COLS;   // threads across a row, four columns each
+  const int lanes_y = LC_THREADS / groups_x;                // row groups of this CTA
+  const int gx = tid % groups_x, gy = tid / groups_x;
+  const int y_begin = rank * P.rows_per_cta, y_end = min(P.out_h, y_begin + P.rows_per_cta);
+  unsigned near = 0;
+  if (gy < lanes_y) {
+    const int x0 = gx * UP_COLS;
+    const int ncol = max(0, min(UP_COLS, P.out_w - x0));
+    const bool vec = (ncol == UP_COLS) && P.vec_ok;
+    Tap xt[NL][UP_COLS];
+    int cur0[NL], cur1[NL];
+    float h0[NL][UP_COLS], h1[NL][UP_COLS];
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+#pragma unroll
+      for (int c = 0; c < UP_COLS; ++c) {
+        xt[k][c] = make_tap(P.scale_x[k], min(x0 + c, P.out_w - 1), P.w[k]);
+        h0[k][c] = h1[k][c] = 0.f;
+      }
+      cur0[k] = cur1[k] = -1;
+    }
+    const bool mean_by_mul = P.inv_layers != 0.f;
+    const int shape = P.alpha_mode != 0 ? 0 : (P.alpha == 1.0f ? 1 : 2);
+    const bool count_near = P.near_count != nullptr;
+    // consecutive rows per thread, so that the horizontal interpolations of a low-resolution row pair are reused
+    const int per = (y_end - y_begin + lanes_y - 1) / lanes_y;
+    const int ya = y_begin + gy * per, yb = min(y_end, ya + per);
+    for (int y = ya; y < yb; ++y) {
+      float sacc[UP_COLS];
+#pragma unroll
+      for (int k = 0; k < NL; ++k) {
+        const Tap yt = make_tap(P.scale_y[k], y, P.h[k]);
+        if (yt.i0 != cur0[k] || yt.i1 != cur1[k]) {
+          const int w = P.w[k];
+          const float* basek = s_low + P.low_off[k];
+          if (yt.i0 == cur1[k]) {
+#pragma unroll
+            for (int c = 0; c < UP_COLS; ++c) h0[k][c] = h1[k][c];
+          } else {
+            const float* r0 = basek + yt.i0 * w;
+#pragma unroll
+            for (int c = 0; c < UP_COLS; ++c) h0[k][c] = lerp2(xt[k][c].l0, r0[xt[k][c].i0], xt[k][c].l1, r0[xt[k][c].i1]);
+          }
+          if (yt.i1 == yt.i0) {
+#pragma unroll
+            for (int c = 0; c < UP_COLS; ++c) h1[k][c] = h0[k][c];
+          } else {
+            const float* r1 = basek + yt.i1 * w;
+#pragma unroll
+            for (int c = 0; c < UP_COLS; ++c) h1[k][c] = lerp2(xt[k][c].l0, r1[xt[k][c].i0], xt[k][c].l1, r1[xt[k][c].i1]);
+          }
+          cur0[k] = yt.i0, cur1[k] = yt.i1;
+        }
+#pragma unroll
+        for (int c = 0; c < UP_COLS; ++c) {
+          const float v = lerp2(yt.l0, h0[k][c], yt.l1, h1[k][c]);
+          sacc[c] = (k == 0) ? v : sacc[c] + v;  // python sum(): 0 + cam_0 + cam_1 ... (LayerCAM.py:74)
+        }
+      }
+      float cam[UP_COLS];
+      unsigned bits = 0;
+#pragma unroll
+      for (int c = 0; c < UP_COLS; ++c) {
+        float v = mean_by_mul ? sacc[c] * P.inv_layers : __fdiv_rn(sacc[c], P.n_layers_f);
+        if (shape == 1) v = fmaxf(v, 0.f);
+        else if (shape == 2) v = pow_like_torch(fmaxf(v, 0.f), P.alpha);
+        cam[c] = v;
+        if (v >= P.thresh && v > 0.f) bits |= 1u << (8 * c);
+        if (count_near && c < ncol) near += (fabsf(v - P.thresh) < P.band) ? 1u : 0u;
+      }
+      if (ncol == 0) continue;
+      const size_t o = ((size_t)b * P.out_h + y) * P.out_w + x0;
+      if (vec) {
+        if (P.cam_out) *reinterpret_cast<float4*>(P.cam_out + o) = make_float4(cam[0], cam[1], cam[2], cam[3]);
+        if (P.mask_out) *reinterpret_cast<unsigned*>(P.mask_out + o) = bits;
+      } else {
+#pragma unroll
+        for (int c = 0; c < UP_COLS; ++c)
+          if (c < ncol) {
+            if (P.cam_out) P.cam_out[o + c] = cam[c];
+            if (P.mask_out) P.mask_out[o + c] = (uint8_t)((bits >> (8 * c)) & 1u);
+          }
+      }
+    }
+  }
+  if (P.near_count) {
+    near = warp_sum_u32(near);
+    if ((tid & 31) == 0 && near) atomicAdd(P.near_count, (unsigned long long)near);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side: work decomposition ("plan"), shared by the workspace query and the launcher
 // ------------------------------------------------------------------------------------------
 struct LcPlan {
@@ -585,6 +832,108 @@ static void launch_channel_sum(const LcPlan& pl, cudaStream_t s) {
     layercam_channel_sum<DTYPE, 1><<<pl.total_items, LC_THREADS, 0, s>>>(pl.P);
 }
 
+template <int DTYPE, int VEC, int UNROLL>
+static int sc_launch_t(const ScParams& P, cudaStream_t s, bool query_only) {
+  void (*kern)(ScParams) = nullptr;
+  switch (P.n_layers) {
+    case 1: kern = layercam_cluster_kernel<DTYPE, VEC, 1, UNROLL>; break;
+    case 2: kern = layercam_cluster_kernel<DTYPE, VEC, 2, UNROLL>; break;
+    case 3: kern = layercam_cluster_kernel<DTYPE, VEC, 3, UNROLL>; break;
+    default: kern = layercam_cluster_kernel<DTYPE, VEC, 4, UNROLL>; break;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(SC_CLUSTER * P.B), cfg.blockDim = dim3(LC_THREADS), cfg.dynamicSmemBytes = 0, cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = SC_CLUSTER, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 1;
+  }
+  if (query_only) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+      (void)cudaGetLastError();
+      return 1;
+    }
+    return 0;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+// 1: not this path's case (the caller takes the two-kernel path), 0: launched, else a CUDA error
+static int sc_launch(const void* const* act, const void* const* grad, const int* C, const int* h, const int* w, int n_layers,
+                     int B, int dtype, int out_h, int out_w, float alpha, int alpha_mode, float thresh, float band,
+                     float* cam_out, uint8_t* mask_out, unsigned long long* near_count, cudaStream_t s) {
+  static const int off = WSDL_TUNE_INT("WSDL_LAYERCAM_NO_CLUSTER", 0);
+  if (off || n_layers > 4 || B > 16 || out_w > UP_COLS * LC_THREADS || out_w < 1) return 1;
+  const int vecw = dtype == WSDL_F32 ? 4 : 8, esize = dtype == WSDL_F32 ? 4 : 2;
+  ScParams P;
+  memset(&P, 0, sizeof(P));
+  long long total_low = 0, work[4], work_sum = 0, bytes = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const long long hw = (long long)h[l] * w[l];
+    if (hw > SC_MAX_HW || (hw % vecw) != 0 || hw / vecw > LC_THREADS) return 1;
+    if (((uintptr_t)act[l] % 16) || ((uintptr_t)grad[l] % 16)) return 1;
+    P.act[l] = act[l], P.grad[l] = grad[l], P.C[l] = C[l], P.h[l] = h[l], P.w[l] = w[l], P.hw[l] = (int)hw;
+    P.low_off[l] = (int)total_low;
+    total_low += hw;
+    work[l] = (long long)C[l] * hw;
+    work_sum += work[l];
+    bytes += 2LL * C[l] * hw * esize;
+    P.scale_y[l] = (float)h[l] / (float)out_h;
+    P.scale_x[l] = (float)w[l] / (float)out_w;
+  }
+  if (total_low > SC_MAX_LOW || n_layers > SC_CLUSTER) return 1;
+  // one cluster = 16 SMs of one GPC: fine for a few MB per image; bigger images and batches are better off on the
+  // streaming path, which spreads every image over the whole machine and reaches the HBM roofline there
+  if (bytes > (12LL << 20) || bytes * B > (96LL << 20)) return 1;
+  // ranks per layer in proportion to the bytes it streams, at least one each
+  int ranks[4], used = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    ranks[l] = (int)((work[l] * SC_CLUSTER) / work_sum);
+    if (ranks[l] < 1) ranks[l] = 1;
+    used += ranks[l];
+  }
+  while (used > SC_CLUSTER) {  // take from the layer with the least work per rank
+    int k = -1;
+    for (int l = 0; l < n_layers; ++l)
+      if (ranks[l] > 1 && (k < 0 || work[l] * ranks[k] < work[k] * ranks[l])) k = l;
+    if (k < 0) return 1;
+    --ranks[k], --used;
+  }
+  while (used < SC_CLUSTER) {  // give to the layer with the most work per rank
+    int k = 0;
+    for (int l = 1; l < n_layers; ++l)
+      if (work[l] * ranks[k] > work[k] * ranks[l]) k = l;
+    ++ranks[k], ++used;
+  }
+  int r = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    P.first[l] = r, P.count[l] = ranks[l];
+    P.ch_per_cta[l] = (C[l] + ranks[l] - 1) / ranks[l];
+    for (int j = 0; j < ranks[l]; ++j) P.rank_layer[r++] = l;
+  }
+  P.n_layers = n_layers, P.B = B, P.out_h = out_h, P.out_w = out_w;
+  P.rows_per_cta = (out_h + SC_CLUSTER - 1) / SC_CLUSTER;
+  P.alpha = alpha, P.alpha_mode = alpha_mode, P.thresh = thresh, P.band = band;
+  P.inv_layers = ((n_layers & (n_layers - 1)) == 0) ? 1.0f / (float)n_layers : 0.f;
+  P.n_layers_f = (float)n_layers;
+  P.cam_out = cam_out, P.mask_out = mask_out, P.near_count = near_count;
+  P.vec_ok = ((out_w & 3) == 0) && (((uintptr_t)cam_out & 15) == 0) && (((uintptr_t)mask_out & 3) == 0);
+  static int usable[64] = {};  // per device: 0 unknown, 1 clusters of 16 can be scheduled, -1 they cannot
+  int dev_id = 0;
+  if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 64) dev_id = 0;
+  if (usable[dev_id] == 0) usable[dev_id] = sc_launch_t<WSDL_F32, 4, 4>(P, s, true) == 0 ? 1 : -1;
+  if (usable[dev_id] < 0) return 1;
+  if (dtype == WSDL_F32) return B <= 8 ? sc_launch_t<WSDL_F32, 4, 8>(P, s, false) : sc_launch_t<WSDL_F32, 4, 4>(P, s, false);
+  if (dtype == WSDL_BF16) return sc_launch_t<WSDL_BF16, 8, 4>(P, s, false);
+  return sc_launch_t<WSDL_F16, 8, 4>(P, s, false);
+}
+
 }  // namespace wsdl
 
 using namespace wsdl;
@@ -620,6 +969,11 @@ extern "C" int wsdl_layercam_fused(const void* const* act, const void* const* gr
   if (cam_out && ((uintptr_t)cam_out % 4)) return WSDL_E_ALIGN;
   if (near_count && ((uintptr_t)near_count % 8)) return WSDL_E_ALIGN;
   cudaStream_t s = (cudaStream_t)stream;
+  if (cam_out || mask_out || near_count) {  // small batches: one cluster launch per call (no workspace, no memset)
+    const int rc_small = sc_launch(act, grad, C, h, w, n_layers, B, dtype, out_h, out_w, alpha, alpha_mode, thresh, near_band,
+                                   cam_out, mask_out, near_count, s);
+    if (rc_small != 1) return rc_small;
+  }
   uintptr_t ws = ((uintptr_t)workspace + 255) / 256 * 256;
   pl.P.ctrl = reinterpret_cast<unsigned*>(ws);
   pl.P.low = reinterpret_cast<float*>(ws) + pl.ctrl_u32;
