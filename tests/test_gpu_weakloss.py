@@ -133,6 +133,11 @@ def test_bf16_logits_u8_images_u8_labels(WF, lab_dtype):
         assert torch.equal(a, b)
     assert out8[4].dtype == torch.bfloat16
     assert torch.equal(out8[4], out32[4].to(torch.bfloat16))  # same fp32 gradient, rounded once
+    # bf16 logits + f32 images + labels: the training step's own types have a compiled variant of the kernel
+    outb = WF.weak_loss_and_grad(logits.cuda(), (img8.float() / 255).cuda(), labels.cuda(), 1.0, go_c, go_b)
+    for a, b in zip(outb[:4], out32[:4]):
+        assert torch.equal(a, b)
+    assert torch.equal(outb[4], out8[4])
     ref = closed_form_total(logits.float(), img8.float() / 255, labels, 1.0, 0.1, go_b.cpu())
     assert_loss_close(out8[0], ref[0], "total (bf16 / u8 inputs)")
     assert_grad_close(out32[4], ref[4], "gradient (rounded inputs)")

@@ -842,7 +842,7 @@ extern "C" int wsdl_weak_loss_fwd_bwd(const void* logits, int logits_dtype, cons
   if (labels && labels_dtype != WSDL_U8 && labels_dtype != WSDL_I64) return WSDL_E_DTYPE;
   if (grad_logits && grad_dtype != WSDL_F32 && grad_dtype != WSDL_BF16) return WSDL_E_DTYPE;
   if (((uintptr_t)loss_cut % 4) || ((uintptr_t)loss_bnd % 4) || (loss_ce && ((uintptr_t)loss_ce % 4)) ||
-      (labels && labels_dtype == WSDL_I64 && ((uintptr_t)labels % 8)))
+      (labels && ((uintptr_t)labels % (labels_dtype == WSDL_I64 ? 16 : 2))))  // labels are read two at a time
     return WSDL_E_ALIGN;
   if (workspace_bytes < wsdl_weak_loss_workspace_bytes(B, H, W)) return WSDL_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;

@@ -98,15 +98,17 @@ __device__ unsigned long long sg_trace_buf[WSDL_NUM_SMS * SG_GROUPS * 8 * 8];
 // instructions per step, so the hot configurations are compiled with their types known:
 //   0: f32 logits + f32 images, no labels (the cut + boundary launch of BASELINE configs[1])
 //   1: f32 logits + f32 images + labels (cross-entropy fused in)
-//   2: anything else (bf16 logits, u8 images): types read from the parameters
+//   2: anything else (u8 images, ...): types read from the parameters
+//   3: bf16 logits + f32 images + labels, bf16 gradient (the training step under bf16 autocast, BASELINE config 4)
 template <int MODE>
 struct SgMode {
-  static constexpr bool known = MODE < 2;
-  __device__ static __forceinline__ bool ce(const SgParams& P) { return MODE == 0 ? false : (MODE == 1 ? true : P.labels != nullptr); }
-  __device__ static __forceinline__ bool rotate(const SgParams& P) { return known ? true : P.rotate != 0; }
-  __device__ static __forceinline__ bool img_f32(const SgParams& P) { return known ? true : P.image_dtype == WSDL_F32; }
-  __device__ static __forceinline__ bool val_f32(const SgParams& P) { return known ? true : P.logit_dtype == WSDL_F32; }
-  __device__ static __forceinline__ bool grad_f32(const SgParams& P) { return known ? true : P.grad_dtype == WSDL_F32; }
+  static constexpr bool known = MODE < 2;   // f32 raw tiles in the working layout: rotating slots, in-place conversion
+  static constexpr bool typed = MODE != 2;  // element types known at compile time
+  __device__ static __forceinline__ bool ce(const SgParams& P) { return MODE == 0 ? false : (typed ? true : P.labels != nullptr); }
+  __device__ static __forceinline__ bool rotate(const SgParams& P) { return known ? true : (MODE == 3 ? false : P.rotate != 0); }
+  __device__ static __forceinline__ bool img_f32(const SgParams& P) { return typed ? true : P.image_dtype == WSDL_F32; }
+  __device__ static __forceinline__ bool val_f32(const SgParams& P) { return known ? true : (MODE == 3 ? false : P.logit_dtype == WSDL_F32); }
+  __device__ static __forceinline__ bool grad_f32(const SgParams& P) { return known ? true : (MODE == 3 ? false : P.grad_dtype == WSDL_F32); }
 };
 
 __device__ __forceinline__ void sg_bar_wait(unsigned bar, unsigned parity) {
@@ -131,23 +133,28 @@ __device__ __forceinline__ float sg_bf16_lo(unsigned w) { return __uint_as_float
 __device__ __forceinline__ float sg_bf16_hi(unsigned w) { return __uint_as_float(w & 0xffff0000u); }
 
 // Labels of the 4 pixels (y, xs .. xs+3) of image b, one per byte: class ids 0 / 1; anything else (ignore_index, a
-// position outside the image) -> 2 = "no cross-entropy here".  row0 = (b H + y) W.
+// position outside the image) -> 2 = "no cross-entropy here".  row0 = (b H + y) W.  xs is even and W a multiple of 4
+// (the launcher checks), so the pixels come in two pairs that are inside or outside the image together: byte labels
+// are two 16-bit loads.
+__device__ __forceinline__ unsigned sg_label_class(long long v, long long ignore) {
+  return (v == ignore || v < 0 || v > 1) ? 2u : (unsigned)v;
+}
 __device__ __forceinline__ unsigned sg_load_labels4(const SgParams& P, size_t row0, int xs) {
   unsigned out = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int x = xs + j;
-    unsigned c = 2u;
+  for (int h = 0; h < 2; ++h) {
+    const int x = xs + 2 * h;
+    unsigned c0 = 2u, c1 = 2u;
     if (x >= 0 && x < P.W) {
       if (P.label_dtype == WSDL_U8) {
-        const unsigned v = __ldg(reinterpret_cast<const unsigned char*>(P.labels) + row0 + x);
-        c = ((long long)v == P.ignore_index || v > 1u) ? 2u : v;
+        const unsigned v = __ldg(reinterpret_cast<const unsigned short*>(reinterpret_cast<const unsigned char*>(P.labels) + row0 + x));
+        c0 = sg_label_class((long long)(v & 0xffu), P.ignore_index), c1 = sg_label_class((long long)(v >> 8), P.ignore_index);
       } else {
-        const long long v = __ldg(reinterpret_cast<const long long*>(P.labels) + row0 + x);
-        c = (v == P.ignore_index || v < 0 || v > 1) ? 2u : (unsigned)v;
+        const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(P.labels) + row0 + x));
+        c0 = sg_label_class(v.x, P.ignore_index), c1 = sg_label_class(v.y, P.ignore_index);
       }
     }
-    out |= c << (8 * j);
+    out |= (c0 | (c1 << 8)) << (16 * h);
   }
   return out;
 }
@@ -225,8 +232,9 @@ __device__ __forceinline__ void sg_rows_convert(const SgParams& P, const PsBlk& 
       for (int j = 0; j < 4; ++j) {
         const unsigned c = (lab >> (8 * j)) & 0xffu;
         if (c < 2u) {  // -log p_c = softplus(+z) for class 0, softplus(-z) for class 1
+          // log(1 + t), t = e^-|s| in (0, 1]: two MUFU; the absolute error (< 1e-7) is what matters in a mean of O(1) terms
           const float s = c == 0u ? z[j] : -z[j];
-          lsum_ce += fmaxf(s, 0.f) + log1pf(__expf(-fabsf(s)));
+          lsum_ce += fmaxf(s, 0.f) + __logf(1.f + __expf(-fabsf(s)));
         }
       }
     }
@@ -588,7 +596,13 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
           if (P.grad) {
             const float gc = ac[0] + s_gband[(ty + 2) * 12 + slot * 2 + 0];
             const float gb = ab[0] + s_gband[(ty + 2) * 12 + slot * 2 + 1];
-            const unsigned lab = want_ce ? (sg_load_labels4(P, ((size_t)K.b * H + y) * W, x) & 0xffu) : 2u;
+            unsigned lab = 2u;
+            if (want_ce) {
+              const size_t pix = ((size_t)K.b * H + y) * W + x;
+              lab = sg_label_class(P.label_dtype == WSDL_U8 ? (long long)__ldg(reinterpret_cast<const unsigned char*>(P.labels) + pix)
+                                                            : __ldg(reinterpret_cast<const long long*>(P.labels) + pix),
+                                   P.ignore_index);
+            }
             const float o = sg_px_grad(want_ce, p0, gc, gb, K.scale2, scale_b, cw, lab);
             const size_t off = (size_t)K.b * 2 * plane + (size_t)y * W + x;
             if (M::grad_f32(P)) {
@@ -815,6 +829,8 @@ int sg_launch(const SgLaunch& L, cudaStream_t s) {
       e = cudaFuncSetAttribute(weak_loss_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(weak_loss_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(weak_loss_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_done[dev_id] = true;
   }
@@ -825,6 +841,8 @@ int sg_launch(const SgLaunch& L, cudaStream_t s) {
     weak_loss_stream_kernel<0><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
   else if (f32_in)
     weak_loss_stream_kernel<1><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
+  else if (L.labels && L.image_dtype == WSDL_F32 && L.logit_dtype == WSDL_BF16 && (!L.grad || L.grad_dtype == WSDL_BF16))
+    weak_loss_stream_kernel<3><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
   else
     weak_loss_stream_kernel<2><<<grid, SG_THREADS, SG_SMEM_BYTES, s>>>(P, tm_img, tm_val);
   WSDL_LAUNCH_CHECK();
