@@ -193,7 +193,8 @@ def generate_pseudo_masks_sharded(hook_source, n_images, out_size, cam_thresh=0.
             cur.wait_stream(s_)
     if not own_kernel and sink is None:
         result = torch.cat(kept) if kept else None
-    dev = device if device is not None else (result.device if result is not None else None)
+    seen = [t.device for t in near_total if t is not None]
+    dev = device if device is not None else (seen[0] if seen else None)  # NCCL reduces device tensors, gloo host ones
     local = [n_masks, sum(int(t.sum().item()) for t in near_total if t is not None),
              sum(int(t.item()) for t in fg_total if t is not None)]  # the only host reads: after the last chunk
     total = sharding.all_reduce_counters(local, device=dev if (dev is not None and torch.device(dev).type == "cuda") else None)

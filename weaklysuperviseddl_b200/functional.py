@@ -437,12 +437,13 @@ def weak_loss_supported(logits: torch.Tensor, images: torch.Tensor, labels: Opti
 
 def weak_loss_and_grad(logits, images, labels=None, lam_ce=1.0, grad_out_cut=None, grad_out_bnd=None, sigma_cut=0.05,
                        sigma_boundary=0.1, sigma_space=5.0, window_size=5, ignore_index=-100, want_grad=True,
-                       ce_inv_count: Optional[torch.Tensor] = None):
+                       ce_inv_count: Optional[torch.Tensor] = None, packed_out: Optional[torch.Tensor] = None):
     """ONE launch (wsdl_weak_loss_fwd_bwd) for the loss of a weakly-supervised training step on a two-class batch:
     total = lam_ce * CE(logits, labels) + go_cut * cut(logits, images) + sum_b go_bnd[b] * boundary(softmax(logits)[b],
     images[b]).  logits (B,2,H,W) f32 | bf16, images (B,3,H,W) f32 | u8 (8-bit pixels, read as value / 255), labels
     (B,H,W) u8 | int64 or None.  Returns (total (1,), ce (1,) or None, cut (1,), bnd (B,), d total / d logits in the
-    logits' dtype or None); the three loss values are unweighted."""
+    logits' dtype or None); the three loss values are unweighted.  The four loss outputs are views of one (3 + B,) float
+    tensor [total, ce, cut, bnd...], which the caller may provide (`packed_out`) to read everything back in one copy."""
     _require_cuda(logits, "logits")
     _require_cuda(images, "images")
     logits, images = logits.detach(), images.detach()
@@ -455,7 +456,12 @@ def weak_loss_and_grad(logits, images, labels=None, lam_ce=1.0, grad_out_cut=Non
     with torch.cuda.device(dev):
         nbytes = lib.wsdl_weak_loss_workspace_bytes(B, H, W)
         workspace = _pairwise_workspace(lib, dev, nbytes)
-        out = torch.empty(3 + B, dtype=torch.float32, device=dev)  # total, ce, cut, bnd[B]
+        if packed_out is None:
+            out = torch.empty(3 + B, dtype=torch.float32, device=dev)  # total, ce, cut, bnd[B]
+        else:
+            out = packed_out
+            if out.dtype != torch.float32 or out.numel() != 3 + B or not out.is_contiguous() or out.device != dev:
+                raise ValueError(f"packed_out must be a contiguous float32 CUDA tensor of {3 + B} elements")
         grad = torch.empty_like(logits) if want_grad else None
         lab_ptr, lab_code, inv_ptr = None, 0, None
         if labels is not None:
