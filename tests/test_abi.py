@@ -52,7 +52,10 @@ def test_workspace_queries_are_host_only(lib):
     assert lib.wsdl_layercam_workspace_bytes(Int2(1024, 2048), Int2(32, 32), Int2(32, 32), 2, 16, 7) == 0
     assert lib.wsdl_pairwise_workspace_bytes(32, 224, 224) >= 32 * 49 * 4
     assert lib.wsdl_pairwise_workspace_bytes(0, 224, 224) == 0
-    assert lib.wsdl_keep_largest_workspace_bytes(4, 512, 512) >= 4 * 512 * 512 * 8
+    n_ccl = lib.wsdl_keep_largest_workspace_bytes(4, 512, 512)  # per-tile component tables: 4 KB + 256 B per 32x32 tile
+    assert 4 * 256 * (4 * 1024 + 256) <= n_ccl < 4 * 512 * 512 * 8  # round 1 kept 8 bytes per PIXEL
+    assert lib.wsdl_weak_loss_workspace_bytes(32, 224, 224) >= 512 and lib.wsdl_weak_loss_workspace_bytes(0, 1, 1) == 0
+    assert lib.wsdl_refine_workspace_bytes(16, 256, 256) >= 16 * 4 and lib.wsdl_refine_workspace_bytes(1, 0, 5) == 0
 
 
 def test_argument_errors_do_not_touch_the_device(lib):
