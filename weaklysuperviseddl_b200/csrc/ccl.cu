@@ -5,36 +5,35 @@
 // regionprops, max by area (first maximum = lowest label = component whose first pixel comes first
 // in raster order), `labeled == label`.  Empty masks are returned unchanged.
 //
-// Two-level union-find whose per-PIXEL state is one byte and lives in the output buffer itself:
-//   1. ccl_tile    one CTA labels a 32x32 tile in SHARED memory (runs by one ballot per row,
-//                  joins to the row above with shared-memory atomicMin unions, flatten, count).  A 32x32 tile has at
-//                  most 256 8-connected components, so a pixel is described by ONE BYTE: 0 = background, k + 1 = the
-//                  k-th local component of its tile.  That byte is written to `out`; the tile's component table (first
-//                  pixel, area, union-find parent = itself) and the labels of its 124 border pixels go to small side
-//                  arrays.  (Several tiles per CTA -- WSDL_CCL_TPC -- were measured: the phases are divergent latency
-//                  chains that the compiler cannot interleave, and 2 / 4 tiles per CTA cost 5 % / 35 %.)
+// Two-level union-find on RUNS, rows as 32-bit words.  A 32x32 tile is labelled by ONE WARP, lane = row:
+//   1. ccl_tile    the lane packs its row's 32 mask bytes into a word; a run is a maximal group of set bits, a node of the
+//                  tile's union-find (shared memory, <= 16 runs per row).  A run touches the runs of the row above under
+//                  its dilated span -- one `&` against the upper lane's word (warp shuffle), one union per touched run.
+//                  Runs are flattened, counted and numbered: a 32x32 tile has at most 256 8-connected components.  What
+//                  leaves the SM is small: the 32 row words, one byte per run (its component number), the tile's component
+//                  table (first pixel, area, union-find parent = itself) and the component numbers of its 124 border
+//                  pixels.  The mask itself is read once and nothing per-pixel is written.
 //   2. ccl_seams   joins across tile seams on the COMPONENT tables (node = tile * 256 + k), reading the compact border
-//                  labels: a seam pixel costs two bytes from a dense array instead of a 32-byte sector of a label map.
+//                  records: a seam pixel costs two bytes from a dense array instead of a 32-byte sector of a label map.
 //   3. ccl_gather  every local component adds its area and its first pixel (min) to its global root;
 //      ccl_argmax  true roots compete for the per-image (area, -first pixel) maximum packed in one u64 atomicMax.
-//   4. ccl_select  per tile: "does local component k belong to the winner?" for its <= 256 components, then every pixel
-//                  turns its byte into 0 / 1 in place.
-// HBM traffic per image: mask in, labels out, labels in, result out = 4 bytes per pixel (the round-1 version kept an int32
-// label map and a count map: 7x the mask's 2 bytes per pixel; ncu in profiles/).  Integer work: bit-exact against the
-// oracle by construction.
+//   4. ccl_select  one warp per tile again: "does local component k belong to the winner?" for its <= 256 components, then
+//                  every lane rebuilds its row from the row word and the run bytes, expands the kept bits to bytes and
+//                  stores them (two 128-bit stores per row).
+// HBM traffic per image: mask in + result out (2 bytes per pixel, the algorithmic minimum) + ~0.7 KB of tables per tile
+// (round 2, first version: one byte of per-pixel state written and read back, 4 bytes per pixel; round 1: an int32 label
+// map and a count map, 14).  Integer work: bit-exact against the oracle by construction.
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace wsdl {
 
-constexpr int CT = 32;         // tile edge: one warp per row
-#ifndef WSDL_CCL_TPC
-#define WSDL_CCL_TPC 1
-#endif
-constexpr int TPC = WSDL_CCL_TPC;  // tiles per CTA (a 32 x 32 TPC strip)
-constexpr int CCL_MAXR = 256;  // components of a 32x32 tile under 8-connectivity: one per aligned 2x2 cell at most
-constexpr int CCL_THREADS = 256;
+constexpr int CT = 32;          // tile edge: one lane per row, one bit per column
+constexpr int CCL_TPC = 8;      // tiles (warps) per CTA: a 256-column strip of one tile row
+constexpr int CCL_MAXR = 256;   // components of a 32x32 tile under 8-connectivity: one per aligned 2x2 cell at most
+constexpr int CCL_RPR = 16;     // runs of a 32-bit row at most
+constexpr int CCL_THREADS = 32 * CCL_TPC;
 constexpr unsigned short CCL_BG = 0xffffu;
 
 __device__ __forceinline__ int uf_find(const int* L, int i) {
@@ -63,150 +62,140 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 }
 
 struct CclTables {
-  int* n_roots;            // [tiles]
+  int* n_roots;            // [tiles] components of the tile | (most runs in one of its rows) << 16
   int* first_pix;          // [tiles][256] raster index (within the image) of the component's first pixel; never changes
   int* min_pix;            // [tiles][256] at a global root: first pixel of the whole component
   unsigned* area;          // [tiles][256] local pixel count; at a global root: the component's area
   int* parent;             // [tiles][256] union-find over nodes tile * 256 + k
-  unsigned short* border;  // [tiles][4][32]: component index of the top row, bottom row, left column, right column pixels
+  unsigned short* border;  // [tiles][4][32]: component number of the top row, bottom row, left column, right column pixels
+  unsigned* bits;          // [tiles][32] the row words
+  uint8_t* runcomp;        // [tiles][16][32] component number of the k-th run of row r at [k][r]
   unsigned long long* best;  // [B] (area << 32) | (0xffffffff - first pixel)
 };
 
-// ncu (profiles/): this kernel is bound by instruction issue (85 % issue-active), and most of its instructions used to be
-// per-PIXEL union-find work executed under divergence.  Rows are therefore handled as RUNS: a row is one 32-bit ballot,
-// everything a pixel needs to know about its neighbours is bit arithmetic on its row's and the row above's ballots, only
-// the first pixel of a run ever walks the union-find, and the other pixels of the run copy from it.
-__global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restrict__ mask, uint8_t* __restrict__ out,
-                                                        CclTables T, int H, int W, int tiles_x, int tiles_y) {
-  __shared__ int s_lab[TPC][CT * CT];      // run starts: union-find parent (local index); other pixels: their run start
-  __shared__ unsigned s_cnt[TPC][CT * CT];
-  __shared__ short s_roots[TPC][CCL_MAXR];
-  __shared__ short s_idx[TPC][CT * CT];    // at a root: its component number
-  __shared__ unsigned s_bits[TPC][CT];     // foreground ballot of every row
-  __shared__ int s_n[TPC];
-  const int b = blockIdx.z;
-  const int tx0 = blockIdx.x * TPC, ty = blockIdx.y;
-  const int y0 = ty * CT;
-  const size_t img = (size_t)b * H * W;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // 8 warps, 4 rows each
-  const unsigned lt = (1u << lane) - 1u;
-  if (threadIdx.x < TPC) s_n[threadIdx.x] = 0;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) T.best[b] = 0ull;
+// four mask bytes -> four bits (byte != 0)
+__device__ __forceinline__ unsigned ccl_pack4(unsigned v) {
+  const unsigned nz = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;  // bit 7 of every non-zero byte
+  return ((nz >> 7) * 0x01020408u) >> 24;                                     // gathered into bits 0..3
+}
 
-  unsigned row[TPC][4];  // this warp's four row ballots
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int ly = warp * 4 + k, y = y0 + ly;
-    bool fg[TPC];
-#pragma unroll
-    for (int u = 0; u < TPC; ++u) {
-      const int x = (tx0 + u) * CT + lane;
-      fg[u] = y < H && x < W && mask[img + (size_t)y * W + x] != 0;
-    }
-#pragma unroll
-    for (int u = 0; u < TPC; ++u) {
-      const unsigned bits = __ballot_sync(0xffffffffu, fg[u]);
-      row[u][k] = bits;
-      const unsigned below = ~bits & lt;                 // background pixels left of this one
-      const int start = below ? 32 - __clz(below) : 0;   // first pixel after the last of them
-      s_lab[u][ly * CT + lane] = fg[u] ? ly * CT + start : -1;
-      s_cnt[u][ly * CT + lane] = 0u;
-      if (lane == 0) s_bits[u][ly] = bits;
+// four bits -> four bytes of 0 / 1
+__device__ __forceinline__ unsigned ccl_expand4(unsigned nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+// the run of `m` that starts at bit a: its length and its bits
+__device__ __forceinline__ unsigned ccl_run(unsigned m, int a, int* len) {
+  const unsigned after = ~(m >> a);  // bit i: pixel a + i is background (the shift fills with background)
+  const int l = __ffs(after) - 1;    // >= 1; after != 0 unless a == 0 and the row is full
+  *len = after ? l : CT;
+  return (after ? ((1u << l) - 1u) : 0xffffffffu) << a;
+}
+
+// number of the run that holds bit x, given the row's run-start bits
+__device__ __forceinline__ int ccl_run_of(unsigned starts, int x) { return __popc(starts & ((2u << x) - 1u)) - 1; }
+
+// ncu (profiles/): the per-pixel version of this kernel (one thread per pixel, rows as ballots) issued ~6 warp
+// instructions per pixel and was bound by instruction issue.  Here a lane owns a ROW: everything a run needs to know
+// about the row above is bit arithmetic on two words, and the loops run over runs (a handful per row for a CAM mask).
+__global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restrict__ mask, CclTables T, int H, int W, int tiles_x,
+                                                        int tiles_y, int vec_ok) {
+  __shared__ int s_par[CCL_TPC][CT * CCL_RPR];        // union-find over runs, node = row * 16 + k
+  __shared__ unsigned s_cnt[CCL_TPC][CT * CCL_RPR];   // at a root: pixels of the component
+  __shared__ unsigned short s_root[CCL_TPC][CCL_MAXR];   // component number -> root node
+  __shared__ unsigned short s_first[CCL_TPC][CCL_MAXR];  // component number -> first pixel (row * 32 + column)
+  __shared__ uint8_t s_comp[CCL_TPC][CT * CCL_RPR];   // root node -> component number
+  __shared__ int s_n[CCL_TPC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x * CCL_TPC + warp;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) T.best[b] = 0ull;
+  if (tx >= tiles_x) return;  // warps are independent: only __syncwarp below
+  const int y0 = ty * CT, x0 = tx * CT, y = y0 + lane;
+  const size_t img = (size_t)b * H * W;
+  const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx;
+  int* par = s_par[warp];
+  unsigned* cnt = s_cnt[warp];
+
+  unsigned m = 0u;  // my row
+  if (y < H) {
+    const uint8_t* p = mask + img + (size_t)y * W + x0;
+    if (vec_ok && x0 + CT <= W) {
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+      m = ccl_pack4(lo.x) | (ccl_pack4(lo.y) << 4) | (ccl_pack4(lo.z) << 8) | (ccl_pack4(lo.w) << 12) |
+          (ccl_pack4(hi.x) << 16) | (ccl_pack4(hi.y) << 20) | (ccl_pack4(hi.z) << 24) | (ccl_pack4(hi.w) << 28);
+    } else {
+      const int nx = min(CT, W - x0);
+      for (int j = 0; j < nx; ++j) m |= (p[j] != 0 ? 1u : 0u) << j;
     }
   }
-  __syncthreads();
-  // join with the row above: N, else NW / NE, skipping the joins the left / right neighbour makes anyway.  The unions
-  // act on run starts (a pixel stands for the start of its run).
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int ly = warp * 4 + k;
-    if (ly == 0) continue;
-#pragma unroll
-    for (int u = 0; u < TPC; ++u) {
-      const unsigned cur = row[u][k], up = k > 0 ? row[u][k - 1] : s_bits[u][ly - 1];
-      if (!((cur >> lane) & 1u)) continue;
-      const bool n = (up >> lane) & 1u;
-      const bool w = lane > 0 && ((cur >> (lane - 1)) & 1u), nw = lane > 0 && ((up >> (lane - 1)) & 1u);
-      const bool e = lane < CT - 1 && ((cur >> (lane + 1)) & 1u), ne = lane < CT - 1 && ((up >> (lane + 1)) & 1u);
-      int other = -1;
-      if (n) {
-        if (!(w && nw)) other = lane;  // else W has joined NW, which is in N's run
+  const unsigned up_raw = __shfl_up_sync(0xffffffffu, m, 1);
+  const unsigned up = lane ? up_raw : 0u;  // the row above inside the tile
+  const unsigned st = m & ~(m << 1), ust = up & ~(up << 1);  // run starts
+  const int nr = __popc(st);
+  const int maxruns = __reduce_max_sync(0xffffffffu, nr);
+  for (int k = 0; k < nr; ++k) par[lane * CCL_RPR + k] = lane * CCL_RPR + k, cnt[lane * CCL_RPR + k] = 0u;
+  if (lane == 0) s_n[warp] = 0;
+  __syncwarp();
+  {  // a run joins every run of the row above that has a pixel under its span widened by one column either side
+    unsigned s = st;
+    for (int k = 0; s; ++k) {
+      const int a = __ffs(s) - 1;
+      s &= s - 1u;
+      int len;
+      const unsigned R = ccl_run(m, a, &len);
+      const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
+      unsigned ts = touched & ~(touched << 1);  // one group of touched bits per run of the row above
+      while (ts) {
+        const int p = __ffs(ts) - 1;
+        ts &= ts - 1u;
+        uf_union(par, lane * CCL_RPR + k, (lane - 1) * CCL_RPR + ccl_run_of(ust, p));
+      }
+    }
+  }
+  __syncwarp();
+  {  // flatten, add the run's length to its root's count, number the components
+    unsigned s = st;
+    for (int k = 0; s; ++k) {
+      const int a = __ffs(s) - 1;
+      s &= s - 1u;
+      int len;
+      ccl_run(m, a, &len);
+      const int i = lane * CCL_RPR + k;
+      const int r = uf_find(par, i);
+      atomicAdd(&cnt[r], (unsigned)len);
+      if (r == i) {  // the root is the component's first run in raster order (unions hang the larger node under the smaller)
+        const int c = atomicAdd(&s_n[warp], 1);
+        s_root[warp][c] = (unsigned short)i;
+        s_first[warp][c] = (unsigned short)(lane * CT + a);
+        s_comp[warp][i] = (uint8_t)c;
       } else {
-        if (nw && !w) other = lane - 1;  // else W has joined its N = NW
-        if (ne && !e) {
-          if (other >= 0) uf_union(s_lab[u], s_lab[u][ly * CT + lane], s_lab[u][(ly - 1) * CT + other]);
-          other = lane + 1;  // else E joins its N = NE
-        }
-      }
-      if (other >= 0) uf_union(s_lab[u], s_lab[u][ly * CT + lane], s_lab[u][(ly - 1) * CT + other]);
-    }
-  }
-  __syncthreads();
-  // run starts: flatten, add the run's length to the root's count, number the components
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int ly = warp * 4 + k, i = ly * CT + lane;
-#pragma unroll
-    for (int u = 0; u < TPC; ++u) {
-      const unsigned cur = row[u][k];
-      const bool start = ((cur >> lane) & 1u) && !(lane > 0 && ((cur >> (lane - 1)) & 1u));
-      if (!start) continue;
-      const unsigned after = ~cur >> lane;                      // first background pixel at or after this one ends the run
-      const int len = after ? __ffs(after) - 1 : CT - lane;
-      const int r = uf_find(s_lab[u], i);
-      atomicAdd(&s_cnt[u][r], (unsigned)len);
-      if (r == i) {
-        const int c = atomicAdd(&s_n[u], 1);
-        s_roots[u][c] = (short)i;
-        s_idx[u][i] = (short)c;
-      } else {
-        s_lab[u][i] = r;  // roots keep s_lab[r] == r, so concurrent finds stay correct
+        par[i] = r;  // roots keep par[r] == r, so concurrent finds stay correct
       }
     }
   }
-  __syncthreads();
-  // component tables
-#pragma unroll
-  for (int u = 0; u < TPC; ++u) {
-    if (tx0 + u >= tiles_x) continue;
-    const int n = s_n[u];
-    const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx0 + u;
-    if (threadIdx.x == 0) T.n_roots[tile] = n;
-    if ((int)threadIdx.x < n) {
-      const int r = s_roots[u][threadIdx.x];
-      const int g = (y0 + r / CT) * W + ((tx0 + u) * CT + r % CT);
-      const size_t node = tile * CCL_MAXR + threadIdx.x;
-      T.first_pix[node] = g;
-      T.min_pix[node] = g;
-      T.area[node] = s_cnt[u][r];
-      T.parent[node] = (int)node;
-    }
+  __syncwarp();
+  const int n = s_n[warp];
+  if (lane == 0) T.n_roots[tile] = n | (maxruns << 16);
+  for (int c = lane; c < n; c += 32) {
+    const int i = s_root[warp][c], f = s_first[warp][c];
+    const int g = (y0 + (f >> 5)) * W + x0 + (f & 31);
+    const size_t node = tile * CCL_MAXR + c;
+    T.first_pix[node] = g;
+    T.min_pix[node] = g;
+    T.area[node] = cnt[i];
+    T.parent[node] = (int)node;
   }
-  // one byte per pixel into `out`, two bytes per border pixel into the tile's border record
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int ly = warp * 4 + k, y = y0 + ly;
-    const int i = ly * CT + lane;
-#pragma unroll
-    for (int u = 0; u < TPC; ++u) {
-      if (tx0 + u >= tiles_x) continue;
-      const int x = (tx0 + u) * CT + lane;
-      const int st = s_lab[u][i];                   // -1, my run start (or, at a run start, its root)
-      int comp = -1;
-      if (st >= 0) {
-        const bool start = !(lane > 0 && ((row[u][k] >> (lane - 1)) & 1u));
-        const int root = start ? st : s_lab[u][st];  // a run start holds its root (or is one); the others hold their start
-        comp = (int)s_idx[u][root];
-      }
-      if (y < H && x < W) out[img + (size_t)y * W + x] = comp < 0 ? 0 : (uint8_t)(comp == 255 ? 255 : comp + 1);
-      const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx0 + u;
-      unsigned short* rec = T.border + tile * 128;
-      const unsigned short v = comp < 0 ? CCL_BG : (unsigned short)comp;
-      if (ly == 0) rec[lane] = v;
-      if (ly == CT - 1) rec[32 + lane] = v;
-      if (lane == 0) rec[64 + ly] = v;
-      if (lane == CT - 1) rec[96 + ly] = v;
-    }
+  T.bits[tile * CT + lane] = m;
+  for (int k = 0; k < maxruns; ++k)  // par[i] is i's root by now
+    T.runcomp[(tile * CCL_RPR + k) * CT + lane] = k < nr ? s_comp[warp][par[lane * CCL_RPR + k]] : (uint8_t)0;
+  // component numbers of the border pixels: top / bottom row (lane = column), left / right column (lane = row)
+  unsigned short* rec = T.border + tile * 128;
+  {
+    const unsigned m0 = __shfl_sync(0xffffffffu, m, 0), st0 = __shfl_sync(0xffffffffu, st, 0);
+    const unsigned m31 = __shfl_sync(0xffffffffu, m, CT - 1), st31 = __shfl_sync(0xffffffffu, st, CT - 1);
+    rec[lane] = (m0 >> lane) & 1u ? (unsigned short)s_comp[warp][par[ccl_run_of(st0, lane)]] : CCL_BG;
+    rec[32 + lane] =
+        (m31 >> lane) & 1u ? (unsigned short)s_comp[warp][par[(CT - 1) * CCL_RPR + ccl_run_of(st31, lane)]] : CCL_BG;
+    rec[64 + lane] = m & 1u ? (unsigned short)s_comp[warp][par[lane * CCL_RPR]] : CCL_BG;
+    rec[96 + lane] = m >> 31 ? (unsigned short)s_comp[warp][par[lane * CCL_RPR + nr - 1]] : CCL_BG;
   }
 }
 
@@ -259,7 +248,7 @@ __global__ void ccl_seams(CclTables T, int H, int W, int tiles_x, int tiles_y) {
 __global__ void ccl_gather(CclTables T, int n_tiles) {
   const int sub = threadIdx.x & 7;
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n_tiles; t += (gridDim.x * blockDim.x) >> 3) {
-    const int n = T.n_roots[t];
+    const int n = T.n_roots[t] & 0xffff;
     for (int k = sub; k < n; k += 8) {
       const int node = t * CCL_MAXR + k;
       const int r = uf_find(T.parent, node);
@@ -282,7 +271,7 @@ __global__ void ccl_argmax(CclTables T, int tiles_per_image, int n_tiles) {
     int b = 0;
     if (t < n_tiles) {
       b = t / tiles_per_image;
-      const int n = T.n_roots[t];
+      const int n = T.n_roots[t] & 0xffff;
       for (int k = sub; k < n; k += 8) {
         const int node = t * CCL_MAXR + k;
         if (T.parent[node] == node) {  // a true root
@@ -303,70 +292,56 @@ __global__ void ccl_argmax(CclTables T, int tiles_per_image, int n_tiles) {
   }
 }
 
-// One CTA per strip of four tiles: which of each tile's components belong to the winner, then the bytes in place.
-constexpr int SPC = 4;  // tiles per CTA of the select pass (straight-line code: wider strips only save CTAs and barriers)
+// One warp per tile: flag the tile's components that belong to the winner, then every lane rebuilds its row.
 __global__ void __launch_bounds__(CCL_THREADS) ccl_select(uint8_t* __restrict__ out, CclTables T, unsigned* __restrict__ best_area,
-                                                          int H, int W, int tiles_x, int tiles_y) {
-  __shared__ uint8_t s_flag[SPC][CCL_MAXR];
-  __shared__ uint8_t s_cell[SPC][CCL_MAXR];  // only for a tile with 256 components: flag by aligned 2x2 cell
-  __shared__ int s_n[SPC];
-  const int b = blockIdx.z;
-  const int tx0 = blockIdx.x * SPC, ty = blockIdx.y, y0 = ty * CT;
+                                                          int H, int W, int tiles_x, int tiles_y, int vec_ok) {
+  __shared__ uint8_t s_flag[CCL_TPC][CCL_MAXR];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x * CCL_TPC + warp;
   const unsigned long long key = T.best[b];
   const int win = key ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -2;  // first pixel of the winning component
   if (best_area && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) best_area[b] = (unsigned)(key >> 32);
-  {  // 64 threads per tile walk its component table (a handful of entries for a blobby mask)
-    const int u = threadIdx.x >> 6, k0 = threadIdx.x & 63;
-    int n = 0;
-    if (tx0 + u < tiles_x) {
-      const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx0 + u;
-      n = T.n_roots[tile];
-      for (int k = k0; k < n; k += 64) {
-        const int node = (int)(tile * CCL_MAXR + k);
-        const int r = uf_find(T.parent, node);
-        const uint8_t f = T.min_pix[r] == win ? 1 : 0;
-        s_flag[u][k] = f;
-        if (n == CCL_MAXR) {  // every component sits in its own aligned 2x2 cell: the cell identifies it
-          const int g = T.first_pix[node], ly = g / W - y0, lx = g % W - (tx0 + u) * CT;
-          s_cell[u][(ly >> 1) * 16 + (lx >> 1)] = f;
-        }
-      }
-    }
-    if (k0 == 0) s_n[u] = n;
+  if (tx >= tiles_x) return;
+  const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx;
+  const int nn = T.n_roots[tile], n = nn & 0xffff;
+  bool mine_any = false, mine_all = true;
+  for (int c = lane; c < n; c += 32) {
+    const int node = (int)(tile * CCL_MAXR + c);
+    const bool f = T.min_pix[uf_find(T.parent, node)] == win;
+    s_flag[warp][c] = f ? 1 : 0;
+    mine_any |= f, mine_all &= f;
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t img = (size_t)b * H * W;
-  const bool vec = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
-  const int x = tx0 * CT + 4 * lane;  // four pixels of tile u = lane / 8
-  const int u = lane >> 3;
-  if (x >= W) return;
-  const bool full = s_n[u] == CCL_MAXR;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int ly = warp * 4 + k, y = y0 + ly;
-    if (y >= H) continue;
-    uint8_t* p = out + img + (size_t)y * W + x;
-    if (vec) {
-      const unsigned v = *reinterpret_cast<const unsigned*>(p);
-      unsigned o = 0u;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned l = (v >> (8 * j)) & 0xffu;
-        const int lx = (4 * lane + j) & 31;
-        const unsigned f = l == 0u ? 0u : (full ? s_cell[u][(ly >> 1) * 16 + (lx >> 1)] : s_flag[u][l - 1u]);
-        o |= f << (8 * j);
-      }
-      *reinterpret_cast<unsigned*>(p) = o;
+  __syncwarp();
+  const bool any = __any_sync(0xffffffffu, mine_any), all = __all_sync(0xffffffffu, mine_all);
+  unsigned keep = 0u;  // the bits of my row that belong to the winner
+  if (any) {           // (most tiles of a blobby mask hold no part of the winner, or nothing else)
+    const unsigned m = T.bits[tile * CT + lane];
+    if (all) {
+      keep = m;
     } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (x + j >= W) break;
-        const unsigned l = p[j];
-        const int lx = (4 * lane + j) & 31;
-        p[j] = l == 0u ? 0 : (full ? s_cell[u][(ly >> 1) * 16 + (lx >> 1)] : s_flag[u][l - 1u]);
+      unsigned s = m & ~(m << 1);
+      for (int k = 0; s; ++k) {
+        const int a = __ffs(s) - 1;
+        s &= s - 1u;
+        int len;
+        const unsigned R = ccl_run(m, a, &len);
+        if (s_flag[warp][T.runcomp[(tile * CCL_RPR + k) * CT + lane]]) keep |= R;
       }
     }
+  }
+  const int x0 = tx * CT, y = ty * CT + lane;
+  if (y >= H) return;
+  uint8_t* p = out + (size_t)b * H * W + (size_t)y * W + x0;
+  if (vec_ok && x0 + CT <= W) {
+    uint4 lo, hi;
+    lo.x = ccl_expand4(keep & 15u), lo.y = ccl_expand4((keep >> 4) & 15u), lo.z = ccl_expand4((keep >> 8) & 15u);
+    lo.w = ccl_expand4((keep >> 12) & 15u), hi.x = ccl_expand4((keep >> 16) & 15u), hi.y = ccl_expand4((keep >> 20) & 15u);
+    hi.z = ccl_expand4((keep >> 24) & 15u), hi.w = ccl_expand4(keep >> 28);
+    reinterpret_cast<uint4*>(p)[0] = lo;
+    reinterpret_cast<uint4*>(p)[1] = hi;
+  } else {
+    const int nx = min(CT, W - x0);
+    for (int j = 0; j < nx; ++j) p[j] = (uint8_t)((keep >> j) & 1u);
   }
 }
 
@@ -379,7 +354,8 @@ static size_t ccl_al(size_t x) { return (x + 255) / 256 * 256; }
 extern "C" size_t wsdl_keep_largest_workspace_bytes(int B, int H, int W) {
   if (B < 1 || H < 1 || W < 1) return 0;
   const size_t tiles = (size_t)B * ((H + CT - 1) / CT) * ((W + CT - 1) / CT);
-  return 256 + ccl_al((size_t)B * 8) + ccl_al(tiles * 4) + 4 * ccl_al(tiles * CCL_MAXR * 4) + ccl_al(tiles * 128 * 2);
+  return 256 + ccl_al((size_t)B * 8) + ccl_al(tiles * 4) + 4 * ccl_al(tiles * CCL_MAXR * 4) + ccl_al(tiles * 128 * 2) +
+         ccl_al(tiles * CT * 4) + ccl_al(tiles * CCL_RPR * CT);
 }
 
 extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8_t* out, unsigned* best_area,
@@ -399,10 +375,14 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   T.min_pix = reinterpret_cast<int*>(ws), ws += ccl_al(tiles * CCL_MAXR * 4);
   T.area = reinterpret_cast<unsigned*>(ws), ws += ccl_al(tiles * CCL_MAXR * 4);
   T.parent = reinterpret_cast<int*>(ws), ws += ccl_al(tiles * CCL_MAXR * 4);
-  T.border = reinterpret_cast<unsigned short*>(ws);
+  T.border = reinterpret_cast<unsigned short*>(ws), ws += ccl_al(tiles * 128 * 2);
+  T.bits = reinterpret_cast<unsigned*>(ws), ws += ccl_al(tiles * CT * 4);
+  T.runcomp = reinterpret_cast<uint8_t*>(ws);
   cudaStream_t s = (cudaStream_t)stream;
-  const dim3 strips((tx + TPC - 1) / TPC, ty, B);
-  ccl_tile<<<strips, CCL_THREADS, 0, s>>>(mask, out, T, H, W, tx, ty);
+  const dim3 strips((tx + CCL_TPC - 1) / CCL_TPC, ty, B);
+  // 128-bit row accesses: rows of a tile start on 16-byte boundaries
+  const int vec_in = (W % 16 == 0) && ((uintptr_t)mask % 16 == 0), vec_out = (W % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  ccl_tile<<<strips, CCL_THREADS, 0, s>>>(mask, T, H, W, tx, ty, vec_in);
   const int seam_px = ((H - 1) / CT) * W + ((W - 1) / CT) * H;
   if (seam_px > 0) {
     // latency bound (dependent look-ups): a few waves of 256-thread CTAs per SM (tuning aid: WSDL_CCL_CAP)
@@ -418,7 +398,7 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
     ccl_gather<<<(int)gb, 256, 0, s>>>(T, (int)n_tiles);
     ccl_argmax<<<(int)gb, 256, 0, s>>>(T, tx * ty, (int)n_tiles);
   }
-  ccl_select<<<dim3((tx + SPC - 1) / SPC, ty, B), CCL_THREADS, 0, s>>>(out, T, best_area, H, W, tx, ty);
+  ccl_select<<<strips, CCL_THREADS, 0, s>>>(out, T, best_area, H, W, tx, ty, vec_out);
   WSDL_LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,10 @@
 #include "pairwise.cuh"
 #include "pairwise_march.cuh"
 
+#ifndef WSDL_X_SKIP
+#define WSDL_X_SKIP 0  // experiments only (dual kernel): 1 no conversion, 2 no head rows, 4 no march, 8 no band pass
+#endif
+
 namespace wsdl {
 
 
@@ -592,10 +596,14 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
         }
       }
     }
+#if !(WSDL_X_SKIP & 1)
     ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, r0, re, lane);
+#endif
     if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");
     PS_TR(2);
+#if !(WSDL_X_SKIP & 1)
     ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, re, r1, lane);
+#endif
     __syncwarp();
     PS_TR(3);
     if (warp < PS_WARPS - 1) asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
@@ -607,7 +615,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   float oy[4][2], oz[4][2];
 #pragma unroll
   for (int q = 0; q < 4; ++q) oy[q][0] = oy[q][1] = oz[q][0] = oz[q][1] = 0.f;
-  if (warp * 2 * S < K.nc) {
+  if (!(WSDL_X_SKIP & 4) && warp * 2 * S < K.nc) {
 #if WSDL_PS_PACKED
     float2 A[4][2], Bq[4][2], Cq[4][2];
 #pragma unroll
@@ -700,7 +708,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   __syncthreads();
 
   // ---- the first two rows of segments 1..7, now complete ----
-  if (seg > 0) {
+  if (!(WSDL_X_SKIP & 2) && seg > 0) {
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
       const int t = t0 + i;
@@ -721,7 +729,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 
   PS_TR(11);
   // ---- band columns (and corners) ----
-  if (K.xband) {
+  if (!(WSDL_X_SKIP & 8) && K.xband) {
     __syncthreads();
     const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
     const int ncb = nlo + nhi;
