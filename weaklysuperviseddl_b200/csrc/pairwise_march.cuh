@@ -130,10 +130,10 @@ template <int C>
 __device__ __forceinline__ void ps_exchange(const float (&X)[8][C], float (&own)[4][C], int strip) {
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    float r0 = __shfl_down_sync(0xffffffffu, X[0][c], 1), r1 = __shfl_down_sync(0xffffffffu, X[1][c], 1);
-    float l0 = __shfl_up_sync(0xffffffffu, X[6][c], 1), l1 = __shfl_up_sync(0xffffffffu, X[7][c], 1);
-    if (strip == 15) r0 = 0.f, r1 = 0.f;
-    if (strip == 0) l0 = 0.f, l1 = 0.f;
+    const float r0 = __shfl_down_sync(0xffffffffu, X[0][c], 1), r1 = __shfl_down_sync(0xffffffffu, X[1][c], 1);
+    const float l0 = __shfl_up_sync(0xffffffffu, X[6][c], 1), l1 = __shfl_up_sync(0xffffffffu, X[7][c], 1);
+    // strip 0 receives nothing real from its left and strip 15 nothing from its right (the lane there belongs to the
+    // other segment): the two sums that take those values are the tile's halo columns, which no caller keeps
     own[0][c] = X[2][c] + l0;
     own[1][c] = X[3][c] + l1;
     own[2][c] = X[4][c] + r0;
@@ -239,10 +239,9 @@ template <int CS>
 __device__ __forceinline__ void ps_exchangep(const float2 (&X)[4][CS], float (&own)[4][CS], int strip) {
 #pragma unroll
   for (int c = 0; c < CS; ++c) {
-    float r0 = __shfl_down_sync(0xffffffffu, X[0][c].x, 1), r1 = __shfl_down_sync(0xffffffffu, X[0][c].y, 1);
-    float l0 = __shfl_up_sync(0xffffffffu, X[3][c].x, 1), l1 = __shfl_up_sync(0xffffffffu, X[3][c].y, 1);
-    if (strip == 15) r0 = 0.f, r1 = 0.f;
-    if (strip == 0) l0 = 0.f, l1 = 0.f;
+    const float r0 = __shfl_down_sync(0xffffffffu, X[0][c].x, 1), r1 = __shfl_down_sync(0xffffffffu, X[0][c].y, 1);
+    const float l0 = __shfl_up_sync(0xffffffffu, X[3][c].x, 1), l1 = __shfl_up_sync(0xffffffffu, X[3][c].y, 1);
+    // (strip 0 / strip 15: what arrives from the other segment's lane only reaches halo columns -- see ps_exchange)
     own[0][c] = X[1][c].x + l0;
     own[1][c] = X[1][c].y + l1;
     own[2][c] = X[2][c].x + r0;
@@ -411,6 +410,68 @@ __device__ __forceinline__ void ps_xfix_item(int H, float g1, float g4, float es
   }
 }
 
+// The same for the cut loss (gamma = 1, squared distances as staged) and the boundary loss (gamma_b, distances times
+// `ratio`) of one band pixel at once: the two corrections differ in their weights only, so the partner loads, the colour
+// differences and p(a) - p(b) are shared.  s_wxc / s_wxb: the pixel's column-weight rows of the two tables.
+__device__ __forceinline__ void ps_xfix_dual(int H, float g1b, float g4b, float ratio, const float* s_img, const float* s_p,
+                                             const float* s_wxc, const float* s_wxb, int ys, int x0, int zy, int zx,
+                                             float& ac, float& ab, float& pz) {
+  const int so = (zy - (ys - 2)) * PS_PITCH + (zx - (x0 - 4));
+  const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
+  pz = s_p[so];
+  // the (at most two) partner columns whose weights are not the interior ones: reflect geometry, the same for both losses
+  int jsp[2] = {-1, -1};
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float f = s_wxc[j], b = s_wxc[5 + j];
+    if (f != 0.f && (f != 1.f || b != 1.f)) {
+      if (jsp[0] < 0) jsp[0] = j;
+      else jsp[1] = j;
+    }
+  }
+  float wc[5][3], wb[5][3];  // per partner row: forward, backward, applied by the march
+  if (zy >= 5 && zy <= H - 6) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float g = ps_gpow(i < 2 ? 2 - i : i - 2, g1b, g4b);
+      wc[i][0] = wc[i][1] = 1.f, wc[i][2] = 2.f;
+      wb[i][0] = wb[i][1] = g, wb[i][2] = 2.f * g;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int yb = zy + i - 2;
+      const bool in = yb >= 0 && yb < H;
+      const int dd = i < 2 ? 2 - i : i - 2;
+      wc[i][0] = in ? ps_w1d(zy, yb, H, 1.f, 1.f) : 0.f;
+      wc[i][1] = in ? ps_w1d(yb, zy, H, 1.f, 1.f) : 0.f;
+      wc[i][2] = in ? 2.f * ps_row_mult(zy, yb, H, 1.f) : 0.f;
+      wb[i][0] = in ? ps_w1d(zy, yb, H, g1b, g4b) : 0.f;
+      wb[i][1] = in ? ps_w1d(yb, zy, H, g1b, g4b) : 0.f;
+      wb[i][2] = in ? 2.f * ps_gpow(dd, g1b, g4b) * ps_row_mult(zy, yb, H, g4b) : 0.f;
+    }
+  }
+  ac = 0.f, ab = 0.f;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = jsp[u] < 0 ? 2 : jsp[u];  // no such column: the pixel's own (weight 0 below)
+    const float live = jsp[u] < 0 ? 0.f : 0.5f;
+    const float cf = s_wxc[j], cb = s_wxc[5 + j];
+    const float bf = s_wxb[j], bb = s_wxb[5 + j], gx = ps_gpow(j < 2 ? 2 - j : j - 2, g1b, g4b);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float dc = live * (fmaf(wc[i][0], cf, wc[i][1] * cb) - wc[i][2]);  // 0 for rows outside the image
+      const float db = live * (fmaf(wb[i][0], bf, wb[i][1] * bb) - wb[i][2] * gx);
+      const int sn = so + (i - 2) * PS_PITCH + (j - 2);
+      const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+      const float e = fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0));
+      const float dp = pz - s_p[sn];
+      ac = fmaf(dc * ex2_approx(e), dp, ac);
+      ab = fmaf(db * ex2_approx(ratio * e), dp, ab);
+    }
+  }
+}
+
 // ---- staging ----
 __device__ __forceinline__ unsigned ps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -435,65 +496,95 @@ __device__ __noinline__ void ps_rows_load_slow(const PsParams& Q, const PsBlk& K
 }
 
 // Rows [r0, r1) of the tile, in place: image * sqrt(-kc) (sentinel outside the image), values -> probabilities.
+// The pass is a latency chain (LDS -> FMUL / MUFU.EX2 / MUFU.RCP -> STS) run by a warp that has nothing else to do, so
+// PS_CONV_U groups of four pixels are in flight per lane (loads first, then arithmetic, then stores), the loop carries no
+// per-group border logic, and the positions outside the image -- whole rows and whole column ranges of a border tile --
+// get their sentinel colour in a short second pass.
+#ifndef WSDL_PS_CONV_U
+#define WSDL_PS_CONV_U 1
+#endif
+constexpr int PS_CONV_U = WSDL_PS_CONV_U;
+
 template <int C, int CS, bool SOFTMAX>
 __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk& K, float* s_img, float* s_val, int r0,
                                                   int r1, int lane) {
   const int H = Q.p.H, W = Q.p.W;
   const float sc = Q.img_scale;
-#pragma unroll 2
-  for (int it = r0 * PS_Q + lane; it < r1 * PS_Q; it += 32) {
-    const int t = it / PS_Q, q = it - t * PS_Q;
-    const int y = K.ys - 2 + t, xb = K.x0 - 4 + 4 * q;
-    const bool row_in = y >= 0 && y < H;
-    const int so = it * 4;  // PS_PITCH == 4 * PS_Q
-    float4 v[3];
+  const int i1 = r1 * PS_Q;
+  for (int base0 = r0 * PS_Q; base0 < i1; base0 += 32 * PS_CONV_U) {  // warp-uniform trip count (__syncwarp inside)
+    const int base = base0 + lane;
+    float4 v[PS_CONV_U][3], u[PS_CONV_U][C];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = *reinterpret_cast<const float4*>(s_img + c * PS_PLANE + so);
-    float4 u[C];
+    for (int k = 0; k < PS_CONV_U; ++k) {
+      const int so = min(base + 32 * k, i1 - 1) * 4;  // PS_PITCH == 4 * PS_Q; a lane past the end re-reads the last group
 #pragma unroll
-    for (int c = 0; c < C; ++c) u[c] = *reinterpret_cast<const float4*>(s_val + c * PS_PLANE + so);
+      for (int c = 0; c < 3; ++c) v[k][c] = *reinterpret_cast<const float4*>(s_img + c * PS_PLANE + so);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = make_float4(v[c].x * sc, v[c].y * sc, v[c].z * sc, v[c].w * sc);
-    if (!row_in || xb < 0 || xb + 3 >= W) {  // some element lies outside the image (rare: border tiles only)
-      const bool all_out = !row_in || xb + 3 < 0 || xb >= W;
-      if (all_out) {
-        v[0] = make_float4(PS_SENTINEL, PS_SENTINEL, PS_SENTINEL, PS_SENTINEL);
-      } else {  // a group straddling the border: widths that are not a multiple of 4
-        if (xb + 0 < 0 || xb + 0 >= W) v[0].x = PS_SENTINEL;
-        if (xb + 1 < 0 || xb + 1 >= W) v[0].y = PS_SENTINEL;
-        if (xb + 2 < 0 || xb + 2 >= W) v[0].z = PS_SENTINEL;
-        if (xb + 3 < 0 || xb + 3 >= W) v[0].w = PS_SENTINEL;
-      }
+      for (int c = 0; c < C; ++c) u[k][c] = *reinterpret_cast<const float4*>(s_val + c * PS_PLANE + so);
     }
+    __syncwarp();  // every lane holds its groups before anyone overwrites one (the clamped re-reads)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = v[c];
-    float w[C][4];
+    for (int k = 0; k < PS_CONV_U; ++k) {
+      const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
-    for (int c = 0; c < C; ++c) w[c][0] = u[c].x, w[c][1] = u[c].y, w[c][2] = u[c].z, w[c][3] = u[c].w;
-    if (CS != C) {  // p0 = 1 / (1 + e^(v1 - v0))
+      for (int c = 0; c < 3; ++c) {  // two-lane FP32: half the issue slots
+        const float2 lo = __fmul2_rn(make_float2(v[k][c].x, v[k][c].y), sc2), hi = __fmul2_rn(make_float2(v[k][c].z, v[k][c].w), sc2);
+        v[k][c] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+      float w[C][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) w[0][e] = rcp_approx(1.f + ex2_approx((w[1][e] - w[0][e]) * LOG2E));
-    } else if (SOFTMAX) {
+      for (int c = 0; c < C; ++c) w[c][0] = u[k][c].x, w[c][1] = u[k][c].y, w[c][2] = u[k][c].z, w[c][3] = u[k][c].w;
+      if (CS != C) {  // p0 = 1 / (1 + e^(v1 - v0))
+        const float2 l2 = make_float2(LOG2E, LOG2E), one = make_float2(1.f, 1.f);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float m = w[0][e];
-#pragma unroll
-        for (int c = 1; c < C; ++c) m = fmaxf(m, w[c][e]);
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          w[c][e] = ex2_approx((w[c][e] - m) * LOG2E);
-          s += w[c][e];
+        for (int h = 0; h < 2; ++h) {
+          const float2 z = __fmul2_rn(__fadd2_rn(make_float2(w[1][2 * h], w[1][2 * h + 1]), make_float2(-w[0][2 * h], -w[0][2 * h + 1])), l2);
+          const float2 d = __fadd2_rn(make_float2(ex2_approx(z.x), ex2_approx(z.y)), one);
+          w[0][2 * h] = rcp_approx(d.x), w[0][2 * h + 1] = rcp_approx(d.y);
         }
-        const float inv = rcp_approx(s);
+      } else if (SOFTMAX) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) w[c][e] *= inv;
+        for (int e = 0; e < 4; ++e) {
+          float m = w[0][e];
+#pragma unroll
+          for (int c = 1; c < C; ++c) m = fmaxf(m, w[c][e]);
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            w[c][e] = ex2_approx((w[c][e] - m) * LOG2E);
+            sum += w[c][e];
+          }
+          const float inv = rcp_approx(sum);
+#pragma unroll
+          for (int c = 0; c < C; ++c) w[c][e] *= inv;
+        }
+      }
+      if (base + 32 * k < i1) {
+        const int so = (base + 32 * k) * 4;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = v[k][c];
+        if (CS != C || SOFTMAX) {
+#pragma unroll
+          for (int c = 0; c < CS; ++c)
+            *reinterpret_cast<float4*>(s_val + c * PS_PLANE + so) = make_float4(w[c][0], w[c][1], w[c][2], w[c][3]);
+        }
       }
     }
-    if (CS != C || SOFTMAX) {
-#pragma unroll
-      for (int c = 0; c < CS; ++c)
-        *reinterpret_cast<float4*>(s_val + c * PS_PLANE + so) = make_float4(w[c][0], w[c][1], w[c][2], w[c][3]);
+  }
+  // sentinel colour (channel 0) outside the image: block-uniform tests, a handful of stores on border tiles only
+  const int cl = max(0, 4 - K.x0);               // staged columns [0, cl) lie left of the image
+  const int cr = min(PS_PITCH, W - (K.x0 - 4));  // staged columns [cr, 68) lie right of it
+  const int t_top = min(r1, 2 - K.ys), t_bot = max(r0, H - K.ys + 2);  // rows [r0, t_top) and [t_bot, r1) lie outside
+  if (cl > 0 || cr < PS_PITCH || t_top > r0 || t_bot < r1) {
+    __syncwarp();
+    for (int t = r0 + lane; t < r1; t += 32) {  // a lane per row (a warp converts at most 12)
+      for (int x = 0; x < cl; ++x) s_img[t * PS_PITCH + x] = PS_SENTINEL;
+      for (int x = cr; x < PS_PITCH; ++x) s_img[t * PS_PITCH + x] = PS_SENTINEL;
+    }
+    const float4 s4 = make_float4(PS_SENTINEL, PS_SENTINEL, PS_SENTINEL, PS_SENTINEL);
+    if (lane < PS_Q) {
+      for (int tt = r0; tt < t_top; ++tt) *reinterpret_cast<float4*>(s_img + tt * PS_PITCH + 4 * lane) = s4;
+      for (int tt = t_bot; tt < r1; ++tt) *reinterpret_cast<float4*>(s_img + tt * PS_PITCH + 4 * lane) = s4;
     }
   }
 }

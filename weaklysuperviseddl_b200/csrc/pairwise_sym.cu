@@ -444,14 +444,11 @@ __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, 
   const int H = Q.p.H, W = Q.p.W;
   const int y = K.ys - 2 + t;
   const int xs = K.x0 - 2 + 4 * strip;
-  if (K.xband) {  // block-uniform: the band-column pass finishes these pixels from their G
+  if (okmask >> 4) {  // this lane owns band-column pixels (bits 4.. : their slots + 1): the band pass finishes them from G
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int slot = ps_band_slot(xs + j, W);
-      if (((okmask >> j) & 1) && slot >= 0) {
-        s_gband[t * PS_PITCH + slot * 2 + 0] = G[j][0];
-        s_gband[t * PS_PITCH + slot * 2 + 1] = G[j][1];
-      }
+      const int slot1 = (okmask >> (4 + 4 * j)) & 15;
+      if (slot1) *reinterpret_cast<float2*>(s_gband + t * PS_PITCH + (slot1 - 1) * 2) = make_float2(G[j][0], G[j][1]);
     }
   }
   float out[4];
@@ -484,7 +481,7 @@ __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, 
   }
 }
 
-constexpr size_t PS_DUAL_SMEM_FLOATS = (size_t)5 * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * 2 * 64 + 2 * 6 * 10;
+constexpr size_t PS_DUAL_SMEM_FLOATS = (size_t)5 * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * 2 * 64 + 2 * 6 * 10 + 6 * 2 * 8 + 11 * 5 * 8;
 
 __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     pairwise_dual_kernel(const __grid_constant__ PsParams Q, const __grid_constant__ PsDual D,
@@ -498,6 +495,8 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   // once a row is converted (p0 lives in plane 0), and a row's entries are written by the warp that converted it
   float* s_gband = s_p + PS_PLANE;                       // [row t][6 slots][cut, boundary]
   float* s_wx = s_head + (PS_SEGS - 1) * 2 * 2 * 64;     // [2][6][2][5]: column weights, cut then boundary
+  float* s_fx = s_wx + 2 * 6 * 10;                       // [6][2][8]: per band slot, its two special partner columns
+  float* s_wy = s_fx + 6 * 2 * 8;                        // [11][5][8]: row weights of the 10 row-band rows + the interior
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ float s_red[2][PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
@@ -548,11 +547,14 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   }
   K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out) : 1.f);
   const float scale_b = (float)(4.0 * D.kappa_bnd) * (D.grad_out_bnd ? __ldg(D.grad_out_bnd + K.b) : 1.f);
-  int okmask = 0;
+  int okmask = 0;  // bits 0..3: pixel j of the strip is owned; bits 4 + 4 j ..: its band slot + 1 (0: not a band column)
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int col = 4 * strip + j;
-    if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
+    const bool ok = col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W;
+    if (ok) okmask |= 1 << j;
+    const int slot = ok ? ps_band_slot(K.x0 - 2 + col, W) : -1;
+    if (slot >= 0) okmask |= (slot + 1) << (4 + 4 * j);
   }
   float lsum_c = 0.f, lsum_b = 0.f;
   if (K.xband && tid < 120) {  // column weights of the band slots for gamma = 1 (cut) and gamma_b (boundary)
@@ -564,6 +566,45 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     s_wx[tid] = w;
   }
   __syncthreads();  // s_bar is initialised
+  if (K.xband && tid < 12) {
+    // A band pixel differs from the interior in at most two partner columns (the reflect geometry, the same for both
+    // losses).  Per slot and such column: its offset and 1/2 of the column weights Wx(a->b), Wx(b->a), gamma_b^dx^2.
+    const int slot = tid >> 1, u = tid & 1;
+    const float* wc = s_wx + slot * 10;
+    const float* wb = s_wx + 60 + slot * 10;
+    int found = -1, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float f = wc[j], b = wc[5 + j];
+      if (f != 0.f && (f != 1.f || b != 1.f)) {
+        if (cnt == u) found = j;
+        ++cnt;
+      }
+    }
+    const int j = found < 0 ? 2 : found;  // no such column: the pixel's own, weight 0
+    const float live = found < 0 ? 0.f : 0.5f;
+    float* fx = s_fx + tid * 8;
+    fx[0] = __int_as_float(j), fx[1] = live * wc[j], fx[2] = live * wc[5 + j], fx[3] = live;
+    fx[4] = live * wb[j], fx[5] = live * wb[5 + j], fx[6] = live * ps_gpow(j < 2 ? 2 - j : j - 2, D.g1b, D.g4b), fx[7] = 0.f;
+  } else if (K.xband && tid >= 32 && tid < 32 + 55) {
+    // Row weights of a band pixel in row zy towards its partner row zy + i - 2: forward, backward, and what the march
+    // applied (cut: gamma = 1; boundary: gamma_b).  Slots 0..4: rows 0..4, 5..9: rows H-5..H-1, 10: every other row.
+    const int rs = (tid - 32) / 5, i = (tid - 32) - rs * 5, dd = i < 2 ? 2 - i : i - 2;
+    const float g = ps_gpow(dd, D.g1b, D.g4b);
+    float4 a = make_float4(1.f, 1.f, 2.f, g), b4 = make_float4(g, 2.f * g, 0.f, 0.f);
+    if (rs < 10) {
+      const int zy = rs < 5 ? rs : H - 10 + rs, yb = zy + i - 2;
+      const bool in = yb >= 0 && yb < H;
+      a.x = in ? ps_w1d(zy, yb, H, 1.f, 1.f) : 0.f;
+      a.y = in ? ps_w1d(yb, zy, H, 1.f, 1.f) : 0.f;
+      a.z = in ? 2.f * ps_row_mult(zy, yb, H, 1.f) : 0.f;
+      a.w = in ? ps_w1d(zy, yb, H, D.g1b, D.g4b) : 0.f;
+      b4.x = in ? ps_w1d(yb, zy, H, D.g1b, D.g4b) : 0.f;
+      b4.y = in ? 2.f * g * ps_row_mult(zy, yb, H, D.g4b) : 0.f;
+    }
+    *reinterpret_cast<float4*>(s_wy + (tid - 32) * 8) = a;
+    *reinterpret_cast<float4*>(s_wy + (tid - 32) * 8 + 4) = b4;
+  }
 
   {
     const int r0 = min(2 * warp * S, rows), r1 = warp == PS_WARPS - 1 ? rows : min(2 * (warp + 1) * S, rows);
@@ -730,7 +771,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   PS_TR(11);
   // ---- band columns (and corners) ----
   if (!(WSDL_X_SKIP & 8) && K.xband) {
-    __syncthreads();
+    if (!(WSDL_X_SKIP & 64)) __syncthreads();
     const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
     const int ncb = nlo + nhi;
     const size_t plane = (size_t)H * W;
@@ -738,15 +779,45 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       const int ty = i / ncb, k = i - ty * ncb;
       const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
       const int slot = ps_band_slot(x, W);
-      float ac[1], ab[1], pz[1];
-      ps_xfix_item<1>(H, 1.f, 1.f, 1.f, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, ac, pz);
-      ps_xfix_item<1>(H, D.g1b, D.g4b, D.ratio, s_img, s_p, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ab, pz);
-      const float p0 = pz[0], p1 = 1.f - p0;
-      lsum_c = fmaf(p0 - p1, ac[0], lsum_c);  // the losses are linear in G: the corrections' share
-      lsum_b = fmaf(p0 - p1, ab[0], lsum_b);
-      if (Q.p.grad_values) {
-        const float gc = ac[0] + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 0];
-        const float gb = ab[0] + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 1];
+      float ac, ab, p0;
+      if (WSDL_X_SKIP & 32) {
+        ac = ab = 0.f, p0 = 0.5f;
+      } else if (H >= 10) {
+        // (true pair weight - weight the march applied) / 2 * k (p(a) - p(b)) over the five rows of the two special
+        // partner columns, both losses from one set of loads and one squared distance; weights from the two tables
+        const int so = (ty + 2) * PS_PITCH + (x - (K.x0 - 4));
+        const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
+        p0 = s_p[so];
+        const float* wy = s_wy + (y < 5 ? y : (y > H - 6 ? y - (H - 10) : 10)) * 40;
+        ac = 0.f, ab = 0.f;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 fc = *reinterpret_cast<const float4*>(s_fx + (slot * 2 + u) * 8);
+          const float4 fb = *reinterpret_cast<const float4*>(s_fx + (slot * 2 + u) * 8 + 4);
+          const int sj = so + __float_as_int(fc.x) - 2;
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const float4 wa = *reinterpret_cast<const float4*>(wy + r * 8);
+            const float2 wb2 = *reinterpret_cast<const float2*>(wy + r * 8 + 4);
+            const int sn = sj + (r - 2) * PS_PITCH;  // rows outside the image: weights 0, the staged values are finite
+            const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+            const float e = fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0));
+            const float dp = p0 - s_p[sn];
+            const float dc = fmaf(wa.x, fc.y, fmaf(wa.y, fc.z, -fc.w * wa.z));
+            const float db = fmaf(wa.w, fb.x, fmaf(wb2.x, fb.y, -fb.z * wb2.y));
+            ac = fmaf(dc * ex2_approx(e), dp, ac);
+            ab = fmaf(db * ex2_approx(D.ratio * e), dp, ab);
+          }
+        }
+      } else {
+        ps_xfix_dual(H, D.g1b, D.g4b, D.ratio, s_img, s_p, s_wx + slot * 10, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ac, ab, p0);
+      }
+      const float p1 = 1.f - p0;
+      lsum_c = fmaf(p0 - p1, ac, lsum_c);  // the losses are linear in G: the corrections' share
+      lsum_b = fmaf(p0 - p1, ab, lsum_b);
+      if (!(WSDL_X_SKIP & 16) && Q.p.grad_values) {
+        const float gc = ac + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 0];
+        const float gb = ab + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 1];
         const float o = 2.f * p0 * p1 * fmaf(K.scale2, gc, scale_b * gb);
         float* go = Q.p.grad_values + (size_t)K.b * 2 * plane + (size_t)y * W + x;
         go[0] = o, go[plane] = -o;
