@@ -28,7 +28,10 @@ for rep in range(3):
 g = torch.Generator(device="cuda").manual_seed(0)
 f = torch.nn.functional.avg_pool2d(torch.rand(128, 1, 512 + 32, 512 + 32, device="cuda", generator=g), 33, stride=1)[:, 0]
 m = (f > f.mean()).to(torch.uint8).contiguous()
+fc = torch.nn.functional.interpolate(torch.rand(128, 1, 16, 16, device="cuda", generator=g), size=(512, 512), mode="bilinear")[:, 0]
+mc = (fc > 0.5).to(torch.uint8).contiguous()  # CAM-like masks: smooth outlines
 for _ in range(2):
     WF.keep_largest(m)
+    WF.keep_largest(mc)
 torch.cuda.synchronize()
 print("ok")

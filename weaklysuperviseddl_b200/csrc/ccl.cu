@@ -13,8 +13,9 @@
 //                  leaves the SM is small: the 32 row words, one byte per run (its component number), the tile's component
 //                  table (first pixel, area, union-find parent = itself) and the component numbers of its 124 border
 //                  pixels.  The mask itself is read once and nothing per-pixel is written.
-//   2. ccl_seams   joins across tile seams on the COMPONENT tables (node = tile * 256 + k), reading the compact border
-//                  records: a seam pixel costs two bytes from a dense array instead of a 32-byte sector of a label map.
+//   2. ccl_seams   joins across tile seams on the COMPONENT tables (node = tile * 256 + k), one warp per tile again: the
+//                  seam with the tile on the left row by row from the two tiles' border records, the seam with the tile
+//                  above run by run from the two row words -- no per-pixel label map is ever consulted.
 //   3. ccl_gather  every local component adds its area and its first pixel (min) to its global root;
 //      ccl_argmax  true roots compete for the per-image (area, -first pixel) maximum packed in one u64 atomicMax.
 //   4. ccl_select  one warp per tile again: "does local component k belong to the winner?" for its <= 256 components, then
@@ -134,7 +135,21 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
   for (int k = 0; k < nr; ++k) par[lane * CCL_RPR + k] = lane * CCL_RPR + k, cnt[lane * CCL_RPR + k] = 0u;
   if (lane == 0) s_n[warp] = 0;
   __syncwarp();
-  {  // a run joins every run of the row above that has a pixel under its span widened by one column either side
+  {  // A run joins every run of the row above that has a pixel under its span widened by one column either side.  The
+     // first such run becomes its parent with a plain store (a node is written by its own lane only; the link goes to
+     // a smaller node, like every union) -- the common case costs no find and no atomic.
+    unsigned s = st;
+    for (int k = 0; s; ++k) {
+      const int a = __ffs(s) - 1;
+      s &= s - 1u;
+      int len;
+      const unsigned R = ccl_run(m, a, &len);
+      const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
+      if (touched) par[lane * CCL_RPR + k] = (lane - 1) * CCL_RPR + ccl_run_of(ust, __ffs(touched) - 1);
+    }
+  }
+  __syncwarp();
+  {  // a run that touches several runs of the row above merges their components: real unions, on the row above
     unsigned s = st;
     for (int k = 0; s; ++k) {
       const int a = __ffs(s) - 1;
@@ -143,14 +158,27 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
       const unsigned R = ccl_run(m, a, &len);
       const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
       unsigned ts = touched & ~(touched << 1);  // one group of touched bits per run of the row above
-      while (ts) {
-        const int p = __ffs(ts) - 1;
+      if (ts & (ts - 1u)) {
+        const int first = (lane - 1) * CCL_RPR + ccl_run_of(ust, __ffs(ts) - 1);
         ts &= ts - 1u;
-        uf_union(par, lane * CCL_RPR + k, (lane - 1) * CCL_RPR + ccl_run_of(ust, p));
+        while (ts) {
+          const int p = __ffs(ts) - 1;
+          ts &= ts - 1u;
+          uf_union(par, first, (lane - 1) * CCL_RPR + ccl_run_of(ust, p));
+        }
       }
     }
   }
   __syncwarp();
+  // pointer jumping: a blob that spans the tile is a chain of 32 runs; five halvings leave (almost) every run at its root
+#pragma unroll 1
+  for (int round = 0; round < 5; ++round) {
+    for (int k = 0; k < nr; ++k) {
+      const int i = lane * CCL_RPR + k;
+      par[i] = par[par[i]];
+    }
+    __syncwarp();
+  }
   {  // flatten, add the run's length to its root's count, number the components
     unsigned s = st;
     for (int k = 0; s; ++k) {
@@ -199,48 +227,61 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
   }
 }
 
-// component index of a BORDER pixel (y, x) of image b, or CCL_BG
-__device__ __forceinline__ int ccl_border(const CclTables& T, int b, int y, int x, int tiles_x, int tiles_y, int* node) {
-  const int ty = y / CT, tx = x / CT, ly = y - ty * CT, lx = x - tx * CT;
+// Joins across the tile seams, on the component tables (node = tile * 256 + component).  One warp per tile:
+//   * the seam with the tile on the LEFT, lane = row: my column 0 against its column 31 (rows r-1, r, r+1; the diagonal
+//     partners are skipped when the straight one exists -- they are its vertical neighbours, already joined inside the tile);
+//   * the seam with the tile ABOVE, lane = run of my row 0: the same run-against-word arithmetic as inside a tile, plus
+//     the two corner pixels of the tiles above-left / above-right (every diagonal that crosses a tile corner goes
+//     up-left or up-right from some tile's first row, so this covers them all).
+__global__ void __launch_bounds__(CCL_THREADS) ccl_seams(CclTables T, int tiles_x, int tiles_y) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x * CCL_TPC + warp;
+  if (tx >= tiles_x) return;
   const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx;
-  const unsigned short* rec = T.border + tile * 128;
-  const unsigned short v = ly == 0 ? rec[lx] : (ly == CT - 1 ? rec[32 + lx] : (lx == 0 ? rec[64 + ly] : rec[96 + ly]));
-  *node = (int)(tile * CCL_MAXR + v);
-  return v;
-}
-
-// joins across the tile seams; one thread per seam pixel (first row and first column of every tile)
-__global__ void ccl_seams(CclTables T, int H, int W, int tiles_x, int tiles_y) {
-  const int b = blockIdx.y;
-  const int rows = (H - 1) / CT, cols = (W - 1) / CT;  // interior seams
-  const int n_row = rows * W, n_col = cols * H;
   int* P = T.parent;
-#define CCL_AT(yy, xx, nd) (ccl_border(T, b, (yy), (xx), tiles_x, tiles_y, &(nd)) != CCL_BG)
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_row + n_col; t += gridDim.x * blockDim.x) {
-    int me, a, c, d, dummy;
-    if (t < n_row) {  // pixel (y, x) in the first row of a tile: N, NW, NE are across the seam
-      const int y = (t / W + 1) * CT, x = t % W;
-      if (!CCL_AT(y, x, me)) continue;
-      const bool n = CCL_AT(y - 1, x, a);
-      const bool w = x > 0 && CCL_AT(y, x - 1, dummy), nw = x > 0 && CCL_AT(y - 1, x - 1, c);
-      const bool e = x + 1 < W && CCL_AT(y, x + 1, dummy), ne = x + 1 < W && CCL_AT(y - 1, x + 1, d);
-      // the left / right neighbour's own seam join covers ours exactly as inside a tile, whichever tile it is in
-      if (n) {
-        if (!(w && nw)) uf_union(P, me, a);
+  const unsigned m = T.bits[tile * CT + lane];
+  if (tx > 0) {
+    const size_t tl = tile - 1;
+    const unsigned col = __ballot_sync(0xffffffffu, T.bits[tl * CT + lane] >> 31);  // the left tile's right column, bit = row
+    if ((m & 1u) && (col >> (lane ? lane - 1 : 0) & 7u)) {
+      const int me = (int)(tile * CCL_MAXR) + T.border[tile * 128 + 64 + lane];
+      const unsigned short* rl = T.border + tl * 128 + 96;
+      const int base = (int)(tl * CCL_MAXR);
+      if ((col >> lane) & 1u) {
+        uf_union(P, me, base + rl[lane]);
       } else {
-        if (nw && !w) uf_union(P, me, c);
-        if (ne && !e) uf_union(P, me, d);
+        if (lane > 0 && ((col >> (lane - 1)) & 1u)) uf_union(P, me, base + rl[lane - 1]);
+        if (lane < CT - 1 && ((col >> (lane + 1)) & 1u)) uf_union(P, me, base + rl[lane + 1]);
       }
-    } else {  // pixel in the first column of a tile: W, NW, SW are across the seam
-      const int u = t - n_row;
-      const int x = (u / H + 1) * CT, y = u % H;
-      if (!CCL_AT(y, x, me)) continue;
-      if (CCL_AT(y, x - 1, a)) uf_union(P, me, a);
-      if (y > 0 && CCL_AT(y - 1, x - 1, c)) uf_union(P, me, c);
-      if (y + 1 < H && CCL_AT(y + 1, x - 1, d)) uf_union(P, me, d);
     }
   }
-#undef CCL_AT
+  if (ty > 0) {
+    const size_t tu = tile - tiles_x;
+    const unsigned cur = __shfl_sync(0xffffffffu, m, 0);
+    const unsigned up = T.bits[tu * CT + CT - 1];
+    const unsigned st = cur & ~(cur << 1), ust = up & ~(up << 1);
+    if (lane < __popc(st)) {
+      const int a = __fns(st, 0, lane + 1);  // start of my run
+      int len;
+      const unsigned R = ccl_run(cur, a, &len);
+      const int me = (int)(tile * CCL_MAXR) + T.runcomp[(tile * CCL_RPR + lane) * CT];
+      const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
+      unsigned ts = touched & ~(touched << 1);
+      while (ts) {
+        const int p = __ffs(ts) - 1;
+        ts &= ts - 1u;
+        uf_union(P, me, (int)(tu * CCL_MAXR) + T.runcomp[(tu * CCL_RPR + ccl_run_of(ust, p)) * CT + CT - 1]);
+      }
+      if (a == 0 && tx > 0 && !(up & 1u)) {  // (with a pixel straight above, the corner pixel is its row neighbour)
+        const unsigned short v = T.border[(tu - 1) * 128 + 32 + CT - 1];
+        if (v != CCL_BG) uf_union(P, me, (int)((tu - 1) * CCL_MAXR) + v);
+      }
+      if (a + len == CT && tx + 1 < tiles_x && !(up >> 31)) {
+        const unsigned short v = T.border[(tu + 1) * 128 + 32];
+        if (v != CCL_BG) uf_union(P, me, (int)((tu + 1) * CCL_MAXR) + v);
+      }
+    }
+  }
 }
 
 // Local components hand their area and first pixel to their global root; eight threads per tile (a tile of a blobby mask
@@ -383,15 +424,7 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   // 128-bit row accesses: rows of a tile start on 16-byte boundaries
   const int vec_in = (W % 16 == 0) && ((uintptr_t)mask % 16 == 0), vec_out = (W % 16 == 0) && ((uintptr_t)out % 16 == 0);
   ccl_tile<<<strips, CCL_THREADS, 0, s>>>(mask, T, H, W, tx, ty, vec_in);
-  const int seam_px = ((H - 1) / CT) * W + ((W - 1) / CT) * H;
-  if (seam_px > 0) {
-    // latency bound (dependent look-ups): a few waves of 256-thread CTAs per SM (tuning aid: WSDL_CCL_CAP)
-    static const int cap_mult = WSDL_TUNE_INT("WSDL_CCL_CAP", 32) > 0 ? WSDL_TUNE_INT("WSDL_CCL_CAP", 32) : 32;
-    const int cap = (WSDL_NUM_SMS * cap_mult + B - 1) / B;
-    int sb = (seam_px + 255) / 256;
-    if (sb > cap) sb = cap < 1 ? 1 : cap;
-    ccl_seams<<<dim3(sb, B), 256, 0, s>>>(T, H, W, tx, ty);
-  }
+  if (tx > 1 || ty > 1) ccl_seams<<<strips, CCL_THREADS, 0, s>>>(T, tx, ty);
   {
     long long gb = (n_tiles * 8 + 255) / 256;
     if (gb > WSDL_NUM_SMS * 16) gb = WSDL_NUM_SMS * 16;
