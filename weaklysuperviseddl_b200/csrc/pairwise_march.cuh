@@ -149,11 +149,11 @@ struct PsWinP {
   float2 e[3 + CS][4];  // [plane: I0, I1, I2, p...][even pair = columns (2k, 2k+1) of the 8-column window]
 };
 
-template <int CS>
+template <int CS, int PLANE = PS_PLANE>
 __device__ __forceinline__ void ps_loadp(PsWinP<CS>& w, const float* s_img, const float* s_p, int off) {
 #pragma unroll
   for (int c = 0; c < 3 + CS; ++c) {
-    const float* src = (c < 3 ? s_img + c * PS_PLANE : s_p + (c - 3) * PS_PLANE) + off;
+    const float* src = (c < 3 ? s_img + c * PLANE : s_p + (c - 3) * PLANE) + off;
     const float4 a = *reinterpret_cast<const float4*>(src);
     const float4 b = *reinterpret_cast<const float4*>(src + 4);
     w.e[c][0] = make_float2(a.x, a.y), w.e[c][1] = make_float2(a.z, a.w);
@@ -413,11 +413,12 @@ __device__ __forceinline__ void ps_xfix_item(int H, float g1, float g4, float es
 // The same for the cut loss (gamma = 1, squared distances as staged) and the boundary loss (gamma_b, distances times
 // `ratio`) of one band pixel at once: the two corrections differ in their weights only, so the partner loads, the colour
 // differences and p(a) - p(b) are shared.  s_wxc / s_wxb: the pixel's column-weight rows of the two tables.
+template <int PLANE = PS_PLANE>
 __device__ __forceinline__ void ps_xfix_dual(int H, float g1b, float g4b, float ratio, const float* s_img, const float* s_p,
                                              const float* s_wxc, const float* s_wxb, int ys, int x0, int zy, int zx,
                                              float& ac, float& ab, float& pz) {
   const int so = (zy - (ys - 2)) * PS_PITCH + (zx - (x0 - 4));
-  const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
+  const float i0 = s_img[so], i1 = s_img[PLANE + so], i2 = s_img[2 * PLANE + so];
   pz = s_p[so];
   // the (at most two) partner columns whose weights are not the interior ones: reflect geometry, the same for both losses
   int jsp[2] = {-1, -1};
@@ -463,7 +464,7 @@ __device__ __forceinline__ void ps_xfix_dual(int H, float g1b, float g4b, float 
       const float dc = live * (fmaf(wc[i][0], cf, wc[i][1] * cb) - wc[i][2]);  // 0 for rows outside the image
       const float db = live * (fmaf(wb[i][0], bf, wb[i][1] * bb) - wb[i][2] * gx);
       const int sn = so + (i - 2) * PS_PITCH + (j - 2);
-      const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+      const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PLANE + sn], d2 = i2 - s_img[2 * PLANE + sn];
       const float e = fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0));
       const float dp = pz - s_p[sn];
       ac = fmaf(dc * ex2_approx(e), dp, ac);
@@ -476,7 +477,7 @@ __device__ __forceinline__ void ps_xfix_dual(int H, float g1b, float g4b, float 
 __device__ __forceinline__ unsigned ps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // Rows [r0, r1) of the tile, element by element, raw values (0 outside the image): the layout a TMA load leaves.
-template <int C>
+template <int C, int PLANE = PS_PLANE>
 __device__ __noinline__ void ps_rows_load_slow(const PsParams& Q, const PsBlk& K, float* s_img, float* s_val, int r0,
                                                int r1, int lane) {
   const int H = Q.p.H, W = Q.p.W;
@@ -489,9 +490,9 @@ __device__ __noinline__ void ps_rows_load_slow(const PsParams& Q, const PsBlk& K
     const bool in = y >= 0 && y < H && x >= 0 && x < W;
     const size_t o = in ? (size_t)y * W + x : 0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) s_img[c * PS_PLANE + i] = in ? __ldg(img + c * plane + o) : 0.f;
+    for (int c = 0; c < 3; ++c) s_img[c * PLANE + i] = in ? __ldg(img + c * plane + o) : 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) s_val[c * PS_PLANE + i] = in ? __ldg(val + c * plane + o) : 0.f;
+    for (int c = 0; c < C; ++c) s_val[c * PLANE + i] = in ? __ldg(val + c * plane + o) : 0.f;
   }
 }
 
@@ -505,7 +506,7 @@ __device__ __noinline__ void ps_rows_load_slow(const PsParams& Q, const PsBlk& K
 #endif
 constexpr int PS_CONV_U = WSDL_PS_CONV_U;
 
-template <int C, int CS, bool SOFTMAX>
+template <int C, int CS, bool SOFTMAX, int PLANE = PS_PLANE>
 __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk& K, float* s_img, float* s_val, int r0,
                                                   int r1, int lane) {
   const int H = Q.p.H, W = Q.p.W;
@@ -518,9 +519,9 @@ __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk
     for (int k = 0; k < PS_CONV_U; ++k) {
       const int so = min(base + 32 * k, i1 - 1) * 4;  // PS_PITCH == 4 * PS_Q; a lane past the end re-reads the last group
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[k][c] = *reinterpret_cast<const float4*>(s_img + c * PS_PLANE + so);
+      for (int c = 0; c < 3; ++c) v[k][c] = *reinterpret_cast<const float4*>(s_img + c * PLANE + so);
 #pragma unroll
-      for (int c = 0; c < C; ++c) u[k][c] = *reinterpret_cast<const float4*>(s_val + c * PS_PLANE + so);
+      for (int c = 0; c < C; ++c) u[k][c] = *reinterpret_cast<const float4*>(s_val + c * PLANE + so);
     }
     __syncwarp();  // every lane holds its groups before anyone overwrites one (the clamped re-reads)
 #pragma unroll
@@ -562,11 +563,11 @@ __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk
       if (base + 32 * k < i1) {
         const int so = (base + 32 * k) * 4;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PS_PLANE + so) = v[k][c];
+        for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(s_img + c * PLANE + so) = v[k][c];
         if (CS != C || SOFTMAX) {
 #pragma unroll
           for (int c = 0; c < CS; ++c)
-            *reinterpret_cast<float4*>(s_val + c * PS_PLANE + so) = make_float4(w[c][0], w[c][1], w[c][2], w[c][3]);
+            *reinterpret_cast<float4*>(s_val + c * PLANE + so) = make_float4(w[c][0], w[c][1], w[c][2], w[c][3]);
         }
       }
     }
@@ -704,10 +705,11 @@ __device__ __forceinline__ void ps_pair2(float2 (&ga)[2], float2 (&gb)[2], const
 
 // All 12 forward pairs of the columns of row t.  X, Y, Z: even-pair accumulators [pair][cut, boundary] of rows t, t+1,
 // t+2.  On return X also holds the odd-aligned contributions of this step (columns 1..6).
+template <int PLANE = PS_PLANE>
 __device__ __forceinline__ void ps_step_dual2(float2 (&X)[4][2], float2 (&Y)[4][2], float2 (&Z)[4][2], float (&pc)[4],
                                               const float* s_img, const float* s_p, int off, const PsKsDual& ks, float ratio) {
   PsWinP<1> c;
-  ps_loadp<1>(c, s_img, s_p, off);
+  ps_loadp<1, PLANE>(c, s_img, s_p, off);
   pc[0] = c.e[3][1].x, pc[1] = c.e[3][1].y, pc[2] = c.e[3][2].x, pc[3] = c.e[3][2].y;
   float2 co[3][4];  // odd pairs of row t: [k][plane] = columns (2k+1, 2k+2)
 #pragma unroll
@@ -729,7 +731,7 @@ __device__ __forceinline__ void ps_step_dual2(float2 (&X)[4][2], float2 (&Y)[4][
     const float kc = r == 1 ? ks.cb : ks.cc;
     const float k0 = r == 1 ? ks.b0 : ks.c0, k1 = r == 1 ? ks.b1 : ks.c1, k4 = r == 1 ? ks.b4 : ks.c4;
     PsWinP<1> n;
-    ps_loadp<1>(n, s_img, s_p, off + r * PS_PITCH);
+    ps_loadp<1, PLANE>(n, s_img, s_p, off + r * PS_PITCH);
     const float2 n0[4] = PS_PL(n, 0), n1[4] = PS_PL(n, 1), n2[4] = PS_PL(n, 2), n3[4] = PS_PL(n, 3);
     ps_pair2(X[1], Yr[0], ce1, n0, kc, k4, ratio);     // dx = -2
     ps_pair2(X[2], Yr[1], ce2, n1, kc, k4, ratio);

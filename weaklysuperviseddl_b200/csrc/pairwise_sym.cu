@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
 
 // 4 finished pixels of centre row t: G[.][0] cut, G[.][1] boundary, one probability p0 each
 __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, float scale_b, int t, int strip, int okmask,
-                                             const float (&G)[4][2], const float (&pc)[4], float* s_gband, float& lsum_c,
+                                             const float (&G)[4][2], const float (&pc)[4], float* gband_row, float& lsum_c,
                                              float& lsum_b) {
   const int H = Q.p.H, W = Q.p.W;
   const int y = K.ys - 2 + t;
@@ -448,7 +448,7 @@ __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int slot1 = (okmask >> (4 + 4 * j)) & 15;
-      if (slot1) *reinterpret_cast<float2*>(s_gband + t * PS_PITCH + (slot1 - 1) * 2) = make_float2(G[j][0], G[j][1]);
+      if (slot1) *reinterpret_cast<float2*>(gband_row + (slot1 - 1) * 2) = make_float2(G[j][0], G[j][1]);
     }
   }
   float out[4];
@@ -481,20 +481,24 @@ __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, 
   }
 }
 
-constexpr size_t PS_DUAL_SMEM_FLOATS = (size_t)5 * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * 2 * 64 + 2 * 6 * 10 + 6 * 2 * 8 + 11 * 5 * 8;
+// Geometry of the dual kernel: segments of up to 6 rows (48 centre rows, 46 owned).  A block's fixed costs -- tile wait,
+// prologue, segment heads, loss ticket -- are paid once per CTA, and 224 rows split into 5 blocks instead of 6.  The tile
+// grows to 68.5 KB; three CTAs still share an SM because the segment heads and the band-column G no longer have a region
+// of their own: they live in shared memory that is dead by the time they are written (below).
+constexpr int DU_SMAX = 6;
+constexpr int DU_ROWS = PS_SEGS * DU_SMAX + 2;
+constexpr int DU_CAP = PS_SEGS * DU_SMAX - 2;
+constexpr int DU_PLANE = (DU_ROWS * PS_PITCH + 31) / 32 * 32;
+constexpr size_t PS_DUAL_SMEM_FLOATS = (size_t)5 * DU_PLANE + 2 * 6 * 10 + 6 * 2 * 8 + 11 * 5 * 8;
 
 __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     pairwise_dual_kernel(const __grid_constant__ PsParams Q, const __grid_constant__ PsDual D,
                          const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_val) {
   constexpr int C = 2;
   extern __shared__ __align__(128) float ps_smem[];
-  float* s_img = ps_smem;                                // [3][PS_ROWS][PS_PITCH]: raw, then scaled for sigma_cut
-  float* s_p = s_img + 3 * PS_PLANE;                     // [2][PS_ROWS][PS_PITCH]: logits, then p0 in plane 0
-  float* s_head = s_p + C * PS_PLANE;                    // [7][2][2][64]: G (cut, boundary) of the segment heads
-  // G of the band-column pixels, 12 floats at the start of each tile row of the SECOND logit plane: that plane is dead
-  // once a row is converted (p0 lives in plane 0), and a row's entries are written by the warp that converted it
-  float* s_gband = s_p + PS_PLANE;                       // [row t][6 slots][cut, boundary]
-  float* s_wx = s_head + (PS_SEGS - 1) * 2 * 2 * 64;     // [2][6][2][5]: column weights, cut then boundary
+  float* s_img = ps_smem;                                // [3][DU_ROWS][PS_PITCH]: raw, then scaled for sigma_cut
+  float* s_p = s_img + 3 * DU_PLANE;                     // [2][DU_ROWS][PS_PITCH]: logits, then p0 in plane 0
+  float* s_wx = s_p + C * DU_PLANE;                      // [2][6][2][5]: column weights, cut then boundary
   float* s_fx = s_wx + 2 * 6 * 10;                       // [6][2][8]: per band slot, its two special partner columns
   float* s_wy = s_fx + 6 * 2 * 8;                        // [11][5][8]: row weights of the 10 row-band rows + the interior
   __shared__ __align__(8) unsigned long long s_bar;
@@ -515,6 +519,16 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   const int xe = min(K.x0 + PS_TW, W);
   K.xband = (K.x0 <= 2) || (xe - 1 >= W - 3);
   const int rows = K.nc + 2;
+  // Per warp, 512 + 24 S floats: G (cut, boundary) of the first two rows of its two segments [h][i][c][64], then G of
+  // the band-column pixels of its 2 S centre rows [row][6 slots][cut, boundary].  With S >= 5 they fit into the warp's
+  // OWN rows of the second logit plane -- dead once the warp has converted them (p0 lives in plane 0), which it has
+  // before it marches, so there is no block-wide barrier between conversion and march; shorter blocks leave the rows
+  // past 8 S + 2 of every plane unused, and warp w takes those of plane w.
+  const auto wreg = [&](int w) -> float* {
+    return S >= 5 ? s_p + DU_PLANE + 2 * w * S * PS_PITCH : s_img + w * DU_PLANE + (PS_SEGS * S + 2) * PS_PITCH;
+  };
+  float* const my_head = wreg(warp) + (lane >> 4) * 256;  // + (i * 2 + c) * 64 + 4 * strip
+  float* const my_gband = wreg(warp) + 512 - 2 * warp * S * 12;  // + t * 12 + slot * 2 for a centre row t of this warp
   PS_TR(0);
 #ifdef WSDL_PS_TRACE
   if (lane == 0) {
@@ -540,7 +554,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       const int pl = c < 3 ? K.b * 3 + c : K.b * C + (c - 3);
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-              ps_smem_u32(s_img + c * PS_PLANE)),
+              ps_smem_u32(s_img + c * DU_PLANE)),
           "l"(tm), "r"(K.x0 - 4), "r"(K.ys - 2), "r"(pl), "r"(bar)
           : "memory");
     }
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
           "r"(20000u)
           : "memory");
     } else {
-      ps_rows_load_slow<C>(Q, K, s_img, s_p, r0, r1, lane);
+      ps_rows_load_slow<C, DU_PLANE>(Q, K, s_img, s_p, r0, r1, lane);
       __syncwarp();
     }
     PS_TR(1);
@@ -638,12 +652,12 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       }
     }
 #if !(WSDL_X_SKIP & 1)
-    ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, r0, re, lane);
+    ps_rows_transform<C, 1, true, DU_PLANE>(Q, K, s_img, s_p, r0, re, lane);
 #endif
     if (warp > 0) asm volatile("bar.arrive %0, 64;" ::"r"(warp) : "memory");
     PS_TR(2);
 #if !(WSDL_X_SKIP & 1)
-    ps_rows_transform<C, 1, true>(Q, K, s_img, s_p, re, r1, lane);
+    ps_rows_transform<C, 1, true, DU_PLANE>(Q, K, s_img, s_p, re, r1, lane);
 #endif
     __syncwarp();
     PS_TR(3);
@@ -657,16 +671,11 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 #pragma unroll
   for (int q = 0; q < 4; ++q) oy[q][0] = oy[q][1] = oz[q][0] = oz[q][1] = 0.f;
   if (!(WSDL_X_SKIP & 4) && warp * 2 * S < K.nc) {
-#if WSDL_PS_PACKED
     float2 A[4][2], Bq[4][2], Cq[4][2];
 #pragma unroll
     for (int w = 0; w < 4; ++w)
 #pragma unroll
       for (int c = 0; c < 2; ++c) A[w][c] = Bq[w][c] = Cq[w][c] = make_float2(0.f, 0.f);
-#else
-    float A[8][2], Bq[8][2], Cq[8][2];
-    ps_zero<2>(A), ps_zero<2>(Bq), ps_zero<2>(Cq);
-#endif
     const float ksu = D.ksu_b, ratio = D.ratio;
     // one copy of the step in the instruction stream: unrolling by 2 / 3 (which would let the accumulator rows rotate
     // by renaming instead of moves) costs 29 -> 36 / 41 us per step -- the ~13 KB body already strains the
@@ -688,27 +697,20 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
         ks.a1 = ksu + l0b - ra, ks.a4 = 4.f * ksu + l0b - ra;
         ks.b0 = ksu + l1 - rb, ks.b1 = 2.f * ksu + l1 - rb, ks.b4 = 5.f * ksu + l1 - rb;
         ks.c0 = 4.f * ksu + l2 - rc, ks.c1 = 5.f * ksu + l2 - rc, ks.c4 = 8.f * ksu + l2 - rc;
-#if WSDL_PS_PACKED
-        ps_step_dual2(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
+        ps_step_dual2<DU_PLANE>(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
       }
       ps_exchangep<2>(A, own, strip);
-#else
-        ps_step_dual(A, Bq, Cq, pc, s_img, s_p, t * PS_PITCH + 4 * strip, ks, ratio);
-      }
-      ps_exchange<2>(A, own, strip);
-#endif
       if (act) {
         if (s >= 2) {
-          ps_emit_dual(Q, K, scale_b, t, strip, okmask, own, pc, s_gband, lsum_c, lsum_b);
+          ps_emit_dual(Q, K, scale_b, t, strip, okmask, own, pc, my_gband + t * 12, lsum_c, lsum_b);
         } else if (seg > 0) {
 #pragma unroll
           for (int c = 0; c < 2; ++c)
-            *reinterpret_cast<float4*>(s_head + (((seg - 1) * 2 + s) * 2 + c) * 64 + 4 * strip) =
+            *reinterpret_cast<float4*>(my_head + (s * 2 + c) * 64 + 4 * strip) =
                 make_float4(own[0][c], own[1][c], own[2][c], own[3][c]);
         }
       }
       if (s < 4) PS_TR(5 + s);
-#if WSDL_PS_PACKED
 #pragma unroll
       for (int w = 0; w < 4; ++w)
 #pragma unroll
@@ -716,30 +718,22 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     }
     ps_exchangep<2>(A, oy, strip);
     ps_exchangep<2>(Bq, oz, strip);
-#else
-#pragma unroll
-      for (int w = 0; w < 8; ++w)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) A[w][c] = Bq[w][c], Bq[w][c] = Cq[w][c], Cq[w][c] = 0.f;
-    }
-    ps_exchange<2>(A, oy, strip);
-    ps_exchange<2>(Bq, oz, strip);
-#endif
   }
   PS_TR(9);
   __syncthreads();  // every head row holds its own segment's part
   PS_TR(10);
   if (seg < PS_SEGS - 1) {
+    float* const next_head = wreg((seg + 1) >> 1) + ((seg + 1) & 1) * 256;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       if (t0 + S < K.nc) {
-        float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 0) * 2 + c) * 64 + 4 * strip);
+        float4* h = reinterpret_cast<float4*>(next_head + c * 64 + 4 * strip);
         float4 v = *h;
         v.x += oy[0][c], v.y += oy[1][c], v.z += oy[2][c], v.w += oy[3][c];
         *h = v;
       }
       if (t0 + S + 1 < K.nc) {
-        float4* h = reinterpret_cast<float4*>(s_head + ((seg * 2 + 1) * 2 + c) * 64 + 4 * strip);
+        float4* h = reinterpret_cast<float4*>(next_head + (2 + c) * 64 + 4 * strip);
         float4 v = *h;
         v.x += oz[0][c], v.y += oz[1][c], v.z += oz[2][c], v.w += oz[3][c];
         *h = v;
@@ -757,13 +751,13 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
         float G[4][2], pc[4];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const float4 h = *reinterpret_cast<const float4*>(s_head + (((seg - 1) * 2 + i) * 2 + c) * 64 + 4 * strip);
+          const float4 h = *reinterpret_cast<const float4*>(my_head + (i * 2 + c) * 64 + 4 * strip);
           G[0][c] = h.x, G[1][c] = h.y, G[2][c] = h.z, G[3][c] = h.w;
         }
         const float2 p01 = *reinterpret_cast<const float2*>(s_p + t * PS_PITCH + 4 * strip + 2);
         const float2 p23 = *reinterpret_cast<const float2*>(s_p + t * PS_PITCH + 4 * strip + 4);
         pc[0] = p01.x, pc[1] = p01.y, pc[2] = p23.x, pc[3] = p23.y;
-        ps_emit_dual(Q, K, scale_b, t, strip, okmask, G, pc, s_gband, lsum_c, lsum_b);
+        ps_emit_dual(Q, K, scale_b, t, strip, okmask, G, pc, my_gband + t * 12, lsum_c, lsum_b);
       }
     }
   }
@@ -786,7 +780,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
         // (true pair weight - weight the march applied) / 2 * k (p(a) - p(b)) over the five rows of the two special
         // partner columns, both losses from one set of loads and one squared distance; weights from the two tables
         const int so = (ty + 2) * PS_PITCH + (x - (K.x0 - 4));
-        const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
+        const float i0 = s_img[so], i1 = s_img[DU_PLANE + so], i2 = s_img[2 * DU_PLANE + so];
         p0 = s_p[so];
         const float* wy = s_wy + (y < 5 ? y : (y > H - 6 ? y - (H - 10) : 10)) * 40;
         ac = 0.f, ab = 0.f;
@@ -800,7 +794,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
             const float4 wa = *reinterpret_cast<const float4*>(wy + r * 8);
             const float2 wb2 = *reinterpret_cast<const float2*>(wy + r * 8 + 4);
             const int sn = sj + (r - 2) * PS_PITCH;  // rows outside the image: weights 0, the staged values are finite
-            const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+            const float d0 = i0 - s_img[sn], d1 = i1 - s_img[DU_PLANE + sn], d2 = i2 - s_img[2 * DU_PLANE + sn];
             const float e = fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0));
             const float dp = p0 - s_p[sn];
             const float dc = fmaf(wa.x, fc.y, fmaf(wa.y, fc.z, -fc.w * wa.z));
@@ -810,14 +804,15 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
           }
         }
       } else {
-        ps_xfix_dual(H, D.g1b, D.g4b, D.ratio, s_img, s_p, s_wx + slot * 10, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ac, ab, p0);
+        ps_xfix_dual<DU_PLANE>(H, D.g1b, D.g4b, D.ratio, s_img, s_p, s_wx + slot * 10, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ac, ab, p0);
       }
       const float p1 = 1.f - p0;
       lsum_c = fmaf(p0 - p1, ac, lsum_c);  // the losses are linear in G: the corrections' share
       lsum_b = fmaf(p0 - p1, ab, lsum_b);
       if (!(WSDL_X_SKIP & 16) && Q.p.grad_values) {
-        const float gc = ac + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 0];
-        const float gb = ab + s_gband[(ty + 2) * PS_PITCH + slot * 2 + 1];
+        const int tw = min((ty + 2) / (2 * S), PS_WARPS - 1);  // the warp that marched centre row ty + 2
+        const float2 g2 = *reinterpret_cast<const float2*>(wreg(tw) + 512 + (ty + 2 - 2 * tw * S) * 12 + slot * 2);
+        const float gc = ac + g2.x, gb = ab + g2.y;
         const float o = 2.f * p0 * p1 * fmaf(K.scale2, gc, scale_b * gb);
         float* go = Q.p.grad_values + (size_t)K.b * 2 * plane + (size_t)y * W + x;
         go[0] = o, go[plane] = -o;
@@ -880,10 +875,10 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 // Row blocks per column tile: at most PS_CAP rows each; among the next few candidates the count with the lowest
 // modelled time = (march steps per block + fixed cost of a block, in steps) x blocks an SM works through (a launch
 // below two blocks per SM is latency bound: more, shorter blocks keep winning there).
-static int ps_row_blocks(int B, int H, int W) {
+static int ps_row_blocks(int B, int H, int W, int cap = PS_CAP) {
   static const int forced = WSDL_TUNE_INT("WSDL_PS_NB", 0);
   const int n_x = (W + PS_TW - 1) / PS_TW;
-  const int nb_min = (H + PS_CAP - 1) / PS_CAP;
+  const int nb_min = (H + cap - 1) / cap;
   if (forced >= nb_min) return forced;
   int best = nb_min;
   double best_cost = 1e300;
@@ -899,9 +894,10 @@ static int ps_row_blocks(int B, int H, int W) {
   return best;
 }
 
-size_t ps_workspace_floats(int B, int H, int W) {
+size_t ps_workspace_floats(int B, int H, int W) {  // one loss partial per block, whichever kernel cuts the rows
   const int n_x = (W + PS_TW - 1) / PS_TW;
-  return (size_t)B * n_x * ps_row_blocks(B, H, W);
+  const int nb = ps_row_blocks(B, H, W), nb_dual = ps_row_blocks(B, H, W, DU_CAP);
+  return (size_t)B * n_x * (nb > nb_dual ? nb : nb_dual);
 }
 
 typedef CUresult (*PsEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -998,7 +994,7 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   PsParams Q;
   Q.p = P;
   Q.n_x = (P.W + PS_TW - 1) / PS_TW;
-  Q.nb = ps_row_blocks(P.B, P.H, P.W);
+  Q.nb = ps_row_blocks(P.B, P.H, P.W, DU_CAP);
   if (Q.nb > 65535 || Q.n_x > 65535 || P.B > 65535) return 1;
   const int n_max = (P.H + Q.nb - 1) / Q.nb;
   Q.S = (n_max + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n_max + 2 + PS_SEGS - 1) / PS_SEGS;
