@@ -8,7 +8,7 @@ python bench.py --workload layercam --steps 5 > gpurun_out/r2_bench_layercam_n1.
 CMD="python bench.py --steps 16 --warmup 8 --no-graph --no-cpu-baseline --no-also"
 $CMD > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches_bench.csv $CMD > gpurun_out/ncu_bench.log 2>&1
 python scripts/ncu_target.py > gpurun_out/plain_target.log 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"pairwise_dual|weak_loss|ccl_" -c 40 --csv --log-file gpurun_out/r2_launches_target.csv python scripts/ncu_target.py > gpurun_out/ncu_target.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"pairwise_dual|weak_loss" -s 3 -c 3 -f -o gpurun_out/r2_prof_pairwise python scripts/ncu_target.py > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"pairwise_dual|weak_loss" -s 5 -c 5 -f -o gpurun_out/r2_prof_pairwise python scripts/ncu_target.py > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"
 for f in gpurun_out/r2_bench_n1.json gpurun_out/r2_bench_trainstep_n1.json gpurun_out/r2_bench_layercam_n1.json; do python - "$f" <<'PY'
 import json,sys

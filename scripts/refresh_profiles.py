@@ -46,7 +46,7 @@ if os.path.exists(p):
     with open(os.path.join(pr, f"{tag}_d_launches_target.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,\n"
                 "#   smsp__issue_active --clock-control none: python scripts/ncu_target.py (32x2x224x224 pairwise launches with a 256 MB\n"
-                "#   L2 flush before each; keep_largest on 128 blobby 512x512 masks).  Cold and serialised: compare shares and counts.\n"
+                "#   L2 flush before each; keep_largest on 128 512x512 masks of two kinds).  Cold and serialised: compare shares and counts.\n"
                 "# id | kernel | grid | us | dram read MB | dram write MB | warp instructions (M) | issue active %\n")
         ccl = collections.defaultdict(list)
         for (i, k, g), m in d.items():
@@ -55,22 +55,22 @@ if os.path.exists(p):
                     f"{m['smsp__issue_active.avg.pct_of_peak_sustained_active']:5.1f}\n")
             if k.startswith("ccl_"):
                 ccl[k].append(m)
-        if ccl:
-            n = min(len(v) for v in ccl.values())
-            rd = sum(v[-1]["dram__bytes_read.sum"] for v in ccl.values()) / 1e6
-            wr = sum(v[-1]["dram__bytes_write.sum"] for v in ccl.values()) / 1e6
-            us = sum(v[-1]["gpu__time_duration.sum"] for v in ccl.values()) / 1e3
-            f.write(f"# keep_largest, one call (128 x 512^2): {us:.0f} us under ncu, DRAM {rd:.0f} MB read + {wr:.0f} MB written = "
-                    f"{rd + wr:.0f} MB for 67 MB algorithmic (mask in + mask out); round 1: 473 MB\n")
+        if ccl:  # scripts/ncu_target.py alternates the two mask kinds: noise-outline masks, then CAM-like masks
+            for which, name in ((-2, "box-filtered-noise masks (ragged outlines)"), (-1, "CAM-like masks (bilinear 16x16 -> 512x512)")):
+                rd = sum(v[which]["dram__bytes_read.sum"] for v in ccl.values()) / 1e6
+                wr = sum(v[which]["dram__bytes_write.sum"] for v in ccl.values()) / 1e6
+                us = sum(v[which]["gpu__time_duration.sum"] for v in ccl.values()) / 1e3
+                f.write(f"# keep_largest, one call (128 x 512^2), {name}: {us:.0f} us under ncu, DRAM {rd:.0f} MB read + {wr:.0f} MB written = "
+                        f"{rd + wr:.0f} MB for 67 MB algorithmic (mask in + mask out); round 1: 473 MB, round 2 first version: 122 MB\n")
 
 # ---- one --set full capture of the pairwise kernels
 rep = os.path.join(go, "r2_prof_pairwise.ncu-rep")
 if os.path.exists(rep):
     with open(os.path.join(pr, f"{tag}_c_ncu_full_pairwise.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:'pairwise_dual|weak_loss' -s 3 -c N: python scripts/ncu_target.py\n"
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:'pairwise_dual|weak_loss' -s 5 -c 5: python scripts/ncu_target.py\n"
                 "# (32x2x224x224, 256 MB L2 flush before every launch)\n")
         f.write(run("scripts/ncu_summary.py", rep))
-        for i in range(4):
+        for i in range(5):
             s = run("scripts/ncu_sass.py", rep, str(i))
             if s.strip():
                 f.write(f"\n# SASS opcode mix + stall samples of launch {i}\n" + s)
