@@ -217,6 +217,19 @@ def test_keep_largest_matches_oracle(WF):
         spiral[64 - k, k:65 - k] = 1
         spiral[k + 2:65 - k, k] = 1
     cases.append(spiral)
+    cb = np.zeros((70, 100), np.uint8)                  # 256 components per 32x32 tile, 16 runs in every other row
+    cb[::2, ::2] = 1
+    cb[10, 10:15] = 1                                   # ... and one of five pixels that wins
+    cases.append(cb)
+    stripes = np.zeros((64, 96), np.uint8)              # 16 runs per row, every run spans the tile seams
+    stripes[:, ::2] = 1
+    stripes[31:33, 40:47] = 1
+    cases.append(stripes)
+    anti = np.zeros((96, 96), np.uint8)                 # a diagonal that crosses tile corners up-right
+    anti[np.arange(96), 95 - np.arange(96)] = 1
+    cases.append(anti)
+    yy, xx = np.mgrid[0:200, 0:208]                     # CAM-like blobs over several tiles (smooth outlines)
+    cases.append((((yy - 60) ** 2 + (xx - 70) ** 2 < 50 ** 2) | ((yy - 150) ** 2 / 4 + (xx - 150) ** 2 < 30 ** 2)).astype(np.uint8))
     for m in cases:
         out, area = WF.keep_largest(torch.from_numpy(m).cuda(), return_area=True)
         ref = O.keep_largest(m)

@@ -284,7 +284,10 @@ DUAL_CASES = [(2, 64, 64), (1, 224, 224), (2, 45, 70), (1, 6, 6), (3, 39, 44), (
               (2, 300, 520), (5, 7, 9),
               # row blocks of the 5-row-segment geometry (38 owned rows): exactly one block and one column tile, a 2-row
               # last block, two full blocks + 1 row
-              (1, 38, 60), (2, 40, 64), (1, 77, 60)]
+              (1, 38, 60), (2, 40, 64), (1, 77, 60),
+              # the fused kernel's own geometry (segments of up to 6 rows, 46 owned rows per block): exactly one block, a
+              # 2-row last block, two full blocks + 1 row; 3-row segments (heads in the unused tail of the planes)
+              (1, 46, 60), (2, 48, 64), (1, 93, 60), (2, 22, 30)]
 
 
 @pytest.mark.parametrize("case", range(len(DUAL_CASES)))
