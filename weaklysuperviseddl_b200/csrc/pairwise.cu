@@ -737,7 +737,7 @@ extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* imag
   if (workspace_bytes < wsdl_pairwise_dual_workspace_bytes(B, H, W)) return WSDL_E_WORKSPACE;
   cudaStream_t s = (cudaStream_t)stream;
   // Two regularisers only, f32: the one-tile-per-CTA kernel (pairwise_sym.cu) is the faster one when launches overlap
-  // (25 vs 30 us per launch on configs[1]; 41 us either way for a lone launch).  The tile-streaming kernel
+  // (22 vs 30 us per launch on configs[1]; 37 vs 41 us for a lone launch).  The tile-streaming kernel
   // (pairwise_stream.cu) is the one that also takes labels, bf16 logits and u8 images: wsdl_weak_loss_fwd_bwd.
   static const int no_stream = !WSDL_TUNE_INT("WSDL_PAIRWISE_DUAL_STREAM", 0);
   if (!no_stream) {
