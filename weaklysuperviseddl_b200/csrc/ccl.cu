@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
   __shared__ int s_n[CCL_TPC];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x * CCL_TPC + warp;
+  pdl_wait();
+  pdl_launch_dependents();
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) T.best[b] = 0ull;
   if (tx >= tiles_x) return;  // warps are independent: only __syncwarp below
   const int y0 = ty * CT, x0 = tx * CT, y = y0 + lane;
@@ -126,6 +128,25 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
       const int nx = min(CT, W - x0);
       for (int j = 0; j < nx; ++j) m |= (p[j] != 0 ? 1u : 0u) << j;
     }
+  }
+  // Most tiles of a CAM mask lie entirely outside or entirely inside a blob: their tables are known without any labelling.
+  if (!__any_sync(0xffffffffu, m != 0u) || __all_sync(0xffffffffu, m == 0xffffffffu)) {
+    const bool full = m != 0u;
+    unsigned short* rec = T.border + tile * 128;
+    const unsigned short v = full ? (unsigned short)0 : CCL_BG;
+    rec[lane] = v, rec[32 + lane] = v, rec[64 + lane] = v, rec[96 + lane] = v;
+    T.bits[tile * CT + lane] = m;
+    if (full) T.runcomp[tile * CCL_RPR * CT + lane] = 0;
+    if (lane == 0) {
+      T.n_roots[tile] = full ? (1 | (1 << 16)) : 0;
+      if (full) {
+        const size_t node = tile * CCL_MAXR;
+        T.first_pix[node] = T.min_pix[node] = y0 * W + x0;
+        T.area[node] = CT * CT;
+        T.parent[node] = (int)node;
+      }
+    }
+    return;
   }
   const unsigned up_raw = __shfl_up_sync(0xffffffffu, m, 1);
   const unsigned up = lane ? up_raw : 0u;  // the row above inside the tile
@@ -236,10 +257,13 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
 __global__ void __launch_bounds__(CCL_THREADS) ccl_seams(CclTables T, int tiles_x, int tiles_y) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x * CCL_TPC + warp;
+  pdl_wait();
+  pdl_launch_dependents();
   if (tx >= tiles_x) return;
   const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx;
   int* P = T.parent;
   const unsigned m = T.bits[tile * CT + lane];
+  if (!__any_sync(0xffffffffu, m != 0u)) return;  // an empty tile has nothing to join
   if (tx > 0) {
     const size_t tl = tile - 1;
     const unsigned col = __ballot_sync(0xffffffffu, T.bits[tl * CT + lane] >> 31);  // the left tile's right column, bit = row
@@ -287,6 +311,8 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_seams(CclTables T, int tiles_
 // Local components hand their area and first pixel to their global root; eight threads per tile (a tile of a blobby mask
 // holds a handful of components).
 __global__ void ccl_gather(CclTables T, int n_tiles) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int sub = threadIdx.x & 7;
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n_tiles; t += (gridDim.x * blockDim.x) >> 3) {
     const int n = T.n_roots[t] & 0xffff;
@@ -303,6 +329,8 @@ __global__ void ccl_gather(CclTables T, int n_tiles) {
 }
 
 __global__ void ccl_argmax(CclTables T, int tiles_per_image, int n_tiles) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int sub = threadIdx.x & 7;
   const int stride = (gridDim.x * blockDim.x) >> 3;
   // warp-uniform trip count (the shuffles below need the whole warp): four tiles per warp and iteration
@@ -339,6 +367,8 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_select(uint8_t* __restrict__ 
   __shared__ uint8_t s_flag[CCL_TPC][CCL_MAXR];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x * CCL_TPC + warp;
+  pdl_wait();
+  pdl_launch_dependents();
   const unsigned long long key = T.best[b];
   const int win = key ? (int)(0xffffffffu - (unsigned)(key & 0xffffffffull)) : -2;  // first pixel of the winning component
   if (best_area && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) best_area[b] = (unsigned)(key >> 32);
@@ -423,15 +453,21 @@ extern "C" int wsdl_keep_largest(const uint8_t* mask, int B, int H, int W, uint8
   const dim3 strips((tx + CCL_TPC - 1) / CCL_TPC, ty, B);
   // 128-bit row accesses: rows of a tile start on 16-byte boundaries
   const int vec_in = (W % 16 == 0) && ((uintptr_t)mask % 16 == 0), vec_out = (W % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  ccl_tile<<<strips, CCL_THREADS, 0, s>>>(mask, T, H, W, tx, ty, vec_in);
-  if (tx > 1 || ty > 1) ccl_seams<<<strips, CCL_THREADS, 0, s>>>(T, tx, ty);
+  // five short dependent kernels: each is launched so that its CTAs are scheduled under the tail of the one before
+  cudaError_t e = launch_pdl(ccl_tile, strips, dim3(CCL_THREADS), 0, s, mask, T, H, W, tx, ty, vec_in);
+  if (e != cudaSuccess) return (int)e;
+  if (tx > 1 || ty > 1) e = launch_pdl(ccl_seams, strips, dim3(CCL_THREADS), 0, s, T, tx, ty);
+  if (e != cudaSuccess) return (int)e;
   {
     long long gb = (n_tiles * 8 + 255) / 256;
     if (gb > WSDL_NUM_SMS * 16) gb = WSDL_NUM_SMS * 16;
-    ccl_gather<<<(int)gb, 256, 0, s>>>(T, (int)n_tiles);
-    ccl_argmax<<<(int)gb, 256, 0, s>>>(T, tx * ty, (int)n_tiles);
+    e = launch_pdl(ccl_gather, dim3((unsigned)gb), dim3(256), 0, s, T, (int)n_tiles);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_pdl(ccl_argmax, dim3((unsigned)gb), dim3(256), 0, s, T, tx * ty, (int)n_tiles);
+    if (e != cudaSuccess) return (int)e;
   }
-  ccl_select<<<strips, CCL_THREADS, 0, s>>>(out, T, best_area, H, W, tx, ty, vec_out);
+  e = launch_pdl(ccl_select, strips, dim3(CCL_THREADS), 0, s, out, T, best_area, H, W, tx, ty, vec_out);
+  if (e != cudaSuccess) return (int)e;
   WSDL_LAUNCH_CHECK();
   return 0;
 }

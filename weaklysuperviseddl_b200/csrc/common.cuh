@@ -26,6 +26,24 @@
 
 namespace wsdl {
 
+// Programmatic dependent launch.  A kernel launched through wsdl::launch_pdl may start while the previous kernel of the
+// stream is still draining: it must not touch global memory before pdl_wait() (which returns once that kernel's writes are
+// visible), and pdl_launch_dependents() tells the scheduler that ITS successor may be scheduled as soon as every CTA got
+// there.  With a predecessor that never signals (any other kernel) the launch simply behaves like a normal one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // 128-bit streaming load: read-only path, do not allocate in L1 (every input byte of the
 // channel-sum is touched exactly once).
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {

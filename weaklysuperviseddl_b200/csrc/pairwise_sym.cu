@@ -113,11 +113,12 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     // CTA of an SM holds back k quarter-wave transfer times: the quarters complete in turn, the early ones march
     // under the later ones' traffic, and the SM's CTAs stay out of phase from then on.
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    if (cta >= WSDL_NUM_SMS && cta < (unsigned)WSDL_NUM_SMS * PsCfg<C, SOFTMAX>::CTAS && Q.stagger_ns > 0)
-      __nanosleep((cta / WSDL_NUM_SMS) * Q.stagger_ns);
     const unsigned bar = ps_smem_u32(&s_bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pdl_wait();  // programmatic dependent launch: nothing before this line touches global memory
+    if (cta >= WSDL_NUM_SMS && cta < (unsigned)WSDL_NUM_SMS * PsCfg<C, SOFTMAX>::CTAS && Q.stagger_ns > 0)
+      __nanosleep((cta / WSDL_NUM_SMS) * Q.stagger_ns);
     const unsigned bytes = (unsigned)((3 + C) * (PS_SEGS * S + 2) * PS_PITCH * sizeof(float));
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 #pragma unroll
@@ -131,7 +132,6 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
           : "memory");
     }
   }
-  K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
   int okmask = 0;  // which of this thread's 4 columns are owned pixels of the image
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     s_wx[e] = w;
   }
   __syncthreads();  // s_bar is initialised
+  pdl_wait();  // (see pairwise_dual_kernel: the prologue above runs under the previous kernel's tail)
+  pdl_launch_dependents();
+  K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
 
   // ---- each warp: its own rows (the centre rows of its two segments; warp 3 also the 2 look-ahead rows) ----
   {
@@ -437,20 +440,6 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   }
 }
 
-#ifndef WSDL_PS_PDL
-#define WSDL_PS_PDL 1  // programmatic dependent launch of the dual kernel (prologue under the predecessor's tail)
-#endif
-__device__ __forceinline__ void ps_grid_dependency_wait() {
-#if WSDL_PS_PDL
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
-__device__ __forceinline__ void ps_launch_dependents() {
-#if WSDL_PS_PDL
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-
 // 4 finished pixels of centre row t: G[.][0] cut, G[.][1] boundary, one probability p0 each
 __device__ __forceinline__ void ps_emit_dual(const PsParams& Q, const PsBlk& K, float scale_b, int t, int strip, int okmask,
                                              const float (&G)[4][2], const float (&pc)[4], float* gband_row, float& lsum_c,
@@ -558,7 +547,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     const unsigned bar = ps_smem_u32(&s_bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    ps_grid_dependency_wait();  // programmatic dependent launch: nothing before this line touches global memory
+    pdl_wait();  // programmatic dependent launch: nothing before this line touches global memory
     if (cta >= WSDL_NUM_SMS && cta < (unsigned)WSDL_NUM_SMS * WSDL_PS_CTAS && Q.stagger_ns > 0)
       __nanosleep((cta / WSDL_NUM_SMS) * Q.stagger_ns);
     const unsigned bytes = (unsigned)(5 * (PS_SEGS * S + 2) * PS_PITCH * sizeof(float));
@@ -596,8 +585,8 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   // Everything above is index arithmetic and shared-memory tables: launched with programmatic stream serialization, a
   // CTA runs it while the previous kernel of the stream is still draining, and waits here (tid 0: before its tile load)
   // for that kernel's memory to be visible.  Dependents of THIS launch may be scheduled as soon as every CTA got here.
-  ps_grid_dependency_wait();
-  ps_launch_dependents();
+  pdl_wait();
+  pdl_launch_dependents();
   K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out) : 1.f);
   const float scale_b = (float)(4.0 * D.kappa_bnd) * (D.grad_out_bnd ? __ldg(D.grad_out_bnd + K.b) : 1.f);
   if (K.xband && tid < 12) {
@@ -968,7 +957,11 @@ static int ps_launch_t(PsParams& Q, const CUtensorMap& tm_img, const CUtensorMap
   }
   static const size_t pad = (size_t)WSDL_TUNE_INT("WSDL_PS_SMEM_PAD_KB", 0) * 1024;
   if (pad) cudaFuncSetAttribute(pairwise_sym_kernel<C, SOFTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + pad));
-  pairwise_sym_kernel<C, SOFTMAX><<<dim3(Q.nb, Q.n_x, Q.p.B), PS_THREADS, smem + pad, s>>>(Q, tm_img, tm_val);
+  {
+    const cudaError_t e = launch_pdl(pairwise_sym_kernel<C, SOFTMAX>, dim3(Q.nb, Q.n_x, Q.p.B), dim3(PS_THREADS), smem + pad, s, Q,
+                                     tm_img, tm_val);
+    if (e != cudaSuccess) return (int)e;
+  }
   WSDL_LAUNCH_CHECK();
   return 0;
 }
@@ -1058,21 +1051,10 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
     if (e != cudaSuccess) return (int)e;
     attr_done[dev_id] = true;
   }
-#if WSDL_PS_PDL
   {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(Q.nb, Q.n_x, P.B), cfg.blockDim = dim3(PS_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, pairwise_dual_kernel, Q, D, tm_img, tm_val);
+    const cudaError_t e = launch_pdl(pairwise_dual_kernel, dim3(Q.nb, Q.n_x, P.B), dim3(PS_THREADS), smem, s, Q, D, tm_img, tm_val);
     if (e != cudaSuccess) return (int)e;
   }
-#else
-  pairwise_dual_kernel<<<dim3(Q.nb, Q.n_x, P.B), PS_THREADS, smem, s>>>(Q, D, tm_img, tm_val);
-#endif
   WSDL_LAUNCH_CHECK();
   return 0;
 }

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(RF_THREADS) refine_step_kernel(const __grid_co
   const int b = blockIdx.y;
   const size_t plane = (size_t)P.n_pix, base = (size_t)b * 2 * plane;
   const bool update = P.g_cut != nullptr;
+  pdl_wait();  // launched with programmatic stream serialization: scheduled under the tail of the cut launch before it
+  pdl_launch_dependents();
   float lamp = 0.f;
   if (update) {  // lam * (kl / (cut + 1e-6)) in double, handed to the float tensor as a float (python scalar semantics)
     const double kl = (double)__ldg(P.kl_in + b), cut = (double)__ldg(P.loss_cut + b);
@@ -238,7 +240,10 @@ extern "C" int wsdl_refine_step(float* X, const float* S, const float* g_cut, co
     cudaError_t e = cudaMemsetAsync(P.ticket, 0, tickets, s);
     if (e != cudaSuccess) return (int)e;
   }
-  refine_step_kernel<<<dim3(P.blocks_per_image, B), RF_THREADS, 0, s>>>(P);
+  {
+    const cudaError_t e = launch_pdl(refine_step_kernel, dim3(P.blocks_per_image, B), dim3(RF_THREADS), 0, s, P);
+    if (e != cudaSuccess) return (int)e;
+  }
   WSDL_LAUNCH_CHECK();
   return 0;
 }
