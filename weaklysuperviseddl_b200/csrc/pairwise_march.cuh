@@ -631,46 +631,6 @@ struct PsKsDual {  // per pair class: cut exponent offset, and boundary offset m
   float a1, a4, b0, b1, b4, c0, c1, c4;
 };
 
-__device__ __forceinline__ void ps_pair_dual(float (&ga)[2], float (&gb)[2], const PsWin<1>& a, int ia, const PsWin<1>& b,
-                                             int ib, float kc_off, float kb_off, float ratio) {
-  const float d0 = a.i[0][ia] - b.i[0][ib], d1 = a.i[1][ia] - b.i[1][ib], d2 = a.i[2][ia] - b.i[2][ib];
-  const float ec = fmaf(-d2, d2, fmaf(-d1, d1, fmaf(-d0, d0, kc_off)));
-  const float kc = ex2_approx(ec), kb = ex2_approx(fmaf(ec, ratio, kb_off));
-  const float dp = a.p[0][ia] - b.p[0][ib];
-  ga[0] = fmaf(kc, dp, ga[0]);
-  gb[0] = fmaf(-kc, dp, gb[0]);
-  ga[1] = fmaf(kb, dp, ga[1]);
-  gb[1] = fmaf(-kb, dp, gb[1]);
-}
-
-__device__ __forceinline__ void ps_step_dual(float (&X)[8][2], float (&Y)[8][2], float (&Z)[8][2], float (&pc)[4],
-                                             const float* s_img, const float* s_p, int off, const PsKsDual& ks, float ratio) {
-  PsWin<1> c;
-  ps_load<1>(c, s_img, s_p, off);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) pc[j] = c.p[0][2 + j];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    ps_pair_dual(X[2 + j], X[3 + j], c, 2 + j, c, 3 + j, ks.ca, ks.a1, ratio);
-    ps_pair_dual(X[2 + j], X[4 + j], c, 2 + j, c, 4 + j, ks.ca, ks.a4, ratio);
-  }
-  PsWin<1> n;
-  ps_load<1>(n, s_img, s_p, off + PS_PITCH);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int dx = -2; dx <= 2; ++dx)
-      ps_pair_dual(X[2 + j], Y[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks.cb, dx == 0 ? ks.b0 : (dx * dx == 1 ? ks.b1 : ks.b4),
-                   ratio);
-  ps_load<1>(n, s_img, s_p, off + 2 * PS_PITCH);
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int dx = -2; dx <= 2; ++dx)
-      ps_pair_dual(X[2 + j], Z[2 + j + dx], c, 2 + j, n, 2 + j + dx, ks.cc, dx == 0 ? ks.c0 : (dx * dx == 1 ? ks.c1 : ks.c4),
-                   ratio);
-}
-
 // ---- packed (f32x2) form of the dual step -------------------------------------------------------------------
 // sm_100a has two-lane FP32 instructions (FADD2 / FFMA2, with operand negation and scalar broadcast operands): the
 // same lane rate as the scalar ones but HALF the issue slots, and this kernel is bound by issue slots.  Two pairs

@@ -587,15 +587,13 @@ __global__ void __launch_bounds__(SG_THREADS, 1)
           const int ty = i / ncb, kk = i - ty * ncb;
           const int x = kk < nlo ? K.x0 + kk : hi0 + (kk - nlo), y = K.ys + ty;
           const int slot = ps_band_slot(x, W);
-          float ac[1], ab[1], pz[1];
-          ps_xfix_item<1>(H, 1.f, 1.f, 1.f, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, ac, pz);
-          ps_xfix_item<1>(H, P.g1b, P.g4b, P.ratio, s_img, s_p, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ab, pz);
-          const float p0 = pz[0];
-          lsum_c = fmaf(p0 + p0 - 1.f, ac[0], lsum_c);  // the losses are linear in G: the corrections' share
-          lsum_b = fmaf(p0 + p0 - 1.f, ab[0], lsum_b);
+          float ac, ab, p0;  // both losses from one set of partner loads and one squared distance
+          ps_xfix_dual(H, P.g1b, P.g4b, P.ratio, s_img, s_p, s_wx + slot * 10, s_wx + 60 + slot * 10, K.ys, K.x0, y, x, ac, ab, p0);
+          lsum_c = fmaf(p0 + p0 - 1.f, ac, lsum_c);  // the losses are linear in G: the corrections' share
+          lsum_b = fmaf(p0 + p0 - 1.f, ab, lsum_b);
           if (P.grad) {
-            const float gc = ac[0] + s_gband[(ty + 2) * 12 + slot * 2 + 0];
-            const float gb = ab[0] + s_gband[(ty + 2) * 12 + slot * 2 + 1];
+            const float gc = ac + s_gband[(ty + 2) * 12 + slot * 2 + 0];
+            const float gb = ab + s_gband[(ty + 2) * 12 + slot * 2 + 1];
             unsigned lab = 2u;
             if (want_ce) {
               const size_t pix = ((size_t)K.b * H + y) * W + x;
