@@ -15,3 +15,7 @@ import json,sys
 d=json.load(open(sys.argv[1])); print(sys.argv[1], d["metric"][:40], round(d["value"],2), d["unit"], "ms/step", round(d["ms_per_step"],4), "frac", round(d["roofline"]["frac"],3), "e2e", round(d["e2e"]["value"],2), d.get("stage_share",""))
 PY
 done
+PYTHONPATH=. python scripts/bench_ccl.py > gpurun_out/r2_ccl_bench.txt 2>&1
+PYTHONPATH=. python scripts/bench_refine.py > gpurun_out/r2_refine.txt 2>&1
+PYTHONPATH=. python scripts/sweep_layercam.py > gpurun_out/r2_sweep_layercam.txt 2>gpurun_out/sweep_layercam.err
+PYTHONPATH=. python scripts/bench_layercam_small.py > gpurun_out/r2_layercam_small.txt 2>&1

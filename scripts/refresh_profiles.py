@@ -99,7 +99,9 @@ with open(os.path.join(pr, f"{tag}_a_scale.txt"), "w") as f:
                 f"{e['variants']['bf16_logits_u8_images']['value']:.2f} | {lc.get('value', float('nan')):.0f} | {lc.get('ms_per_pass', float('nan')):.2f} | "
                 f"{(lc.get('roofline') or {}).get('frac', float('nan')):.3f} | {ts.get('value', float('nan')):.0f} | {ts.get('ms_per_step', float('nan')):.2f} | "
                 f"{(ts.get('stage_share') or {}).get('loss_fwd_bwd_ms', float('nan')):.3f}\n")
-for src, dst in (("r2_trace_stream_c.txt", "f_trace_stream.txt"),):
+for src, dst in (("r2_trace_stream_c.txt", "f_trace_stream.txt"), ("r2_ccl_bench.txt", "i_keep_largest_bench.txt"),
+                 ("r2_refine.txt", "e_refine_native.txt"), ("r2_sweep_layercam.txt", "j_sweep_layercam_config5.txt"),
+                 ("r2_layercam_small.txt", "h_layercam_small_batch.txt")):
     if os.path.exists(os.path.join(go, src)):
         shutil.copy(os.path.join(go, src), os.path.join(pr, f"{tag}_{dst}"))
 print(open(os.path.join(pr, f"{tag}_a_scale.txt")).read())
