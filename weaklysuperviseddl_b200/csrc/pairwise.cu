@@ -693,10 +693,15 @@ extern "C" int wsdl_pairwise_fwd_bwd(const float* values, const float* images, i
                                per_image_loss, grad_out, loss_out, grad_values, workspace, workspace_bytes, stream, false);
 }
 
+// A prepared workspace: tickets / control words zero, everything behind them "empty" (all ones -- the state the fused
+// launch's per-CTA result slots are polled for and left in; the other kernels write their partials before they read them).
 extern "C" int wsdl_pairwise_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (!workspace) return WSDL_E_NULL;
   if (workspace_bytes < 512) return WSDL_E_WORKSPACE;
-  return (int)cudaMemsetAsync(workspace, 0, 512, (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 512, (cudaStream_t)stream);
+  if (e == cudaSuccess && workspace_bytes > 512)
+    e = cudaMemsetAsync(reinterpret_cast<unsigned char*>(workspace) + 512, 0xff, workspace_bytes - 512, (cudaStream_t)stream);
+  return (int)e;
 }
 
 extern "C" int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int B, int C, int H, int W,
@@ -710,11 +715,15 @@ extern "C" int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* 
 
 static size_t sg_bytes(int B, int H, int W) { return 512 + pw_align(sg_workspace_floats(B, H, W) * sizeof(float)); }
 
+// result slots of the fused launch (one 64-bit word per CTA), a region of their own at the end of the workspace: no other
+// kernel that may share a prepared workspace ever writes there
+static size_t dual_slot_bytes(int B, int H, int W) { return pw_align(ps_workspace_floats(B, H, W) * sizeof(unsigned long long)); }
+
 extern "C" size_t wsdl_pairwise_dual_workspace_bytes(int B, int H, int W) {
   const size_t one = wsdl_pairwise_workspace_bytes(B, H, W);
   if (!one) return 0;
   const size_t sg = sg_bytes(B, H, W);
-  return 2 * one > sg ? 2 * one : sg;
+  return (2 * one > sg ? 2 * one : sg) + 256 + dual_slot_bytes(B, H, W);
 }
 
 extern "C" size_t wsdl_weak_loss_workspace_bytes(int B, int H, int W) {
@@ -767,7 +776,8 @@ extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* imag
   uintptr_t ws = ((uintptr_t)workspace + 255) / 256 * 256;
   P.ticket = reinterpret_cast<unsigned*>(ws);
   P.partial = reinterpret_cast<float*>(ws + 256);
-  float* partial_bnd = reinterpret_cast<float*>(ws + 256 + (one - 512));
+  const size_t slot_bytes = dual_slot_bytes(B, H, W);
+  unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws + (wsdl_pairwise_dual_workspace_bytes(B, H, W) - 256 - slot_bytes));
   P.B = B, P.C = 2, P.H = H, P.W = W, P.pad = 2;
   P.tiles_x = (W + PW_TW - 1) / PW_TW;
   P.tiles_y = (H + PW_TH - 1) / PW_TH;
@@ -778,10 +788,10 @@ extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* imag
   P.ks_unit = 0.f;
   P.kappa = 1.0 / (24.0 * (double)B * (double)H * (double)W * 2.0);
   if (!prepared && no_stream) {
-    cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
+    cudaError_t e = cudaMemsetAsync(slots, 0xff, slot_bytes, s);
     if (e != cudaSuccess) return (int)e;
   }
-  const int rc = ps_launch_dual(P, sigma_cut, sigma_bnd, sigma_space, grad_out_bnd, loss_bnd, partial_bnd, s);
+  const int rc = ps_launch_dual(P, sigma_cut, sigma_bnd, sigma_space, grad_out_bnd, loss_bnd, slots, s);
   return rc == 1 ? WSDL_E_SHAPE : rc;
 }
 

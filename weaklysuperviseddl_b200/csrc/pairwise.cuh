@@ -37,7 +37,7 @@ size_t ps_workspace_floats(int B, int H, int W);
 // Cut loss on the logits + boundary loss on softmax(logits) of a two-class batch in one pass (pairwise_sym.cu).
 // P describes the cut loss; returns 1 when the shape is not supported.
 int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_bnd,
-                   float* loss_bnd, float* partial_bnd, cudaStream_t s);
+                   float* loss_bnd, unsigned long long* slots, cudaStream_t s);
 
 // Persistent tile-streaming kernel for the whole weak-supervision loss of a two-class batch (pairwise_stream.cu):
 // cut + boundary (+ cross-entropy) forward and d/dlogits in one launch, f32 / bf16 logits, f32 / u8 images.

@@ -616,10 +616,17 @@ struct PsCfg {
 // and one tile load, one conversion, one emit.  Two accumulated channels (G of the cut loss, G of the boundary loss)
 // over ONE stored probability channel (p1 = 1 - p0 for both).  Output: both loss values and
 // d(go_cut L_cut + sum_b go_bnd[b] L_bnd[b]) / d logits.
+constexpr unsigned long long PS_SLOT_EMPTY = ~0ull;
+__device__ __forceinline__ unsigned long long ps_ld_slot(const unsigned long long* p) {  // from L2, never hoisted
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct PsDual {
   const float* grad_out_bnd;  // nullable, B upstream gradients of the per-image boundary losses (cut: Q.p.grad_out)
   float* loss_bnd;            // B floats (cut: Q.p.loss_out, 1 float)
-  float* partial_bnd;         // second partial array
+  unsigned long long* slots;  // one per CTA: (cut partial, boundary partial) as two floats, PS_SLOT_EMPTY when unused
   double kappa_bnd;           // 1 / (K H W)
   float ratio;                // (sigma_cut / sigma_bnd)^2: squared distances are staged for the cut loss
   float ksu_b;                // spatial exponent unit of the boundary loss

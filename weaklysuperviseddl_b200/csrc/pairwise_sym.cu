@@ -831,8 +831,11 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
 
   PS_TR(12);
   // ---- loss partials (cut, boundary) per CTA; the last CTA of the grid finishes both ----
+  // No ticket and no fence: a CTA publishes its two partials as ONE naturally aligned 64-bit store into its own slot, and
+  // the finisher polls the slots until none holds the "empty" pattern (all ones: a NaN no arithmetic produces), sums
+  // them in a fixed order and puts the pattern back.  A release reduction on a ticket would make every CTA wait for the
+  // L2 to acknowledge its partials before it may retire -- 0.4 us of a fused launch (profiles/r02_g_phase_skip.txt).
   const int kpi = Q.nb * Q.n_x;
-  const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
   const bool finisher = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
   {
     const float wc = warp_sum(lsum_c), wb = warp_sum(lsum_b);
@@ -842,29 +845,27 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       float tc = 0.f, tb = 0.f;
 #pragma unroll
       for (int i = 0; i < PS_THREADS / 32; ++i) tc += s_red[0][i], tb += s_red[1][i];
-      const size_t idx = (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x;
-      __stcg(Q.p.partial + idx, 2.f * tc);
-      __stcg(D.partial_bnd + idx, 2.f * tb);
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
+      unsigned long long v = (unsigned long long)__float_as_uint(2.f * tc) | ((unsigned long long)__float_as_uint(2.f * tb) << 32);
+      if (v == PS_SLOT_EMPTY) v = 0x7fffffff7fffffffull;  // cannot happen with finite inputs; keep a NaN a NaN
+      __stcg(D.slots + (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x, v);
     }
   }
   PS_TR(13);
   if (!finisher) return;
-  if (tid == 0) {
-    unsigned seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
-      if (seen < n_ctas) __nanosleep(200);
-    } while (seen < n_ctas);
-    *Q.p.ticket = 0u;
-  }
-  __syncthreads();
   double wtot = 0.0;
   for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {  // image by image: cut summed over the batch, boundary per image
     double ac = 0.0, ab = 0.0;
     for (int i = lane; i < kpi; i += 32) {
-      ac += (double)ld_cg_f32(Q.p.partial + (size_t)b * kpi + i);
-      ab += (double)ld_cg_f32(D.partial_bnd + (size_t)b * kpi + i);
+      unsigned long long* slot = D.slots + (size_t)b * kpi + i;
+      unsigned long long v;
+      unsigned spins = 0;
+      while ((v = ps_ld_slot(slot)) == PS_SLOT_EMPTY) {
+        __nanosleep(100);
+        if (++spins > (1u << 24)) __trap();  // a CTA that never reports: fail instead of hanging the device
+      }
+      __stcg(slot, PS_SLOT_EMPTY);
+      ac += (double)__uint_as_float((unsigned)v);
+      ab += (double)__uint_as_float((unsigned)(v >> 32));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ac += __shfl_xor_sync(0xffffffffu, ac, o), ab += __shfl_xor_sync(0xffffffffu, ab, o);
@@ -1002,7 +1003,7 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
 // Host side of the dual kernel.  P describes the cut loss (values = logits, C = 2, inner softmax, batch-mean loss,
 // kc for sigma_cut, no spatial term); the boundary loss comes in through the extra arguments.
 int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float sigma_space, const float* grad_out_bnd,
-                   float* loss_bnd, float* partial_bnd, cudaStream_t s) {
+                   float* loss_bnd, unsigned long long* slots, cudaStream_t s) {
   if (P.pad != 2 || P.C != 2 || P.H < 6 || P.W < 6 || !P.inner_softmax || P.per_image) return 1;
   PsParams Q;
   Q.p = P;
@@ -1026,7 +1027,7 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   PsDual D;
   D.grad_out_bnd = grad_out_bnd;
   D.loss_bnd = loss_bnd;
-  D.partial_bnd = partial_bnd;
+  D.slots = slots;
   D.kappa_bnd = 1.0 / (24.0 * (double)P.H * (double)P.W);
   D.ratio = (sigma_cut * sigma_cut) / (sigma_bnd * sigma_bnd);
   const float inv_2ss = sigma_space > 0.f ? 1.f / (2.f * sigma_space * sigma_space) : 0.f;
