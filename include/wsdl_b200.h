@@ -114,10 +114,10 @@ int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* The same call for a PREPARED workspace: one that wsdl_pairwise_workspace_init() has initialised once (it zeroes the
- * 512-byte control block) and that has since only been used by complete pairwise calls ordered on one stream.
- * Every pairwise kernel leaves the control block initialised again, so the per-call 8-byte memset of
- * wsdl_pairwise_fwd_bwd (one extra node per call in a CUDA graph) is not needed.  A workspace must not be shared by
- * calls that may run concurrently. */
+ * 512-byte control block and marks the per-CTA result slots behind it "empty" -- all ones; a zero-filled buffer is NOT
+ * a prepared workspace) and that has since only been used by complete pairwise calls ordered on one stream.
+ * Every pairwise kernel leaves the workspace prepared again, so the per-call memsets of wsdl_pairwise_fwd_bwd (extra
+ * nodes per call in a CUDA graph) are not needed.  A workspace must not be shared by calls that may run concurrently. */
 int wsdl_pairwise_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
 int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int B, int C, int H, int W, int window,
@@ -136,7 +136,7 @@ int wsdl_pairwise_fwd_bwd_prepared(const float* values, const float* images, int
  *   grad_logits nullable (B,2,H,W): d(go_cut * loss_cut + sum_b go_bnd[b] * loss_bnd[b]) / d logits, softmax backward
  *   included; grad_out_cut / grad_out_bnd nullable device pointers (1 / B floats), NULL = 1.0;
  *   workspace >= wsdl_pairwise_dual_workspace_bytes(); prepared != 0: initialised with wsdl_pairwise_workspace_init
- *   (self-cleaning, as for wsdl_pairwise_fwd_bwd_prepared), 0: the call zeroes the ticket itself. */
+ *   (self-cleaning, as for wsdl_pairwise_fwd_bwd_prepared), 0: the call resets its result slots itself. */
 size_t wsdl_pairwise_dual_workspace_bytes(int B, int H, int W);
 
 int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* images, int B, int H, int W, int window,

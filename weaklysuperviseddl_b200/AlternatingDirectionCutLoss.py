@@ -94,7 +94,10 @@ class _Refiner:
             self.n_ref = lib.wsdl_refine_workspace_bytes(B, H, W)
             self.n_pw = lib.wsdl_pairwise_workspace_bytes(B, H, W)
             self.ws_ref = torch.zeros(self.n_ref, dtype=torch.uint8, device=device)  # zeroed once: the kernels keep it so
-            self.ws_pw = torch.zeros(max(self.n_pw, 512), dtype=torch.uint8, device=device)
+            self.ws_pw = torch.empty(max(self.n_pw, 512), dtype=torch.uint8, device=device)
+            WF._native.check(lib.wsdl_pairwise_workspace_init(self.ws_pw.data_ptr(), self.ws_pw.numel(),
+                                                              torch.cuda.current_stream(device).cuda_stream),
+                             "wsdl_pairwise_workspace_init")  # prepared once: the kernels leave it prepared
         self.graph = None
         if use_graph:
             side = torch.cuda.Stream(device)

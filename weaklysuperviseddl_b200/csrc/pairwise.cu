@@ -620,7 +620,13 @@ extern "C" size_t wsdl_pairwise_workspace_bytes(int B, int H, int W) {
   size_t floats = (size_t)B * tiles;  // one partial per 32x32 tile (generic / fast kernels)
   const size_t sym = ps_workspace_floats(B, H, W);
   if (sym > floats) floats = sym;
-  return 512 + pw_align(floats * sizeof(float));
+  // ... and, behind them, the result slots of the pair-symmetric kernels (one word per CTA): a region no other kernel writes
+  return 512 + pw_align(floats * sizeof(float)) + pw_align(sym * sizeof(unsigned));
+}
+
+static unsigned* pw_sym_slots(uintptr_t ws, int B, int H, int W) {
+  const size_t sym_bytes = pw_align(ps_workspace_floats(B, H, W) * sizeof(unsigned));
+  return reinterpret_cast<unsigned*>(ws + (wsdl_pairwise_workspace_bytes(B, H, W) - sym_bytes));
 }
 
 static int pairwise_fwd_bwd_impl(const float* values, const float* images, int B, int C, int H, int W, int window,
@@ -650,6 +656,7 @@ static int pairwise_fwd_bwd_impl(const float* values, const float* images, int B
   uintptr_t ws = ((uintptr_t)workspace + 255) / 256 * 256;
   P.ticket = reinterpret_cast<unsigned*>(ws);
   P.partial = reinterpret_cast<float*>(ws + 256);
+  P.sym_slots = pw_sym_slots(ws, B, H, W);
   P.B = B, P.C = C, P.H = H, P.W = W, P.pad = pad;
   P.tiles_x = (W + PW_TW - 1) / PW_TW;
   P.tiles_y = (H + PW_TH - 1) / PW_TH;
@@ -663,8 +670,9 @@ static int pairwise_fwd_bwd_impl(const float* values, const float* images, int B
   const double K = (double)window * window - 1.0;
   const double N = (per_image_loss ? 1.0 : (double)B) * (double)H * (double)W;
   P.kappa = 1.0 / (K * N * (divide_by_c ? (double)C : 1.0));
-  if (!prepared) {  // every kernel leaves the ticket at 0 again: a prepared workspace needs no per-call memset
+  if (!prepared) {  // every kernel leaves its ticket at 0 / its slots empty again: a prepared workspace needs no per-call memset
     cudaError_t e = cudaMemsetAsync(P.ticket, 0, 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P.sym_slots, 0xff, ps_workspace_floats(B, H, W) * sizeof(unsigned), s);
     if (e != cudaSuccess) return (int)e;
   }
   if (pad == 2 && H > 2 * PF_PAD && W > 2 * PF_PAD) {
@@ -776,6 +784,7 @@ extern "C" int wsdl_pairwise_dual_fwd_bwd(const float* logits, const float* imag
   uintptr_t ws = ((uintptr_t)workspace + 255) / 256 * 256;
   P.ticket = reinterpret_cast<unsigned*>(ws);
   P.partial = reinterpret_cast<float*>(ws + 256);
+  P.sym_slots = nullptr;
   const size_t slot_bytes = dual_slot_bytes(B, H, W);
   unsigned long long* slots = reinterpret_cast<unsigned long long*>(ws + (wsdl_pairwise_dual_workspace_bytes(B, H, W) - 256 - slot_bytes));
   P.B = B, P.C = 2, P.H = H, P.W = W, P.pad = 2;

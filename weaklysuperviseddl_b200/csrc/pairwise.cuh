@@ -14,6 +14,7 @@ struct PwParams {
   float* grad_values;     // nullable
   float* partial;         // block partial sums (layout is the kernel's own)
   unsigned* ticket;
+  unsigned* sym_slots;    // pair-symmetric kernels: one result slot per CTA, 0xffffffff when empty (a region of its own)
   int B, C, H, W, pad;
   int tiles_x, tiles_y;
   int inner_softmax, per_image;

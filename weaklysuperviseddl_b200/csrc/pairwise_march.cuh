@@ -47,6 +47,7 @@ struct PsParams {
   float img_scale;  // sqrt(-kc)
   float g1, g4;     // gamma, gamma^4 (gamma = exp(-1 / (2 sigma_space^2)), 1 without a spatial term)
   float l32, l1g;   // log2(3/2), log2(1 + gamma^4): row-border pair multiplicities as exponent offsets
+  unsigned* slots;  // single-loss kernels: one loss partial per CTA (a float's bits), 0xffffffff when empty
 };
 
 constexpr float PS_SENTINEL = 1e15f;  // staged colour (channel 0) of positions outside the image: 2^-(1e30) = 0

@@ -358,10 +358,11 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   }
 
   PS_TR(12);
-  // ---- one loss partial per CTA (fire and forget); the last CTA of the grid waits for all of them and adds them
-  // per image in a fixed order, in double.  Every other CTA was dispatched before it and none waits for it. ----
+  // ---- one loss partial per CTA (fire and forget, one 32-bit store into the CTA's own slot); the last CTA of the grid
+  // polls the slots until none holds the "empty" pattern (all ones: a NaN no arithmetic produces), adds them per image in
+  // a fixed order, in double, and puts the pattern back.  No ticket, no fence: a CTA retires without waiting for the L2
+  // to acknowledge its partial.  Every other CTA was dispatched before the finisher and none waits for it. ----
   const int kpi = Q.nb * Q.n_x;  // CTAs (= partials) per image
-  const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z;
   const bool finisher = blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
   {
     const float w = warp_sum(lsum);
@@ -371,8 +372,9 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       float t = 0.f;
 #pragma unroll
       for (int i = 0; i < PS_THREADS / 32; ++i) t += s_red[i];
-      __stcg(Q.p.partial + (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x, 2.f * t);
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(Q.p.ticket) : "memory");
+      unsigned v = __float_as_uint(2.f * t);
+      if (v == 0xffffffffu) v = 0x7fffffffu;  // cannot happen with finite inputs; keep a NaN a NaN
+      __stcg(Q.slots + (size_t)K.b * kpi + blockIdx.y * Q.nb + blockIdx.x, v);
     }
   }
   PS_TR(13);
@@ -387,46 +389,28 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   }
 #endif
   if (!finisher) return;
-  if (tid == 0) {
-    unsigned seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(Q.p.ticket) : "memory");
-      if (seen < n_ctas) __nanosleep(200);
-    } while (seen < n_ctas);
-    *Q.p.ticket = 0u;  // every CTA has checked in: leave the ticket ready for the next launch
-  }
-  __syncthreads();
-  // The tile is no longer needed: stage the partials of a group of images in its shared memory with independent
-  // loads (one L2 round trip instead of one per image), then add them per image in a fixed order.
   double wtot = 0.0;
-  float* s_part = ps_smem;
-  constexpr int STAGE = 3 * PS_PLANE;  // floats available
-  const int ipc = kpi <= STAGE ? STAGE / kpi : 0;  // images per staged group (0: partials of one image do not fit)
-  for (int b0 = 0; b0 < Q.p.B; b0 += (ipc ? ipc : 1)) {
-    const int nb_img = ipc ? min(ipc, Q.p.B - b0) : 1;
-    if (ipc) {
-      const int n = nb_img * kpi;
-      const float* src = Q.p.partial + (size_t)b0 * kpi;
-#pragma unroll 8
-      for (int i = tid; i < n; i += PS_THREADS) s_part[i] = ld_cg_f32(src + i);
-      __syncthreads();
-    }
-    for (int b = warp; b < nb_img; b += PS_THREADS / 32) {
-      double acc = 0.0;
-      if (ipc) {
-        for (int i = lane; i < kpi; i += 32) acc += (double)s_part[b * kpi + i];
-      } else {
-        for (int i = lane; i < kpi; i += 32) acc += (double)ld_cg_f32(Q.p.partial + (size_t)(b0 + b) * kpi + i);
+  for (int b = warp; b < Q.p.B; b += PS_THREADS / 32) {
+    double acc = 0.0;
+    for (int i = lane; i < kpi; i += 32) {
+      unsigned* slot = Q.slots + (size_t)b * kpi + i;
+      unsigned v, spins = 0;
+      while (true) {
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+        if (v != 0xffffffffu) break;
+        __nanosleep(100);
+        if (++spins > (1u << 24)) __trap();  // a CTA that never reports: fail instead of hanging the device
       }
+      __stcg(slot, 0xffffffffu);
+      acc += (double)__uint_as_float(v);
+    }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (Q.p.per_image) {
-        if (lane == 0) Q.p.loss_out[b0 + b] = (float)(acc * Q.p.kappa);
-      } else {
-        wtot += acc;
-      }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (Q.p.per_image) {
+      if (lane == 0) Q.p.loss_out[b] = (float)(acc * Q.p.kappa);
+    } else {
+      wtot += acc;
     }
-    if (ipc) __syncthreads();  // the next group overwrites the stage
   }
   if (!Q.p.per_image) {
     if (lane == 0) s_dred[warp] = wtot;
@@ -977,6 +961,7 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   const int n_max = (P.H + Q.nb - 1) / Q.nb;
   Q.S = (n_max + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n_max + 2 + PS_SEGS - 1) / PS_SEGS;
   Q.nb = (P.H + PS_SEGS * Q.S - 3) / (PS_SEGS * Q.S - 2);  // blocks of 8 S - 2 rows: never more than the model chose
+  Q.slots = P.sym_slots;
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
