@@ -3,6 +3,7 @@
 // See pairwise_sym.cu for the derivations (pair symmetry, Euler loss, border multiplicities, sentinel colour).
 #pragma once
 #include <cuda.h>
+#include <string.h>
 
 #include "pairwise.cuh"
 
@@ -48,6 +49,7 @@ struct PsParams {
   float g1, g4;     // gamma, gamma^4 (gamma = exp(-1 / (2 sigma_space^2)), 1 without a spatial term)
   float l32, l1g;   // log2(3/2), log2(1 + gamma^4): row-border pair multiplicities as exponent offsets
   unsigned* slots;  // single-loss kernels: one loss partial per CTA (a float's bits), 0xffffffff when empty
+  float kappa4;     // (float)(4 kappa): rounded on the host (no double-precision arithmetic in the CTAs' prologue)
 };
 
 constexpr float PS_SENTINEL = 1e15f;  // staged colour (channel 0) of positions outside the image: 2^-(1e30) = 0
@@ -332,13 +334,13 @@ __device__ __forceinline__ void ps_emit(const PsParams& Q, const PsBlk& K, int t
 }
 
 // gamma^(k^2) for k = 0, 1, 2
-__device__ __forceinline__ float ps_gpow(int k, float g1, float g4) { return k == 0 ? 1.f : (k == 1 ? g1 : g4); }
+__host__ __device__ __forceinline__ float ps_gpow(int k, float g1, float g4) { return k == 0 ? 1.f : (k == 1 ? g1 : g4); }
 
 // W(u -> v) = sum_{d=-2..2} [reflect(u + d) == v] gamma^(d^2) for u inside [0, n), n >= 6; 0 for v outside (closed
 // form of pairwise.cu's axis_multiplicity for pad 2).
-__device__ __forceinline__ float ps_w1d(int u, int v, int n, float g1, float g4) {
+__host__ __device__ __forceinline__ float ps_w1d(int u, int v, int n, float g1, float g4) {
   if (v < 0 || v >= n) return 0.f;
-  const int d = abs(v - u), s = u + v, e = 2 * (n - 1) - s;
+  const int d = v > u ? v - u : u - v, s = u + v, e = 2 * (n - 1) - s;
   float w = d <= 2 ? ps_gpow(d, g1, g4) : 0.f;
   if (v >= 1 && s <= 2) w += ps_gpow(s, g1, g4);      // offset -s lands on -v, which reflects to v
   if (v <= n - 2 && e <= 2) w += ps_gpow(e, g1, g4);  // offset +e lands on 2(n-1) - v
@@ -346,8 +348,8 @@ __device__ __forceinline__ float ps_w1d(int u, int v, int n, float g1, float g4)
 }
 
 // multiplicity the march applies to a pair of rows (relative to the interior 2 gamma^|d|^2): see the row step
-__device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
-  const int lo = min(ya, yb), d = abs(ya - yb);
+__host__ __device__ __forceinline__ float ps_row_mult(int ya, int yb, int H, float g4) {
+  const int lo = ya < yb ? ya : yb, d = ya < yb ? yb - ya : ya - yb;
   if (d == 0) return (lo == 1 || lo == H - 2) ? 1.f + g4 : 1.f;
   return (lo == 0 || lo + d == H - 1) ? 1.5f : 1.f;
 }
@@ -629,10 +631,62 @@ struct PsDual {
   float* loss_bnd;            // B floats (cut: Q.p.loss_out, 1 float)
   unsigned long long* slots;  // one per CTA: (cut partial, boundary partial) as two floats, PS_SLOT_EMPTY when unused
   double kappa_bnd;           // 1 / (K H W)
+  float kappa_bnd4;           // (float)(4 kappa_bnd)
   float ratio;                // (sigma_cut / sigma_bnd)^2: squared distances are staged for the cut loss
   float ksu_b;                // spatial exponent unit of the boundary loss
   float g1b, g4b, l1g_b;      // gamma, gamma^4, log2(1 + gamma^4) of the boundary loss (cut: 1, 1, 1)
+  // Weight tables of the band-column pass, the same for every CTA of a launch: built once on the host (ps_band_tables),
+  // copied to shared memory by the border tiles.  fx [6 slots][2][8]: per band slot its two partner columns whose weights
+  // differ from the interior's (offset, then 1/2 of Wx(a->b), Wx(b->a), 1 for the cut loss and the same three for the
+  // boundary loss); wy [11][5][8]: per row-band row (0..4, H-5..H-1, "any other") and partner row its forward / backward /
+  // applied-by-the-march row weights for the cut loss and for the boundary loss.
+  float fx[6 * 2 * 8];
+  float wy[11 * 5 * 8];
 };
+
+// (H >= 10: the row bands of the two image borders do not overlap)
+inline void ps_band_tables(PsDual& D, int H, int W) {
+  for (int slot = 0; slot < 6; ++slot) {
+    float wc[10], wb[10];
+    const int x = slot < 3 ? slot : W - 6 + slot;
+    for (int r = 0; r < 10; ++r) {
+      const int xb = x + r % 5 - 2;
+      const bool in = xb >= 0 && xb < W;
+      wc[r] = !in ? 0.f : (r < 5 ? ps_w1d(x, xb, W, 1.f, 1.f) : ps_w1d(xb, x, W, 1.f, 1.f));
+      wb[r] = !in ? 0.f : (r < 5 ? ps_w1d(x, xb, W, D.g1b, D.g4b) : ps_w1d(xb, x, W, D.g1b, D.g4b));
+    }
+    for (int u = 0; u < 2; ++u) {
+      int found = -1, cnt = 0;
+      for (int j = 0; j < 5; ++j)
+        if (wc[j] != 0.f && (wc[j] != 1.f || wc[5 + j] != 1.f)) {
+          if (cnt == u) found = j;
+          ++cnt;
+        }
+      const int j = found < 0 ? 2 : found;  // no such column: the pixel's own, weight 0
+      const float live = found < 0 ? 0.f : 0.5f;
+      float* fx = D.fx + (slot * 2 + u) * 8;
+      memcpy(&fx[0], &j, sizeof(int));
+      fx[1] = live * wc[j], fx[2] = live * wc[5 + j], fx[3] = live;
+      fx[4] = live * wb[j], fx[5] = live * wb[5 + j], fx[6] = live * ps_gpow(j < 2 ? 2 - j : j - 2, D.g1b, D.g4b), fx[7] = 0.f;
+    }
+  }
+  for (int rs = 0; rs < 11; ++rs)
+    for (int i = 0; i < 5; ++i) {
+      const float g = ps_gpow(i < 2 ? 2 - i : i - 2, D.g1b, D.g4b);
+      float* w = D.wy + (rs * 5 + i) * 8;
+      w[0] = 1.f, w[1] = 1.f, w[2] = 2.f, w[3] = g, w[4] = g, w[5] = 2.f * g, w[6] = 0.f, w[7] = 0.f;
+      if (rs < 10) {
+        const int zy = rs < 5 ? rs : H - 10 + rs, yb = zy + i - 2;
+        const bool in = yb >= 0 && yb < H;
+        w[0] = in ? ps_w1d(zy, yb, H, 1.f, 1.f) : 0.f;
+        w[1] = in ? ps_w1d(yb, zy, H, 1.f, 1.f) : 0.f;
+        w[2] = in ? 2.f * ps_row_mult(zy, yb, H, 1.f) : 0.f;
+        w[3] = in ? ps_w1d(zy, yb, H, D.g1b, D.g4b) : 0.f;
+        w[4] = in ? ps_w1d(yb, zy, H, D.g1b, D.g4b) : 0.f;
+        w[5] = in ? 2.f * g * ps_row_mult(zy, yb, H, D.g4b) : 0.f;
+      }
+    }
+}
 
 struct PsKsDual {  // per pair class: cut exponent offset, and boundary offset minus ratio * cut offset
   float ca, cb, cc;  // cut: same row, one row down, two rows down (no spatial term: one value per row distance)

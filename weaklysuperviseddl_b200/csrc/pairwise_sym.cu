@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   __syncthreads();  // s_bar is initialised
   pdl_wait();  // (see pairwise_dual_kernel: the prologue above runs under the previous kernel's tail)
   pdl_launch_dependents();
-  K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
+  K.scale2 = Q.kappa4 * (Q.p.grad_out ? __ldg(Q.p.grad_out + (Q.p.per_image ? K.b : 0)) : 1.f);
 
   // ---- each warp: its own rows (the centre rows of its two segments; warp 3 also the 2 look-ahead rows) ----
   {
@@ -557,13 +557,17 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
     if (slot >= 0) okmask |= (slot + 1) << (4 + 4 * j);
   }
   float lsum_c = 0.f, lsum_b = 0.f;
-  if (K.xband && tid < 120) {  // column weights of the band slots for gamma = 1 (cut) and gamma_b (boundary)
-    const int which = tid / 60, e = tid - which * 60, slot = e / 10, rem = e - slot * 10, j = rem % 5;
-    const float g1 = which ? D.g1b : 1.f, g4 = which ? D.g4b : 1.f;
-    const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
-    float w = 0.f;
-    if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, g1, g4) : ps_w1d(xb, x, W, g1, g4);
-    s_wx[tid] = w;
+  if (K.xband) {
+    if (H >= 10) {  // the band pass's weight tables: built on the host once per launch (ps_band_tables), 2.1 KB
+      for (int i = tid; i < 6 * 2 * 8 + 11 * 5 * 8; i += PS_THREADS) s_fx[i] = i < 96 ? D.fx[i] : D.wy[i - 96];
+    } else if (tid < 120) {  // tiny images take the generic band pass: its column weights for gamma = 1 and gamma_b
+      const int which = tid / 60, e = tid - which * 60, slot = e / 10, rem = e - slot * 10, j = rem % 5;
+      const float g1 = which ? D.g1b : 1.f, g4 = which ? D.g4b : 1.f;
+      const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
+      float w = 0.f;
+      if (xb >= 0 && xb < W) w = rem < 5 ? ps_w1d(x, xb, W, g1, g4) : ps_w1d(xb, x, W, g1, g4);
+      s_wx[tid] = w;
+    }
   }
   __syncthreads();  // s_bar is initialised
   // Everything above is index arithmetic and shared-memory tables: launched with programmatic stream serialization, a
@@ -571,47 +575,8 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   // for that kernel's memory to be visible.  Dependents of THIS launch may be scheduled as soon as every CTA got here.
   pdl_wait();
   pdl_launch_dependents();
-  K.scale2 = (float)(4.0 * Q.p.kappa) * (Q.p.grad_out ? __ldg(Q.p.grad_out) : 1.f);
-  const float scale_b = (float)(4.0 * D.kappa_bnd) * (D.grad_out_bnd ? __ldg(D.grad_out_bnd + K.b) : 1.f);
-  if (K.xband && tid < 12) {
-    // A band pixel differs from the interior in at most two partner columns (the reflect geometry, the same for both
-    // losses).  Per slot and such column: its offset and 1/2 of the column weights Wx(a->b), Wx(b->a), gamma_b^dx^2.
-    const int slot = tid >> 1, u = tid & 1;
-    const float* wc = s_wx + slot * 10;
-    const float* wb = s_wx + 60 + slot * 10;
-    int found = -1, cnt = 0;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float f = wc[j], b = wc[5 + j];
-      if (f != 0.f && (f != 1.f || b != 1.f)) {
-        if (cnt == u) found = j;
-        ++cnt;
-      }
-    }
-    const int j = found < 0 ? 2 : found;  // no such column: the pixel's own, weight 0
-    const float live = found < 0 ? 0.f : 0.5f;
-    float* fx = s_fx + tid * 8;
-    fx[0] = __int_as_float(j), fx[1] = live * wc[j], fx[2] = live * wc[5 + j], fx[3] = live;
-    fx[4] = live * wb[j], fx[5] = live * wb[5 + j], fx[6] = live * ps_gpow(j < 2 ? 2 - j : j - 2, D.g1b, D.g4b), fx[7] = 0.f;
-  } else if (K.xband && tid >= 32 && tid < 32 + 55) {
-    // Row weights of a band pixel in row zy towards its partner row zy + i - 2: forward, backward, and what the march
-    // applied (cut: gamma = 1; boundary: gamma_b).  Slots 0..4: rows 0..4, 5..9: rows H-5..H-1, 10: every other row.
-    const int rs = (tid - 32) / 5, i = (tid - 32) - rs * 5, dd = i < 2 ? 2 - i : i - 2;
-    const float g = ps_gpow(dd, D.g1b, D.g4b);
-    float4 a = make_float4(1.f, 1.f, 2.f, g), b4 = make_float4(g, 2.f * g, 0.f, 0.f);
-    if (rs < 10) {
-      const int zy = rs < 5 ? rs : H - 10 + rs, yb = zy + i - 2;
-      const bool in = yb >= 0 && yb < H;
-      a.x = in ? ps_w1d(zy, yb, H, 1.f, 1.f) : 0.f;
-      a.y = in ? ps_w1d(yb, zy, H, 1.f, 1.f) : 0.f;
-      a.z = in ? 2.f * ps_row_mult(zy, yb, H, 1.f) : 0.f;
-      a.w = in ? ps_w1d(zy, yb, H, D.g1b, D.g4b) : 0.f;
-      b4.x = in ? ps_w1d(yb, zy, H, D.g1b, D.g4b) : 0.f;
-      b4.y = in ? 2.f * g * ps_row_mult(zy, yb, H, D.g4b) : 0.f;
-    }
-    *reinterpret_cast<float4*>(s_wy + (tid - 32) * 8) = a;
-    *reinterpret_cast<float4*>(s_wy + (tid - 32) * 8 + 4) = b4;
-  }
+  K.scale2 = Q.kappa4 * (Q.p.grad_out ? __ldg(Q.p.grad_out) : 1.f);
+  const float scale_b = D.kappa_bnd4 * (D.grad_out_bnd ? __ldg(D.grad_out_bnd + K.b) : 1.f);
 
   {
     const int r0 = min(2 * warp * S, rows), r1 = warp == PS_WARPS - 1 ? rows : min(2 * (warp + 1) * S, rows);
@@ -962,6 +927,7 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   Q.S = (n_max + 2 + PS_SEGS - 1) / PS_SEGS < 2 ? 2 : (n_max + 2 + PS_SEGS - 1) / PS_SEGS;
   Q.nb = (P.H + PS_SEGS * Q.S - 3) / (PS_SEGS * Q.S - 2);  // blocks of 8 S - 2 rows: never more than the model chose
   Q.slots = P.sym_slots;
+  Q.kappa4 = (float)(4.0 * P.kappa);
   Q.vec2_ok = ((P.W & 1) == 0) && (!P.grad_values || ((uintptr_t)P.grad_values & 7) == 0);
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
@@ -993,6 +959,8 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   PsParams Q;
   Q.p = P;
   Q.n_x = (P.W + PS_TW - 1) / PS_TW;
+  Q.slots = nullptr;
+  Q.kappa4 = (float)(4.0 * P.kappa);
   Q.nb = ps_row_blocks(P.B, P.H, P.W, DU_CAP);
   if (Q.nb > 65535 || Q.n_x > 65535 || P.B > 65535) return 1;
   const int n_max = (P.H + Q.nb - 1) / Q.nb;
@@ -1014,11 +982,14 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   D.loss_bnd = loss_bnd;
   D.slots = slots;
   D.kappa_bnd = 1.0 / (24.0 * (double)P.H * (double)P.W);
+  D.kappa_bnd4 = (float)(4.0 * D.kappa_bnd);
   D.ratio = (sigma_cut * sigma_cut) / (sigma_bnd * sigma_bnd);
   const float inv_2ss = sigma_space > 0.f ? 1.f / (2.f * sigma_space * sigma_space) : 0.f;
   D.ksu_b = -LOG2E * inv_2ss;
   D.g1b = expf(-inv_2ss), D.g4b = expf(-4.f * inv_2ss);
   D.l1g_b = log2f(1.f + D.g4b);
+  if (P.H >= 10) ps_band_tables(D, P.H, P.W);
+  else memset(D.fx, 0, sizeof(D.fx)), memset(D.wy, 0, sizeof(D.wy));
   CUtensorMap tm_img, tm_val;
   memset(&tm_img, 0, sizeof(tm_img)), memset(&tm_val, 0, sizeof(tm_val));
   static const int no_tma = WSDL_TUNE_INT("WSDL_PAIRWISE_NO_TMA", 0);
