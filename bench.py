@@ -39,10 +39,10 @@ PHYS_BYTES_PER_PIX = 28  # what ONE fused launch must move per pixel: 20 B in (2
 MIN_TIMED_MS = 20.0      # a short --steps run repeats its K steps until the timed region is at least this long
 BYTES_PER_PIX = 28  # 20 B read (2 logits + 3 rgb) + 8 B gradient written, C=2
 L2_MB = 126
-NCU_TRAFFIC_BYTES = 32_190_000  # dram read 32.18 MB + write 0.01 MB per launch (ncu --set full, profiles/r02_c_ncu_full_pairwise.txt)
+NCU_TRAFFIC_BYTES = 32_220_000  # dram read 32.19 MB + write 0.03 MB per launch (ncu --set full, profiles/r02_c_ncu_full_pairwise.txt)
 # warp instructions per launch (smsp__inst_executed.sum, profiles/r02_c_ncu_full_pairwise.txt; cut / boundary: round 1): the kernels are bound by
 # instruction issue (FP32 + MUFU), not HBM -- 148 SMs x 4 schedulers x 1 instruction per clock is the second roof
-NCU_WARP_INSTR = {"fused": 14.72e6, "cut": 12.13e6, "boundary": 14.11e6}
+NCU_WARP_INSTR = {"fused": 14.52e6, "cut": 12.13e6, "boundary": 14.11e6}
 # third roof of the fused launch: MUFU (ex2 / rcp) warp instructions per launch from the same capture x 32 lanes against
 # the measured MUFU rate of this B200 (tests/native/pipe_probe.cu: 4.63 T lane-op/s = 16 per clock per SM)
 NCU_MUFU_WARP_INSTR = {"fused": 1.674e6}
