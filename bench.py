@@ -576,7 +576,7 @@ def bench_pairwise(args, lib, dev, rank, world):
         also = {}
         for key, fn in (("layercam_3680", lambda: bench_layercam_sharded(dev, rank, world, 3, 1)),
                         ("trainstep", lambda: _trainstep_brief(bench_trainstep(argparse.Namespace(
-                            steps=12, warmup=4, no_cpu_baseline=True), dev, rank, world)))):
+                            steps=16, warmup=8, no_cpu_baseline=True), dev, rank, world)))):
             try:
                 also[key] = fn()
             except Exception as e:  # a side measurement must never take the headline line down

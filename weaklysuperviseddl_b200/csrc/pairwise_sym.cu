@@ -51,7 +51,7 @@
 #include "pairwise_march.cuh"
 
 #ifndef WSDL_X_SKIP
-#define WSDL_X_SKIP 0  // experiments only (dual kernel): 1 no conversion, 2 no head rows, 4 no march, 8 no band pass
+#define WSDL_X_SKIP 0  // measurement builds only (fused kernel, profiles/r02_g_phase_skip.txt): 1 no conversion, 2 no head rows, 4 no march, 8 no band pass
 #endif
 
 namespace wsdl {
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
   PS_TR(11);
   // ---- band columns (and corners) ----
   if (!(WSDL_X_SKIP & 8) && K.xband) {
-    if (!(WSDL_X_SKIP & 64)) __syncthreads();
+    __syncthreads();
     const int nlo = max(0, min(3, xe) - K.x0), hi0 = max(W - 3, K.x0), nhi = max(0, xe - hi0);
     const int ncb = nlo + nhi;
     const size_t plane = (size_t)H * W;
@@ -732,9 +732,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
       const int slot = ps_band_slot(x, W);
       float ac, ab, p0;
-      if (WSDL_X_SKIP & 32) {
-        ac = ab = 0.f, p0 = 0.5f;
-      } else if (H >= 10) {
+      if (H >= 10) {
         // (true pair weight - weight the march applied) / 2 * k (p(a) - p(b)) over the five rows of the two special
         // partner columns, both losses from one set of loads and one squared distance; weights from the two tables
         const int so = (ty + 2) * PS_PITCH + (x - (K.x0 - 4));
@@ -767,7 +765,7 @@ __global__ void __launch_bounds__(PS_THREADS, WSDL_PS_CTAS)
       const float p1 = 1.f - p0;
       lsum_c = fmaf(p0 - p1, ac, lsum_c);  // the losses are linear in G: the corrections' share
       lsum_b = fmaf(p0 - p1, ab, lsum_b);
-      if (!(WSDL_X_SKIP & 16) && Q.p.grad_values) {
+      if (Q.p.grad_values) {
         const int tw = min((ty + 2) / (2 * S), PS_WARPS - 1);  // the warp that marched centre row ty + 2
         const float2 g2 = *reinterpret_cast<const float2*>(wreg(tw) + 512 + (ty + 2 - 2 * tw * S) * 12 + slot * 2);
         const float gc = ac + g2.x, gb = ab + g2.y;
