@@ -18,10 +18,11 @@ constexpr int PS_Q = PS_PITCH / 4;             // float4 per staged row
 constexpr int PS_SEGS = WSDL_PS_SEGS;          // row segments per block, one per half warp (even)
 constexpr int PS_THREADS = 16 * PS_SEGS;
 constexpr int PS_WARPS = PS_SEGS / 2;
-// Tile height and residency.  3 CTAs per SM with segments of up to 5 rows (40 centre rows, 67 KB of shared memory,
-// <= 168 registers) beat 4 CTAs with 4-row segments (<= 128 registers) on configs[1]: 22.5 vs 25.5 us per fused launch
-// -- the fixed cost of a block (tile load, conversion, segment heads, loss ticket) is spread over more rows, 224 rows
-// split into 6 blocks of 38 use 93 % of the centre rows instead of 87.5 %, and the packed march needs no spills.
+// Tile height and residency of the single-loss kernels and the tile-streaming kernel.  3 CTAs per SM with segments of
+// up to 5 rows (40 centre rows, 67 KB of shared memory, <= 168 registers) beat 4 CTAs with 4-row segments (<= 128
+// registers) on configs[1] -- the fixed cost of a block (tile load, conversion, segment heads, loss partial) is spread
+// over more rows, 224 rows split into 6 blocks of 38 use 93 % of the centre rows instead of 87.5 %, and the packed march
+// needs no spills.  (The fused kernel has 6-row segments: its own constants, DU_*, in pairwise_sym.cu.)
 #ifndef WSDL_PS_SMAX
 #define WSDL_PS_SMAX 5
 #endif
@@ -581,7 +582,7 @@ __device__ __forceinline__ void ps_rows_transform(const PsParams& Q, const PsBlk
   const int t_top = min(r1, 2 - K.ys), t_bot = max(r0, H - K.ys + 2);  // rows [r0, t_top) and [t_bot, r1) lie outside
   if (cl > 0 || cr < PS_PITCH || t_top > r0 || t_bot < r1) {
     __syncwarp();
-    for (int t = r0 + lane; t < r1; t += 32) {  // a lane per row (a warp converts at most 12)
+    for (int t = r0 + lane; t < r1; t += 32) {  // a lane per row (a warp converts at most 14)
       for (int x = 0; x < cl; ++x) s_img[t * PS_PITCH + x] = PS_SENTINEL;
       for (int x = cr; x < PS_PITCH; ++x) s_img[t * PS_PITCH + x] = PS_SENTINEL;
     }

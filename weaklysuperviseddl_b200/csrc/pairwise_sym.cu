@@ -21,7 +21,7 @@
 // to the 2 columns either side of its strip go to the neighbouring lanes by warp shuffle when a row completes.
 // 16 strips (a half warp) span the 64 staged columns of a tile (60 owned + 2 halo each side), 8 segments span the
 // block's rows; the first two rows of a segment are completed by what its upper neighbour adds to them, through
-// shared memory after the march.  A CTA is one block: up to PS_CAP = 38 rows of one 60-column tile of one image (grid = row blocks x
+// shared memory after the march.  A CTA is one block: up to PS_CAP = 38 rows (fused kernel: 46) of one 60-column tile of one image (grid = row blocks x
 // column tiles x images, a few CTAs per SM slot so that the loads of one overlap the march of the others); it
 // pays 2 warm-up rows instead of a halo in y.
 //
