@@ -62,6 +62,37 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   }
 }
 
+// The tile's union-find lives in shared memory, node = row * 16 + k (raster order, which the root rule needs).  A lane
+// mostly touches its own row's nodes: stored at [node] that is a stride of 16 words, a 16-way bank conflict on every
+// access (ncu: 6.5 M conflicts for 18 M instructions).  Nodes are therefore STORED at k * 32 + row: lanes land in 32
+// different banks; the values (parents) stay node numbers.
+__device__ __forceinline__ int ccl_at(int node) { return ((node & (CCL_RPR - 1)) << 5) | (node >> 4); }
+
+__device__ __forceinline__ int uf_find_s(const int* L, int i) {
+  int p = L[ccl_at(i)];
+  while (p != i) {
+    i = p;
+    p = L[ccl_at(i)];
+  }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union_s(int* L, int a, int b) {
+  while (true) {
+    a = uf_find_s(L, a);
+    b = uf_find_s(L, b);
+    if (a == b) return;
+    if (a < b) {
+      int t = a;
+      a = b;
+      b = t;
+    }  // a > b: hang a under b
+    const int old = atomicMin(L + ccl_at(a), b);
+    if (old == a) return;
+    a = old;  // somebody re-rooted a meanwhile; retry with its new parent
+  }
+}
+
 struct CclTables {
   int* n_roots;            // [tiles] components of the tile | (most runs in one of its rows) << 16
   int* first_pix;          // [tiles][256] raster index (within the image) of the component's first pixel; never changes
@@ -153,7 +184,7 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
   const unsigned st = m & ~(m << 1), ust = up & ~(up << 1);  // run starts
   const int nr = __popc(st);
   const int maxruns = __reduce_max_sync(0xffffffffu, nr);
-  for (int k = 0; k < nr; ++k) par[lane * CCL_RPR + k] = lane * CCL_RPR + k, cnt[lane * CCL_RPR + k] = 0u;
+  for (int k = 0; k < nr; ++k) par[k * CT + lane] = lane * CCL_RPR + k, cnt[k * CT + lane] = 0u;  // ccl_at(node)
   if (lane == 0) s_n[warp] = 0;
   __syncwarp();
   {  // A run joins every run of the row above that has a pixel under its span widened by one column either side.  The
@@ -166,7 +197,7 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
       int len;
       const unsigned R = ccl_run(m, a, &len);
       const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
-      if (touched) par[lane * CCL_RPR + k] = (lane - 1) * CCL_RPR + ccl_run_of(ust, __ffs(touched) - 1);
+      if (touched) par[k * CT + lane] = (lane - 1) * CCL_RPR + ccl_run_of(ust, __ffs(touched) - 1);
     }
   }
   __syncwarp();
@@ -185,7 +216,7 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
         while (ts) {
           const int p = __ffs(ts) - 1;
           ts &= ts - 1u;
-          uf_union(par, first, (lane - 1) * CCL_RPR + ccl_run_of(ust, p));
+          uf_union_s(par, first, (lane - 1) * CCL_RPR + ccl_run_of(ust, p));
         }
       }
     }
@@ -195,8 +226,8 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
 #pragma unroll 1
   for (int round = 0; round < 5; ++round) {
     for (int k = 0; k < nr; ++k) {
-      const int i = lane * CCL_RPR + k;
-      par[i] = par[par[i]];
+      const int i = k * CT + lane;
+      par[i] = par[ccl_at(par[i])];
     }
     __syncwarp();
   }
@@ -208,15 +239,15 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
       int len;
       ccl_run(m, a, &len);
       const int i = lane * CCL_RPR + k;
-      const int r = uf_find(par, i);
-      atomicAdd(&cnt[r], (unsigned)len);
+      const int r = uf_find_s(par, i);
+      atomicAdd(&cnt[ccl_at(r)], (unsigned)len);
       if (r == i) {  // the root is the component's first run in raster order (unions hang the larger node under the smaller)
         const int c = atomicAdd(&s_n[warp], 1);
         s_root[warp][c] = (unsigned short)i;
         s_first[warp][c] = (unsigned short)(lane * CT + a);
-        s_comp[warp][i] = (uint8_t)c;
+        s_comp[warp][ccl_at(i)] = (uint8_t)c;
       } else {
-        par[i] = r;  // roots keep par[r] == r, so concurrent finds stay correct
+        par[k * CT + lane] = r;  // roots keep par[r] == r, so concurrent finds stay correct
       }
     }
   }
@@ -229,22 +260,22 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_tile(const uint8_t* __restric
     const size_t node = tile * CCL_MAXR + c;
     T.first_pix[node] = g;
     T.min_pix[node] = g;
-    T.area[node] = cnt[i];
+    T.area[node] = cnt[ccl_at(i)];
     T.parent[node] = (int)node;
   }
   T.bits[tile * CT + lane] = m;
   for (int k = 0; k < maxruns; ++k)  // par[i] is i's root by now
-    T.runcomp[(tile * CCL_RPR + k) * CT + lane] = k < nr ? s_comp[warp][par[lane * CCL_RPR + k]] : (uint8_t)0;
+    T.runcomp[(tile * CCL_RPR + k) * CT + lane] = k < nr ? s_comp[warp][ccl_at(par[k * CT + lane])] : (uint8_t)0;
   // component numbers of the border pixels: top / bottom row (lane = column), left / right column (lane = row)
   unsigned short* rec = T.border + tile * 128;
   {
     const unsigned m0 = __shfl_sync(0xffffffffu, m, 0), st0 = __shfl_sync(0xffffffffu, st, 0);
     const unsigned m31 = __shfl_sync(0xffffffffu, m, CT - 1), st31 = __shfl_sync(0xffffffffu, st, CT - 1);
-    rec[lane] = (m0 >> lane) & 1u ? (unsigned short)s_comp[warp][par[ccl_run_of(st0, lane)]] : CCL_BG;
+    rec[lane] = (m0 >> lane) & 1u ? (unsigned short)s_comp[warp][ccl_at(par[ccl_at(ccl_run_of(st0, lane))])] : CCL_BG;
     rec[32 + lane] =
-        (m31 >> lane) & 1u ? (unsigned short)s_comp[warp][par[(CT - 1) * CCL_RPR + ccl_run_of(st31, lane)]] : CCL_BG;
-    rec[64 + lane] = m & 1u ? (unsigned short)s_comp[warp][par[lane * CCL_RPR]] : CCL_BG;
-    rec[96 + lane] = m >> 31 ? (unsigned short)s_comp[warp][par[lane * CCL_RPR + nr - 1]] : CCL_BG;
+        (m31 >> lane) & 1u ? (unsigned short)s_comp[warp][ccl_at(par[ccl_at((CT - 1) * CCL_RPR + ccl_run_of(st31, lane))])] : CCL_BG;
+    rec[64 + lane] = m & 1u ? (unsigned short)s_comp[warp][ccl_at(par[lane])] : CCL_BG;
+    rec[96 + lane] = m >> 31 ? (unsigned short)s_comp[warp][ccl_at(par[(nr - 1) * CT + lane])] : CCL_BG;
   }
 }
 
