@@ -295,47 +295,56 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_seams(CclTables T, int tiles_
   int* P = T.parent;
   const unsigned m = T.bits[tile * CT + lane];
   if (!__any_sync(0xffffffffu, m != 0u)) return;  // an empty tile has nothing to join
-  if (tx > 0) {
-    const size_t tl = tile - 1;
-    const unsigned col = __ballot_sync(0xffffffffu, T.bits[tl * CT + lane] >> 31);  // the left tile's right column, bit = row
-    if ((m & 1u) && (col >> (lane ? lane - 1 : 0) & 7u)) {
-      const int me = (int)(tile * CCL_MAXR) + T.border[tile * 128 + 64 + lane];
-      const unsigned short* rl = T.border + tl * 128 + 96;
-      const int base = (int)(tl * CCL_MAXR);
+  // The kernel is a chain of dependent look-ups (ncu: long-scoreboard bound): everything that does not depend on another
+  // load is requested here, in one round trip -- the neighbours' row words, the border records, the corner pixels.
+  const bool has_l = tx > 0, has_u = ty > 0;
+  const size_t tl = tile - 1, tu = tile - tiles_x;
+  const unsigned ml = has_l ? T.bits[tl * CT + lane] : 0u;
+  const unsigned up = has_u ? T.bits[tu * CT + CT - 1] : 0u;
+  const unsigned short my_c0 = T.border[tile * 128 + 64 + lane];                    // component of my column-0 pixel
+  const unsigned short l_c31 = has_l ? T.border[tl * 128 + 96 + lane] : CCL_BG;     // left tile, column 31, my row
+  const unsigned short c_nw = has_u && tx > 0 ? T.border[(tu - 1) * 128 + 32 + CT - 1] : CCL_BG;
+  const unsigned short c_ne = has_u && tx + 1 < tiles_x ? T.border[(tu + 1) * 128 + 32] : CCL_BG;
+  const unsigned cur = __shfl_sync(0xffffffffu, m, 0);
+  const unsigned st = cur & ~(cur << 1), ust = up & ~(up << 1);
+  const bool run_lane = has_u && lane < __popc(st);
+  int a = 0, len = 0, me_up = 0, first_up = -1;
+  unsigned ts = 0u;
+  if (run_lane) {  // second round trip: the component of my run of row 0, and of the first run above it touches
+    a = __fns(st, 0, lane + 1);
+    const unsigned R = ccl_run(cur, a, &len);
+    const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
+    ts = touched & ~(touched << 1);
+    me_up = (int)(tile * CCL_MAXR) + T.runcomp[(tile * CCL_RPR + lane) * CT];
+    if (ts) first_up = (int)(tu * CCL_MAXR) + T.runcomp[(tu * CCL_RPR + ccl_run_of(ust, __ffs(ts) - 1)) * CT + CT - 1];
+  }
+  if (has_l) {  // my column 0 against the left tile's column 31 (rows r-1, r, r+1): the neighbours' records by shuffle
+    const unsigned col = __ballot_sync(0xffffffffu, ml >> 31);
+    const unsigned short l_up = (unsigned short)__shfl_up_sync(0xffffffffu, (unsigned)l_c31, 1);
+    const unsigned short l_dn = (unsigned short)__shfl_down_sync(0xffffffffu, (unsigned)l_c31, 1);
+    if (m & 1u) {
+      const int me = (int)(tile * CCL_MAXR) + my_c0, base = (int)(tl * CCL_MAXR);
       if ((col >> lane) & 1u) {
-        uf_union(P, me, base + rl[lane]);
+        uf_union(P, me, base + l_c31);
       } else {
-        if (lane > 0 && ((col >> (lane - 1)) & 1u)) uf_union(P, me, base + rl[lane - 1]);
-        if (lane < CT - 1 && ((col >> (lane + 1)) & 1u)) uf_union(P, me, base + rl[lane + 1]);
+        if (lane > 0 && ((col >> (lane - 1)) & 1u)) uf_union(P, me, base + l_up);
+        if (lane < CT - 1 && ((col >> (lane + 1)) & 1u)) uf_union(P, me, base + l_dn);
       }
     }
   }
-  if (ty > 0) {
-    const size_t tu = tile - tiles_x;
-    const unsigned cur = __shfl_sync(0xffffffffu, m, 0);
-    const unsigned up = T.bits[tu * CT + CT - 1];
-    const unsigned st = cur & ~(cur << 1), ust = up & ~(up << 1);
-    if (lane < __popc(st)) {
-      const int a = __fns(st, 0, lane + 1);  // start of my run
-      int len;
-      const unsigned R = ccl_run(cur, a, &len);
-      const int me = (int)(tile * CCL_MAXR) + T.runcomp[(tile * CCL_RPR + lane) * CT];
-      const unsigned touched = (R | (R << 1) | (R >> 1)) & up;
-      unsigned ts = touched & ~(touched << 1);
+  if (run_lane) {  // my run of row 0 against the runs of the row above
+    if (ts) {
+      uf_union(P, me_up, first_up);
+      ts &= ts - 1u;
       while (ts) {
         const int p = __ffs(ts) - 1;
         ts &= ts - 1u;
-        uf_union(P, me, (int)(tu * CCL_MAXR) + T.runcomp[(tu * CCL_RPR + ccl_run_of(ust, p)) * CT + CT - 1]);
-      }
-      if (a == 0 && tx > 0 && !(up & 1u)) {  // (with a pixel straight above, the corner pixel is its row neighbour)
-        const unsigned short v = T.border[(tu - 1) * 128 + 32 + CT - 1];
-        if (v != CCL_BG) uf_union(P, me, (int)((tu - 1) * CCL_MAXR) + v);
-      }
-      if (a + len == CT && tx + 1 < tiles_x && !(up >> 31)) {
-        const unsigned short v = T.border[(tu + 1) * 128 + 32];
-        if (v != CCL_BG) uf_union(P, me, (int)((tu + 1) * CCL_MAXR) + v);
+        uf_union(P, me_up, (int)(tu * CCL_MAXR) + T.runcomp[(tu * CCL_RPR + ccl_run_of(ust, p)) * CT + CT - 1]);
       }
     }
+    // (with a pixel straight above, the corner pixel is its row neighbour)
+    if (a == 0 && c_nw != CCL_BG && !(up & 1u)) uf_union(P, me_up, (int)((tu - 1) * CCL_MAXR) + c_nw);
+    if (a + len == CT && c_ne != CCL_BG && !(up >> 31)) uf_union(P, me_up, (int)((tu + 1) * CCL_MAXR) + c_ne);
   }
 }
 
