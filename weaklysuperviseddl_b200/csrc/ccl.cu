@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_select(uint8_t* __restrict__ 
   if (tx >= tiles_x) return;
   const size_t tile = ((size_t)b * tiles_y + ty) * tiles_x + tx;
   const int nn = T.n_roots[tile], n = nn & 0xffff;
+  const unsigned m = T.bits[tile * CT + lane];  // requested with the table look-ups, not after them
   bool mine_any = false, mine_all = true;
   for (int c = lane; c < n; c += 32) {
     const int node = (int)(tile * CCL_MAXR + c);
@@ -426,7 +427,6 @@ __global__ void __launch_bounds__(CCL_THREADS) ccl_select(uint8_t* __restrict__ 
   const bool any = __any_sync(0xffffffffu, mine_any), all = __all_sync(0xffffffffu, mine_all);
   unsigned keep = 0u;  // the bits of my row that belong to the winner
   if (any) {           // (most tiles of a blobby mask hold no part of the winner, or nothing else)
-    const unsigned m = T.bits[tile * CT + lane];
     if (all) {
       keep = m;
     } else {
