@@ -600,7 +600,8 @@ __global__ void __launch_bounds__(LC_THREADS) layercam_cluster_kernel(const __gr
         mn = fminf(mn, x[q]), mx = fmaxf(mx, x[q]);
       }
     }
-    cluster.sync();  // (leaders and non-leaders meet here: the peers' partial maps have been read)
+    // (no cluster barrier here: the peers do nothing but wait for the finished maps, and a leader thread overwrites only
+    // the entries of its own partial map that it has read itself)
     MinMax mm = block_minmax(mn, mx, s_red);
     const float den = (mm.mx - mm.mn) + 1e-8f;  // max is taken after the subtraction in the reference
     if (P.alpha_mode == 0) {
@@ -627,10 +628,8 @@ __global__ void __launch_bounds__(LC_THREADS) layercam_cluster_kernel(const __gr
         if (i < hw) s_part[i] = __fdiv_rn(x[q] - m2.mn, den2);
       }
     }
-  } else {
-    cluster.sync();
   }
-  cluster.sync();  // the leaders hold the finished maps
+  cluster.sync();  // the leaders hold the finished maps (and have read every peer's partial map)
 
   // ---- every CTA takes a copy of all maps of the image ----
 #pragma unroll
