@@ -51,6 +51,11 @@ struct PsParams {
   float l32, l1g;   // log2(3/2), log2(1 + gamma^4): row-border pair multiplicities as exponent offsets
   unsigned* slots;  // single-loss kernels: one loss partial per CTA (a float's bits), 0xffffffff when empty
   float kappa4;     // (float)(4 kappa): rounded on the host (no double-precision arithmetic in the CTAs' prologue)
+  // single-loss kernels: weight tables of the band-column pass (ps_band_tables1, H >= 10), as PsDual's but for one loss.
+  // fx1 [6 slots][2][4]: partner-column offset, 1/2 Wx(a->b), 1/2 Wx(b->a), 1/2 gamma^dx^2; wy1 [11][5][4]: forward,
+  // backward and applied-by-the-march row weights of the row-band rows 0..4, H-5..H-1 and of any other row.
+  float fx1[6 * 2 * 4];
+  float wy1[11 * 5 * 4];
 };
 
 constexpr float PS_SENTINEL = 1e15f;  // staged colour (channel 0) of positions outside the image: 2^-(1e30) = 0
@@ -607,7 +612,7 @@ struct PsCfg {
   static constexpr int CS = (C == 2 && SOFTMAX) ? 1 : C;  // accumulated channels
   static constexpr int CTAS = WSDL_PS_CTAS;               // resident CTAs per SM (<= 128 registers per thread)
   static constexpr size_t smem_floats =
-      (size_t)(3 + C) * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 10;
+      (size_t)(3 + C) * PS_PLANE + (size_t)(PS_SEGS - 1) * 2 * CS * 64 + 6 * (size_t)CS * PS_CAP + 6 * 2 * 4 + 11 * 5 * 4 + 4;
 };
 
 // =====================================================================================================
@@ -646,6 +651,46 @@ struct PsDual {
 };
 
 // (H >= 10: the row bands of the two image borders do not overlap)
+inline void ps_band_tables1(PsParams& Q, int H, int W) {
+  const float g1 = Q.g1, g4 = Q.g4;
+  for (int slot = 0; slot < 6; ++slot) {
+    float w[10];
+    const int x = slot < 3 ? slot : W - 6 + slot;
+    for (int r = 0; r < 10; ++r) {
+      const int xb = x + r % 5 - 2;
+      w[r] = (xb < 0 || xb >= W) ? 0.f : (r < 5 ? ps_w1d(x, xb, W, g1, g4) : ps_w1d(xb, x, W, g1, g4));
+    }
+    for (int u = 0; u < 2; ++u) {
+      int found = -1, cnt = 0;
+      for (int j = 0; j < 5; ++j) {
+        const float g = ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
+        if (w[j] != 0.f && (w[j] != g || w[5 + j] != g)) {
+          if (cnt == u) found = j;
+          ++cnt;
+        }
+      }
+      const int j = found < 0 ? 2 : found;  // no such column: the pixel's own, weight 0
+      const float live = found < 0 ? 0.f : 0.5f;
+      float* fx = Q.fx1 + (slot * 2 + u) * 4;
+      memcpy(&fx[0], &j, sizeof(int));
+      fx[1] = live * w[j], fx[2] = live * w[5 + j], fx[3] = live * ps_gpow(j < 2 ? 2 - j : j - 2, g1, g4);
+    }
+  }
+  for (int rs = 0; rs < 11; ++rs)
+    for (int i = 0; i < 5; ++i) {
+      const float g = ps_gpow(i < 2 ? 2 - i : i - 2, g1, g4);
+      float* w = Q.wy1 + (rs * 5 + i) * 4;
+      w[0] = g, w[1] = g, w[2] = 2.f * g, w[3] = 0.f;
+      if (rs < 10) {
+        const int zy = rs < 5 ? rs : H - 10 + rs, yb = zy + i - 2;
+        const bool in = yb >= 0 && yb < H;
+        w[0] = in ? ps_w1d(zy, yb, H, g1, g4) : 0.f;
+        w[1] = in ? ps_w1d(yb, zy, H, g1, g4) : 0.f;
+        w[2] = in ? 2.f * g * ps_row_mult(zy, yb, H, g4) : 0.f;
+      }
+    }
+}
+
 inline void ps_band_tables(PsDual& D, int H, int W) {
   for (int slot = 0; slot < 6; ++slot) {
     float wc[10], wb[10];

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
   float* s_p = s_img + 3 * PS_PLANE;                      // [C][PS_ROWS][PS_PITCH]: raw values, then probabilities
   float* s_head = s_p + C * PS_PLANE;                     // [7][2][CS][64]: G of the first two rows of segments 1..7
   float* s_gband = s_head + (PS_SEGS - 1) * 2 * CS * 64;  // [6][CS][PS_CAP]: G of the band-column pixels
-  float* s_wx = s_gband + 6 * CS * PS_CAP;                // [6][2][5]: column weights of the 6 band slots
+  float* s_wx = s_gband + 6 * CS * PS_CAP;                // H >= 10: the band tables fx1 | wy1 (268 floats); else [6][2][5]
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ float s_red[PS_THREADS / 32];
   __shared__ double s_dred[PS_THREADS / 32];
@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
     if (col >= 2 && col < 2 + PS_TW && K.x0 - 2 + col < W) okmask |= 1 << j;
   }
   float lsum = 0.f;
-  if (K.xband && tid >= 64 && tid < 124) {  // column weights of the band slots: Wx(x -> x + j - 2), Wx(x + j - 2 -> x)
+  if (K.xband && H >= 10) {  // the band pass's weight tables, built on the host once per launch
+    for (int i = tid; i < 48 + 220; i += PS_THREADS) s_wx[i] = i < 48 ? Q.fx1[i] : Q.wy1[i - 48];
+  } else if (K.xband && tid >= 64 && tid < 124) {  // tiny images: column weights Wx(x -> x + j - 2), Wx(x + j - 2 -> x)
     const int e = tid - 64, slot = e / 10, rem = e - slot * 10, j = rem % 5;
     const int x = slot < 3 ? slot : W - 6 + slot, xb = x + j - 2;
     float w = 0.f;
@@ -344,7 +346,31 @@ __global__ void __launch_bounds__(PS_THREADS, PsCfg<C, SOFTMAX>::CTAS)
       const int x = k < nlo ? K.x0 + k : hi0 + (k - nlo), y = K.ys + ty;
       const int slot = ps_band_slot(x, W);
       float acc[CS], pz[CS], o[C];
-      ps_xfix_item<CS>(H, Q.g1, Q.g4, 1.f, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, acc, pz);
+      if (H >= 10) {
+        // (true pair weight - weight the march applied) / 2 * k (p(a) - p(b)) over the five rows of the pixel's two
+        // special partner columns; column and row weights from the tables
+        const int so = (ty + 2) * PS_PITCH + (x - (K.x0 - 4));
+        const float i0 = s_img[so], i1 = s_img[PS_PLANE + so], i2 = s_img[2 * PS_PLANE + so];
+#pragma unroll
+        for (int c = 0; c < CS; ++c) pz[c] = s_p[c * PS_PLANE + so], acc[c] = 0.f;
+        const float* wy = s_wx + 48 + (y < 5 ? y : (y > H - 6 ? y - (H - 10) : 10)) * 20;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 fx = *reinterpret_cast<const float4*>(s_wx + (slot * 2 + u) * 4);
+          const int sj = so + __float_as_int(fx.x) - 2;
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const float4 w = *reinterpret_cast<const float4*>(wy + r * 4);
+            const int sn = sj + (r - 2) * PS_PITCH;  // rows outside the image: weights 0, the staged values are finite
+            const float d0 = i0 - s_img[sn], d1 = i1 - s_img[PS_PLANE + sn], d2 = i2 - s_img[2 * PS_PLANE + sn];
+            const float kk = fmaf(w.x, fx.y, fmaf(w.y, fx.z, -fx.w * w.z)) * ex2_approx(fmaf(-d2, d2, fmaf(-d1, d1, -d0 * d0)));
+#pragma unroll
+            for (int c = 0; c < CS; ++c) acc[c] = fmaf(kk, pz[c] - s_p[c * PS_PLANE + sn], acc[c]);
+          }
+        }
+      } else {
+        ps_xfix_item<CS>(H, Q.g1, Q.g4, 1.f, s_img, s_p, s_wx + slot * 10, K.ys, K.x0, y, x, acc, pz);
+      }
       lsum += ps_pixel_grad<C, CS, SOFTMAX>(K.scale2, pz, acc, o);  // the loss is linear in G: add the correction's share
       if (Q.p.grad_values) {
 #pragma unroll
@@ -930,6 +956,8 @@ int ps_launch(const PwParams& P, cudaStream_t s) {
   Q.img_scale = sqrtf(-P.kc);
   Q.g1 = expf(-P.inv_2ss), Q.g4 = expf(-4.f * P.inv_2ss);
   Q.l32 = log2f(1.5f), Q.l1g = log2f(1.f + Q.g4);
+  if (P.H >= 10) ps_band_tables1(Q, P.H, P.W);
+  else memset(Q.fx1, 0, sizeof(Q.fx1)), memset(Q.wy1, 0, sizeof(Q.wy1));
   {  // a sixteenth of a wave of tiles at ~6 TB/s (a longer hold-back helps a lone launch by 2-3 % and costs launches
      // that overlap on the device 4 %); only when the launch fills the machine
     static const int stagger_env = WSDL_TUNE_INT("WSDL_PS_STAGGER_NS", -1);
@@ -959,6 +987,7 @@ int ps_launch_dual(const PwParams& P, float sigma_cut, float sigma_bnd, float si
   Q.n_x = (P.W + PS_TW - 1) / PS_TW;
   Q.slots = nullptr;
   Q.kappa4 = (float)(4.0 * P.kappa);
+  memset(Q.fx1, 0, sizeof(Q.fx1)), memset(Q.wy1, 0, sizeof(Q.wy1));
   Q.nb = ps_row_blocks(P.B, P.H, P.W, DU_CAP);
   if (Q.nb > 65535 || Q.n_x > 65535 || P.B > 65535) return 1;
   const int n_max = (P.H + Q.nb - 1) / Q.nb;
