@@ -115,7 +115,8 @@ int wsdl_pairwise_fwd_bwd(const float* values, const float* images, int B, int C
 
 /* The same call for a PREPARED workspace: one that wsdl_pairwise_workspace_init() has initialised once (it zeroes the
  * 512-byte control block and marks the per-CTA result slots behind it "empty" -- all ones; a zero-filled buffer is NOT
- * a prepared workspace) and that has since only been used by complete pairwise calls ordered on one stream.
+ * a prepared workspace) and that has since only been used by complete pairwise calls of ONE problem shape (B, H, W: the
+ * regions inside a workspace are laid out per shape) ordered on one stream.
  * Every pairwise kernel leaves the workspace prepared again, so the per-call memsets of wsdl_pairwise_fwd_bwd (extra
  * nodes per call in a CUDA graph) are not needed.  A workspace must not be shared by calls that may run concurrently. */
 int wsdl_pairwise_workspace_init(void* workspace, size_t workspace_bytes, void* stream);

@@ -355,6 +355,32 @@ def test_repeatability_stress(WF):
     torch.cuda.synchronize()
 
 
+def test_prepared_workspaces_survive_interleaved_kernels_and_shapes(WF):
+    """The functional layer caches prepared workspaces.  Calls that take different kernels (pair-symmetric: window 5;
+    generic: window 3 / three classes) and different shapes, interleaved on one stream, must each reproduce what they
+    returned the first time: no kernel may find another call's partials where it expects its own empty result slots."""
+    gen = torch.Generator().manual_seed(321)
+    cases = []
+    for (B, C, H, W_, window) in [(2, 2, 64, 64, 5), (2, 2, 64, 64, 3), (1, 3, 64, 64, 5), (3, 2, 40, 96, 5),
+                                  (3, 2, 40, 96, 3), (1, 2, 224, 224, 5), (2, 2, 64, 64, 7)]:
+        vals = torch.randn(B, C, H, W_, generator=gen).cuda()
+        img = smooth_images(gen, B, H, W_).cuda()
+        cases.append((vals, img, window))
+    first = {}
+    for rep in range(3):
+        for i, (vals, img, window) in enumerate(cases):
+            out = WF.pairwise_loss_and_grad(vals, img, window, 0.05, None, True, True, False)
+            outs = [t.clone() for t in out]
+            if vals.shape[1] == 2 and window == 5:
+                outs += [t.clone() for t in WF.pairwise_dual_loss_and_grad(vals, img)]
+            if i in first:
+                for a, b in zip(first[i], outs):
+                    assert torch.equal(a, b), (i, rep)
+            else:
+                first[i] = outs
+    torch.cuda.synchronize()
+
+
 def _eager_pair_loss(p, img, sigma_color, sigma_space, mean_over_classes):
     """The reference's formula with plain torch ops, any device / dtype: 24 reflect-shifted copies."""
     import torch.nn.functional as F

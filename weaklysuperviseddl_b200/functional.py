@@ -143,19 +143,20 @@ def _upstream(t: Optional[torch.Tensor], n: int, dev, name: str) -> Optional[int
     return t.data_ptr()
 
 
-_PAIR_WS = {}  # (device index, stream, bytes) -> prepared workspace (wsdl_pairwise_workspace_init, then self-cleaning)
+_PAIR_WS = {}  # (device index, stream, bytes, shape) -> prepared workspace (wsdl_pairwise_workspace_init, then self-cleaning)
 
 
-def _pairwise_workspace(lib, dev, nbytes: int) -> torch.Tensor:
-    """One prepared workspace per device, stream and size: calls on one stream are ordered, so they can share it;
-    it is initialised once and every kernel leaves it initialised (no per-call memset, no per-call allocation)."""
+def _pairwise_workspace(lib, dev, nbytes: int, shape=None) -> torch.Tensor:
+    """One prepared workspace per device, stream, size and problem shape: calls on one stream are ordered, so they can
+    share it; it is initialised once and every kernel leaves it initialised (no per-call memset, no per-call
+    allocation).  The shape is part of the key because the regions inside a workspace are laid out per (B, H, W)."""
     stream = _stream_ptr(dev)
     if torch.cuda.is_current_stream_capturing():
         # memory allocated while a CUDA graph is being captured belongs to the graph's pool: do not cache it
         ws = torch.empty(max(nbytes, 512), dtype=torch.uint8, device=dev)
         _native.check(lib.wsdl_pairwise_workspace_init(ws.data_ptr(), ws.numel(), stream), "wsdl_pairwise_workspace_init")
         return ws
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, nbytes)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, nbytes, shape)
     ws = _PAIR_WS.get(key)
     if ws is None:
         if len(_PAIR_WS) > 64:
@@ -173,7 +174,7 @@ def _pairwise_raw(values, images, window, sigma_color, sigma_space, inner_softma
     lib = _native.lib()
     with torch.cuda.device(dev):
         nbytes = lib.wsdl_pairwise_workspace_bytes(B, H, W)
-        workspace = _pairwise_workspace(lib, dev, nbytes)
+        workspace = _pairwise_workspace(lib, dev, nbytes, ("single", B, H, W))
         loss = torch.empty(B if per_image else 1, dtype=torch.float32, device=dev)
         grad = torch.empty_like(values) if want_grad else None
         rc = lib.wsdl_pairwise_fwd_bwd_prepared(
@@ -363,7 +364,7 @@ def pairwise_dual_loss_and_grad(logits, images, sigma_cut=0.05, sigma_boundary=0
     lib = _native.lib()
     with torch.cuda.device(dev):
         nbytes = lib.wsdl_pairwise_dual_workspace_bytes(B, H, W)
-        workspace = _pairwise_workspace(lib, dev, nbytes)
+        workspace = _pairwise_workspace(lib, dev, nbytes, ("dual", B, H, W))
         loss_cut = torch.empty(1, dtype=torch.float32, device=dev)
         loss_bnd = torch.empty(B, dtype=torch.float32, device=dev)
         grad = torch.empty_like(v) if want_grad else None
@@ -455,7 +456,7 @@ def weak_loss_and_grad(logits, images, labels=None, lam_ce=1.0, grad_out_cut=Non
     lib = _native.lib()
     with torch.cuda.device(dev):
         nbytes = lib.wsdl_weak_loss_workspace_bytes(B, H, W)
-        workspace = _pairwise_workspace(lib, dev, nbytes)
+        workspace = _pairwise_workspace(lib, dev, nbytes, ("weak", B, H, W))
         if packed_out is None:
             out = torch.empty(3 + B, dtype=torch.float32, device=dev)  # total, ce, cut, bnd[B]
         else:
